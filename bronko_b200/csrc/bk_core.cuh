@@ -1,0 +1,308 @@
+// bk_core.cuh — the per-read / per-k-mer logic of the counting stage, written once and compiled
+// (a) by nvcc into the sm_100a kernels of bk_device.cu and (b) by g++ into tests/emul (a tests-only
+// shared object that steps the same code on the CPU so the logic can be checked without a GPU; the
+// product library never contains or calls a host build of this file).
+//
+// Counting replaces the KMC3 subprocess (reference src/call.rs:1152-1226; contract in SURVEY.md
+// Appendix B): exact counts of non-canonical k-mers, reads split at non-ACGT symbols.
+//
+// Design: a read is seeded with ONE exact lookup of its first k-mer in the table of
+// reference k-mers, then compared 32 bases at a time against the 2-bit packed oriented reference.
+// Every run of consecutive k-mers that equal consecutive reference k-mers is counted with two
+// atomics on a difference array (+1 at the first raw slot, -1 after the last); a prefix sum gives
+// per-slot counts later.  K-mers that do not extend (sequencing errors, variants, foreign reads) are
+// queued as (byte offset, count) stretches and counted one by one in the leftover kernel: exact
+// reference k-mer → difference array, otherwise → open-addressing table of novel k-mers.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BK_HD __device__ __forceinline__
+#define BK_CLZLL(x) __clzll((long long)(x))
+#define BK_POPCLL(x) __popcll((unsigned long long)(x))
+#else
+#define BK_HD static inline
+#define BK_CLZLL(x) __builtin_clzll((unsigned long long)(x))
+#define BK_POPCLL(x) __builtin_popcountll((unsigned long long)(x))
+struct uint2 { unsigned int x, y; };
+static inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 r; r.x = x; r.y = y; return r; }
+#endif
+
+namespace bk {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef uint8_t u8;
+
+static const u64 BK_EMPTY = ~0ull;
+
+struct GenSlot { u64 key; u32 cnt; u32 pad; };         // novel k-mer table slot, 16 B
+struct ExactSlotD { u64 key; u32 gidx; u32 oseq; };    // reference k-mer table slot, 16 B
+
+BK_HD u32 hash_slot(u64 x, u32 shift) { return (u32)(((x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull) >> shift); }
+
+// --- 4 ASCII bases (one little-endian u32, first base in the low byte) → 8 packed bits, first base
+// in the two high bits, code A=0 C=1 G=2 T=3 (reference src/lcb.rs:47-55, lower case accepted);
+// *err != 0 iff some byte is not one of ACGTacgt.
+BK_HD u32 pack4(u32 w, u32* err) {
+    const u32 u = w & 0xDFDFDFDFu;
+    const u32 a = u >> 1, b = u >> 2, c = u >> 4;
+    const u32 y = (a ^ b) & 0x03030303u;
+    const u32 e1 = c ^ (b & ~a);
+    const u32 e2 = e1 | ~(u ^ c);
+    *err = (e2 & 0x01010101u) | ((u ^ 0x40404040u) & 0xC8C8C8C8u);
+    return (y * 0x40100401u) >> 24;
+}
+
+// Word source: aligned u32 words of the ASCII base buffer (shared-memory tile or global memory).
+// ld(i) returns word i of the buffer the byte offsets refer to.
+template <class Ld>
+BK_HD u32 load_unaligned(const Ld& ld, u32 byte_off) {
+    const u32 wi = byte_off >> 2, sh = (byte_off & 3) * 8;
+    const u32 lo = ld(wi);
+    if (sh == 0) return lo;
+    const u32 hi = ld(wi + 1);
+    return (lo >> sh) | (hi << (32 - sh));
+}
+
+// 32 bases starting at byte_off (nb = how many of them belong to the read, 1..32) → 64 packed bits
+// MSB-first; *bad != 0 iff one of the nb bytes is not ACGT.  Bits of bases >= nb are zero.
+template <class Ld>
+BK_HD u64 pack32(const Ld& ld, u32 byte_off, u32 nb, u32* bad) {
+    const u32 wi = byte_off >> 2, sh = (byte_off & 3) * 8;
+    u32 prev = ld(wi);
+    u32 hi32 = 0, lo32 = 0, acc = 0;
+    const u32 nwords = (nb + 3) >> 2;
+#pragma unroll
+    for (u32 i = 0; i < 8; i++) {
+        u32 w = 0;
+        if (i < nwords) {
+            if (sh) { const u32 nxt = ld(wi + i + 1); w = (prev >> sh) | (nxt << (32 - sh)); prev = nxt; }
+            else { w = prev; prev = ld(wi + i + 1); }
+        }
+        u32 err;
+        u32 p = pack4(w, &err);
+        if (nb < 32) {                     // tail word: ignore bytes past the end of the read
+            const i32 vb = (i32)nb - (i32)(4 * i);
+            if (vb <= 0) { err = 0; p = 0; }
+            else if (vb < 4) { err &= (1u << (8 * vb)) - 1u; p &= 0xFFu << (8 - 2 * vb); }
+        }
+        acc |= err;
+        if (i < 4) hi32 |= p << (24 - 8 * i); else lo32 |= p << (56 - 8 * i);
+    }
+    *bad = acc;
+    return ((u64)hi32 << 32) | lo32;
+}
+
+// k bases starting at byte_off → k-mer value (first base most significant, src/lcb.rs:67-74);
+// returns false if a byte is not ACGT.
+template <class Ld>
+BK_HD bool pack_kmer(const Ld& ld, u32 byte_off, u32 k, u64* out) {
+    u32 bad;
+    const u64 v = pack32(ld, byte_off, k, &bad);
+    *out = v >> (64 - 2 * k);
+    return bad == 0;
+}
+
+// 64 bits of the packed oriented reference starting at global base index g (may be out of range:
+// clamped; the caller masks those bases out).
+template <class LdRef>
+BK_HD u64 ref_word(const LdRef& ldr, i32 g, u32 n_words) {
+    i32 wi = g >> 5;
+    const u32 sh = 2 * (u32)(g & 31);
+    if (wi < 0) wi = 0;
+    if (wi > (i32)n_words - 2) wi = (i32)n_words - 2;
+    const u64 a = ldr((u32)wi);
+    if (sh == 0) return a;
+    const u64 b = ldr((u32)wi + 1);
+    return (a << sh) | (b >> (64 - sh));
+}
+
+// Device-side view of everything the counting stage touches.
+struct CountView {
+    u32 k;
+    const u64* refpk; u32 ref_words;
+    const u32* oseq_start; const u32* oseq_len;
+    const ExactSlotD* exact; u32 exact_shift, exact_mask;
+    u32* diff;                       // n_raw + 2
+    GenSlot* gen; u32 gen_shift, gen_mask;
+    u32* gen_full;                   // set to 1 if the novel table ran out of slots
+    uint2* desc; u32 desc_cap; u32* n_desc;
+};
+
+#if defined(__CUDACC__)
+BK_HD void add_u32(u32* p, u32 v) { atomicAdd(p, v); }
+BK_HD u32 fetch_add_u32(u32* p, u32 v) { return atomicAdd(p, v); }
+BK_HD u64 cas_u64(u64* p, u64 cmp, u64 val) { return atomicCAS((unsigned long long*)p, (unsigned long long)cmp, (unsigned long long)val); }
+BK_HD u64 load_key(const u64* p) { return *(const volatile u64*)p; }
+BK_HD ExactSlotD load_exact(const ExactSlotD* p) {
+    const uint4 v = __ldg((const uint4*)p);
+    ExactSlotD s; s.key = ((u64)v.y << 32) | v.x; s.gidx = v.z; s.oseq = v.w; return s;
+}
+#else
+BK_HD void add_u32(u32* p, u32 v) { *p += v; }
+BK_HD u32 fetch_add_u32(u32* p, u32 v) { u32 o = *p; *p += v; return o; }
+BK_HD u64 cas_u64(u64* p, u64 cmp, u64 val) { u64 o = *p; if (o == cmp) *p = val; return o; }
+BK_HD u64 load_key(const u64* p) { return *p; }
+BK_HD ExactSlotD load_exact(const ExactSlotD* p) { return *p; }
+#endif
+
+BK_HD bool exact_lookup(const CountView& v, u64 kmer, u32* gidx, u32* oseq) {
+    u32 h = hash_slot(kmer, v.exact_shift);
+    for (;;) {
+        const ExactSlotD s = load_exact(v.exact + h);
+        if (s.key == kmer) { *gidx = s.gidx; *oseq = s.oseq; return true; }
+        if (s.key == BK_EMPTY) return false;
+        h = (h + 1) & v.exact_mask;
+    }
+}
+
+// Count one k-mer occurrence that did not extend a run.  Returns 1 if it created a new novel key.
+BK_HD u32 count_one(const CountView& v, u64 kmer) {
+    u32 gidx, oseq;
+    if (exact_lookup(v, kmer, &gidx, &oseq)) {
+        add_u32(v.diff + gidx, 1u);
+        add_u32(v.diff + gidx + 1, 0xFFFFFFFFu);
+        return 0;
+    }
+    u32 h = hash_slot(kmer, v.gen_shift);
+    for (u32 probe = 0; probe <= v.gen_mask; probe++) {
+        u64 cur = load_key(&v.gen[h].key);
+        if (cur == BK_EMPTY) {
+            cur = cas_u64(&v.gen[h].key, BK_EMPTY, kmer);
+            if (cur == BK_EMPTY) { add_u32(&v.gen[h].cnt, 1u); return 1; }
+        }
+        if (cur == kmer) { add_u32(&v.gen[h].cnt, 1u); return 0; }
+        h = (h + 1) & v.gen_mask;
+    }
+    *v.gen_full = 1;
+    return 0;
+}
+
+// Count the k-mers starting at bytes [byte_off, byte_off+cnt) one at a time, validating every base
+// (k-mers that contain a non-ACGT byte are not counted: KMC splits reads there).  step/first let a
+// warp interleave lanes.  Returns the number of new novel keys.
+template <class Ld>
+BK_HD u32 count_stretch(const CountView& v, const Ld& ld, u32 byte_off, u32 cnt, u32 first, u32 step) {
+    u32 created = 0;
+    for (u32 j = first; j < cnt; j += step) {
+        u64 km;
+        if (pack_kmer(ld, byte_off + j, v.k, &km)) created += count_one(v, km);
+    }
+    return created;
+}
+
+// Leftover stretch: k-mers starting at read bases [a, a+cnt) of the read at byte offset o0.
+template <class Ld>
+BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt) {
+    const u32 slot = fetch_add_u32(v.n_desc, 1u);
+    if (slot < v.desc_cap) { v.desc[slot] = make_uint2(o0 + a, cnt); return 0; }
+    return count_stretch(v, ld, o0 + a, cnt, 0, 1);   // queue full: count in place (slow, still exact)
+}
+
+BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
+    add_u32(v.diff + (u32)(g0 + (i32)a), 1u);
+    add_u32(v.diff + (u32)(g0 + (i32)a) + cnt, 0xFFFFFFFFu);
+}
+
+#ifndef BK_MAX_SEEDS
+#define BK_MAX_SEEDS 4      // seed attempts (spaced k apart) per diagonal search
+#endif
+#ifndef BK_MAX_DIAGS
+#define BK_MAX_DIAGS 3      // diagonals tried per read (re-seed after an indel / wrong diagonal)
+#endif
+#ifndef BK_BAIL_MISMATCHES
+#define BK_BAIL_MISMATCHES 8  // this many bad bases inside one 32-base word ends the diagonal
+#endif
+
+// One read: bytes [o0, o0+len) of the word source.  Returns number of new novel keys created by the
+// in-place fallback (normally 0).
+//
+// State: k-mers are indexed by their start base.  `c` = first k-mer start not classified yet (every
+// k-mer below c has been put in a run or a leftover stretch), `ms` = start of the current stretch of
+// matching bases on the current diagonal.  A bad base at e (mismatch, non-ACGT byte, end of the
+// overlap with the oriented sequence, end of read) closes the stretch [ms, e): if it holds >= k bases
+// its k-mers [ms, e-k] become a run, everything pending before ms a leftover stretch.
+template <class Ld, class LdRef>
+BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len) {
+    const u32 k = v.k;
+    if (len < k) return 0;                       // shorter than k: contributes no k-mer
+    const u32 nk = len - k + 1;
+    u32 created = 0;
+    i32 c = 0;
+    i32 seed_from = 0;
+    for (u32 diag = 0; diag < BK_MAX_DIAGS; diag++) {
+        u32 gidx = 0, oseq = 0, q = (u32)seed_from;
+        bool found = false;
+        for (u32 t = 0; t < BK_MAX_SEEDS && q + k <= len; t++, q += k) {
+            u64 km;
+            if (!pack_kmer(ld, o0 + q, k, &km)) continue;
+            if (exact_lookup(v, km, &gidx, &oseq)) { found = true; break; }
+        }
+        if (!found) break;
+        const i32 g0 = (i32)gidx - (i32)q;       // global base index of read base 0 on this diagonal
+        const i32 os = (i32)v.oseq_start[oseq], oe = os + (i32)v.oseq_len[oseq];
+        i32 i_lo = os > g0 ? os - g0 : 0;                                  // read bases inside the
+        const i32 i_hi = (oe - g0) < (i32)len ? (oe - g0) : (i32)len;      // oriented sequence
+        if (i_lo < seed_from) i_lo = seed_from;
+        i32 ms = i_lo;
+        bool bailed = false;
+#define BK_EVENT(e_)                                                                      \
+    do {                                                                                  \
+        const i32 e__ = (e_);                                                             \
+        if (e__ - ms >= (i32)k) {                                                         \
+            if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c));       \
+            emit_run(v, g0, (u32)ms, (u32)(e__ - (i32)k + 1 - ms));                       \
+            c = e__ - (i32)k + 1;                                                         \
+        }                                                                                 \
+        ms = e__ + 1;                                                                     \
+    } while (0)
+        for (i32 w = i_lo >> 5; 32 * w < i_hi; w++) {
+            const i32 b0 = 32 * w;
+            const u32 nb = (u32)((i32)len - b0 < 32 ? (i32)len - b0 : 32);
+            u32 bad;
+            const u64 rd = pack32(ld, o0 + (u32)b0, nb, &bad);
+            const u64 rf = ref_word(ldr, g0 + b0, v.ref_words);
+            u64 x = rd ^ rf;
+            const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
+            const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
+            u64 mask = ~0ull;
+            if (lo > 0) mask &= ~0ull >> (2 * lo);
+            if (hi < 32) mask &= ~(~0ull >> (2 * hi));
+            x &= mask;
+            if ((x | bad) == 0) continue;        // the common case: 32 bases extend the run
+            u64 t = (x | (x >> 1)) & 0x5555555555555555ull;
+            if (bad) {                           // rare: flag all 4 bases of a word holding a non-ACGT byte
+                for (u32 i = 0; i < 8 && 4 * i < nb; i++) {
+                    u32 err;
+                    const u32 nbi = nb - 4 * i;
+                    const u32 wv = load_unaligned(ld, o0 + (u32)b0 + 4 * i);
+                    (void)pack4(wv, &err);
+                    if (nbi < 4) err &= (1u << (8 * nbi)) - 1u;
+                    if (err) t |= 0x55ull << (56 - 8 * i);
+                }
+                t &= mask;
+            }
+            if (BK_POPCLL(t) >= BK_BAIL_MISMATCHES) {   // wrong diagonal from here on: close and re-seed
+                const u32 p = 63 - (u32)BK_CLZLL(t);
+                const i32 e = b0 + (i32)(31 - (p >> 1));
+                BK_EVENT(e);
+                seed_from = e + 1;
+                bailed = true;
+                break;
+            }
+            while (t) {
+                const u32 p = 63 - (u32)BK_CLZLL(t);
+                t ^= 1ull << p;
+                BK_EVENT(b0 + (i32)(31 - (p >> 1)));
+            }
+        }
+        if (!bailed) { BK_EVENT(i_hi); break; }
+#undef BK_EVENT
+    }
+    if ((i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c);
+    return created;
+}
+
+}  // namespace bk

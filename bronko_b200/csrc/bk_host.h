@@ -1,0 +1,97 @@
+// bk_host.h — host-side structures of libbronko_b200 (index, I/O, derived device tables).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/bronko_b200.h"
+
+namespace bk {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+// ---- the decoded BronkoIndex (src/build.rs:23-60) as flat arrays -----------------------------
+struct HostSeq { std::string name; u64 len; std::vector<u8> bases; };
+struct HostGenome { std::string name; std::vector<HostSeq> seqs; };
+
+struct HostIndex {
+    u32 k = 0;
+    u64 meta_k = 0;
+    std::vector<u64> keys;                 // ascending
+    std::vector<u64> entry_off;            // n_keys + 1
+    std::vector<bk_bucket_info> entries;   // per-key order preserved (file order, then location)
+    std::vector<HostGenome> genomes;
+};
+
+// (bucket id, entry) pair used while building / decoding before the sort by key
+struct KeyedEntry { u64 key; bk_bucket_info e; };
+
+// Sort pairs by key (stable) and fill ix.keys / entry_off / entries.
+void index_from_pairs(HostIndex& ix, std::vector<KeyedEntry>& pairs);
+
+bool bkdb_decode(const u8* data, u64 n, HostIndex& ix, std::string& err);
+bool bkdb_read(const std::string& path, HostIndex& ix, std::string& err);
+bool bkdb_write(const std::string& path, const HostIndex& ix, std::string& err);
+bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIndex& ix, std::string& err);
+
+// lcb.rs primitives (host copies used by the builder)
+void assign_buckets_host(u64 kmer, int k, u64* out);
+u64 revcomp_host(u64 v, int k);
+inline u8 nt_to_bits_host(u8 c) {
+    switch (c) { case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 0; }
+}
+
+// ---- text I/O ------------------------------------------------------------------------------
+struct HostReads { std::vector<u8> bases; std::vector<u32> off; u32 max_len = 0; };
+bool slurp_maybe_gz(const std::string& path, std::string& out);
+// FASTQ(.gz), 4-line records; splits into chunks of at most max_chunk_bases so offsets fit u32.
+bool fastq_read(const std::string& path, std::vector<HostReads>& chunks, u64 max_chunk_bases, std::string& err);
+std::string clean_sample_id(const std::string& path);
+std::string first_token(const std::string& s);
+std::string fmt_fixed(double v, int prec);
+
+// ---- tables derived from the index for the device ------------------------------------------
+struct BucketSlot { u64 key; u32 off; u32 len; };                 // 16 B; key == ~0 → empty
+struct BucketEntry { u32 row; u16 file_id; u8 idx; u8 canonical; }; // 8 B; row = global pileup row of `location`
+struct ExactSlot { u64 key; u32 gidx; u32 oseq; };                // 16 B; key == ~0 → empty
+
+struct DerivedIndex {
+    u32 k = 0, n_genomes = 0, n_seqs = 0;
+    // pileup row space: all sequences of all genomes concatenated
+    std::vector<u32> genome_row0;      // n_genomes + 1
+    std::vector<u32> genome_seq_off;   // n_genomes + 1 (into the flat sequence list)
+    std::vector<u32> seq_row0;         // n_seqs + 1, global row of each sequence
+    std::vector<u64> genome_len;       // n_genomes
+    std::vector<u8> ref_code;          // per row: nt_to_bits(base)
+    u32 max_genome_rows = 0;
+    // bucket-id → entries
+    u32 bucket_log2 = 0;
+    std::vector<BucketSlot> bucket_slots;
+    std::vector<BucketEntry> bucket_entries;
+    // oriented reference store (forward and reverse-complement of every sequence), 2-bit packed,
+    // MSB-first, 32 bases per u64; global base index space with REF_PAD_BASES of padding in front
+    std::vector<u64> refpk;
+    std::vector<u32> oseq_start, oseq_len;   // per oriented sequence, in global base indices
+    u32 n_raw = 0;                           // size of the global base index space (incl. padding)
+    // exact (non-canonical) reference k-mer → one representative raw slot
+    u32 exact_log2 = 0;
+    std::vector<ExactSlot> exact_slots;
+    // raw slot → id of the distinct k-mer string (0xFFFFFFFF for invalid slots); id → k-mer
+    std::vector<u32> slot2id;
+    std::vector<u64> id_kmer;
+};
+
+static const u32 REF_PAD_BASES = 64;
+
+void derive_index(const HostIndex& ix, DerivedIndex& d);
+
+// must match bk::hash_slot in bk_core.cuh (the device probes with the same function)
+inline u32 hash_slot_host(u64 x, u32 shift) { return (u32)(((x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull) >> shift); }
+
+// ---- Student-t / Thompson tau table (call.rs:922-929) --------------------------------------
+void tau_table(double* tab301);   // tab[n] for n in 3..300 (others 0)
+
+}  // namespace bk

@@ -1,0 +1,376 @@
+// bk_host_index.cpp — .bkdb (bincode 2) reader/writer, FASTA reader, the
+// host index builder (build_indexes, reference src/build.rs:145-231) and the tables the device
+// kernels need, derived once per index load.
+#include "bk_host.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <zlib.h>
+
+namespace bk {
+
+// ---------------------------------------------------------------------------------------------
+// lcb.rs primitives, closed form.  u64 arithmetic wraps on purpose: for
+// k = 31 the reference's ids exceed 2^64 and wrap too (release build), src/lcb.rs:8-41.
+// ---------------------------------------------------------------------------------------------
+void assign_buckets_host(u64 kmer, int k, u64* out) {
+    u64 mu[32], val[32], cur[32];
+    u32 zero_before[32];
+    u64 sum_mu = 0;
+    u32 zeros = 0;
+    for (int i = 0; i < k; i++) {
+        const int sh = 2 * (k - 1 - i);
+        const u64 w = 1ull << sh;
+        const u64 d = (kmer >> sh) & 3;
+        cur[i] = d << sh;
+        val[i] = kmer & (w - 1);
+        mu[i] = d ? w + (cur[i] >> 2) * (u64)(k - 1 - i) : val[i];
+        zero_before[i] = zeros;
+        zeros += (d == 0);
+        sum_mu += mu[i];
+    }
+    for (int i = 0; i < k; i++)
+        out[i] = sum_mu - mu[i] + val[i] - (u64)zero_before[i] * cur[i] + 1 + zero_before[i];
+}
+
+u64 revcomp_host(u64 v, int k) {
+    u64 x = ~v;
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = __builtin_bswap64(x);
+    return x >> (64 - 2 * k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bincode varint
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cursor {
+    const u8* p; const u8* end; bool ok;
+    u8 byte() { if (p >= end) { ok = false; return 0; } return *p++; }
+    u64 varint() {
+        u8 t = byte();
+        if (t < 251) return t;
+        int n = t == 251 ? 2 : t == 252 ? 4 : t == 253 ? 8 : 0;
+        if (!n) { ok = false; return 0; }
+        if (end - p < n) { ok = false; return 0; }
+        u64 v = 0;
+        memcpy(&v, p, n);   // little endian host
+        p += n;
+        return v;
+    }
+    bool bytes(u64 n, const u8** out) {
+        if ((u64)(end - p) < n) { ok = false; return false; }
+        *out = p; p += n; return true;
+    }
+};
+struct Sink {
+    std::vector<u8> buf;
+    void byte(u8 b) { buf.push_back(b); }
+    void varint(u64 v) {
+        if (v < 251) { buf.push_back((u8)v); return; }
+        int n = v <= 0xFFFFull ? 2 : v <= 0xFFFFFFFFull ? 4 : 8;
+        buf.push_back(n == 2 ? 251 : n == 4 ? 252 : 253);
+        for (int i = 0; i < n; i++) buf.push_back((u8)(v >> (8 * i)));
+    }
+    void blob(const void* p, u64 n) { varint(n); buf.insert(buf.end(), (const u8*)p, (const u8*)p + n); }
+};
+}  // namespace
+
+void index_from_pairs(HostIndex& ix, std::vector<KeyedEntry>& pairs) {
+    std::stable_sort(pairs.begin(), pairs.end(), [](const KeyedEntry& a, const KeyedEntry& b) { return a.key < b.key; });
+    ix.keys.clear(); ix.entry_off.clear(); ix.entries.clear();
+    ix.entries.reserve(pairs.size());
+    for (size_t i = 0; i < pairs.size(); i++) {
+        if (i == 0 || pairs[i].key != pairs[i - 1].key) { ix.keys.push_back(pairs[i].key); ix.entry_off.push_back(i); }
+        ix.entries.push_back(pairs[i].e);
+    }
+    ix.entry_off.push_back(pairs.size());
+}
+
+bool bkdb_decode(const u8* data, u64 n, HostIndex& ix, std::string& err) {
+    Cursor c{data, data + n, true};
+    ix = HostIndex();
+    ix.k = (u32)c.varint();
+    const u64 n_keys = c.varint();
+    std::vector<KeyedEntry> pairs;
+    pairs.reserve(n_keys + n_keys / 8);
+    for (u64 i = 0; i < n_keys && c.ok; i++) {
+        const u64 key = c.varint();
+        const u64 m = c.varint();
+        for (u64 j = 0; j < m && c.ok; j++) {
+            KeyedEntry ke; memset(&ke, 0, sizeof ke);
+            ke.key = key;
+            ke.e.file_id = (u16)c.varint();
+            ke.e.seq_id = c.byte();
+            ke.e.location = (u32)c.varint();
+            ke.e.idx = c.byte();
+            ke.e.canonical = c.byte();
+            pairs.push_back(ke);
+        }
+    }
+    const u64 n_files = c.varint();
+    for (u64 f = 0; f < n_files && c.ok; f++) {
+        HostGenome g;
+        const u8* s; u64 len = c.varint();
+        if (!c.bytes(len, &s)) break;
+        g.name.assign((const char*)s, len);
+        const u64 n_seq = c.varint();
+        for (u64 q = 0; q < n_seq && c.ok; q++) {
+            HostSeq hs;
+            len = c.varint();
+            if (!c.bytes(len, &s)) break;
+            hs.name.assign((const char*)s, len);
+            hs.len = c.varint();
+            len = c.varint();
+            if (!c.bytes(len, &s)) break;
+            hs.bases.assign(s, s + len);
+            g.seqs.push_back(std::move(hs));
+        }
+        ix.genomes.push_back(std::move(g));
+    }
+    ix.meta_k = c.varint();
+    if (!c.ok) { err = "truncated or malformed .bkdb"; return false; }
+    // a map never holds one key twice, so a stable sort by key keeps each key's entry order
+    index_from_pairs(ix, pairs);
+    return true;
+}
+
+bool slurp_maybe_gz(const std::string& path, std::string& out) {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) return false;
+    gzbuffer(g, 1 << 20);
+    std::vector<char> buf(1 << 20);
+    int n;
+    while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), n);
+    gzclose(g);
+    return n == 0;
+}
+
+bool bkdb_read(const std::string& path, HostIndex& ix, std::string& err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { err = "Failed to open file '" + path + "'"; return false; }
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<u8> buf(n > 0 ? n : 0);
+    size_t got = n > 0 ? fread(buf.data(), 1, n, f) : 0;
+    fclose(f);
+    if ((long)got != n) { err = "short read on '" + path + "'"; return false; }
+    if (!bkdb_decode(buf.data(), buf.size(), ix, err)) { err = "Failed to read Bronko Index from '" + path + "': " + err; return false; }
+    return true;
+}
+
+bool bkdb_write(const std::string& path, const HostIndex& ix, std::string& err) {
+    Sink s;
+    s.varint(ix.k);
+    s.varint(ix.keys.size());
+    for (size_t i = 0; i < ix.keys.size(); i++) {
+        s.varint(ix.keys[i]);
+        s.varint(ix.entry_off[i + 1] - ix.entry_off[i]);
+        for (u64 j = ix.entry_off[i]; j < ix.entry_off[i + 1]; j++) {
+            const bk_bucket_info& e = ix.entries[j];
+            s.varint(e.file_id); s.byte(e.seq_id); s.varint(e.location); s.byte(e.idx); s.byte(e.canonical);
+        }
+    }
+    s.varint(ix.genomes.size());
+    for (const HostGenome& g : ix.genomes) {
+        s.blob(g.name.data(), g.name.size());
+        s.varint(g.seqs.size());
+        for (const HostSeq& q : g.seqs) {
+            s.blob(q.name.data(), q.name.size());
+            s.varint(q.len);
+            s.blob(q.bases.data(), q.bases.size());
+        }
+    }
+    s.varint(ix.meta_k);
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { err = "File path " + path + " not valid"; return false; }
+    size_t w = fwrite(s.buf.data(), 1, s.buf.size(), f);
+    fclose(f);
+    if (w != s.buf.size()) { err = "short write on " + path; return false; }
+    return true;
+}
+
+std::string first_token(const std::string& s) {
+    size_t a = 0;
+    while (a < s.size() && isspace((unsigned char)s[a])) a++;
+    size_t b = a;
+    while (b < s.size() && !isspace((unsigned char)s[b])) b++;
+    return s.substr(a, b - a);
+}
+
+static std::string path_stem(const std::string& path) {
+    size_t sl = path.find_last_of('/');
+    std::string f = sl == std::string::npos ? path : path.substr(sl + 1);
+    size_t dot = f.find_last_of('.');
+    return (dot == std::string::npos || dot == 0) ? f : f.substr(0, dot);
+}
+
+// FASTA text → records; header = text after '>' up to end of line, sequence lines concatenated
+// with CR/LF removed (needletail semantics, reference src/build.rs:156-189).
+bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIndex& ix, std::string& err) {
+    ix = HostIndex();
+    ix.k = k; ix.meta_k = k;
+    std::vector<KeyedEntry> pairs;
+    u64 ids[32];
+    for (size_t file_id = 0; file_id < paths.size(); file_id++) {
+        std::string txt;
+        if (!slurp_maybe_gz(paths[file_id], txt)) { err = "Failed to parse fasta file: " + paths[file_id]; return false; }
+        HostGenome g;
+        g.name = path_stem(paths[file_id]);
+        size_t pos = 0;
+        while (pos < txt.size()) {
+            size_t eol = txt.find('\n', pos);
+            if (eol == std::string::npos) eol = txt.size();
+            size_t le = eol;
+            if (le > pos && txt[le - 1] == '\r') le--;
+            if (le > pos && txt[pos] == '>') {
+                HostSeq q;
+                q.name = first_token(txt.substr(pos + 1, le - pos - 1));
+                g.seqs.push_back(std::move(q));
+            } else if (!g.seqs.empty()) {
+                g.seqs.back().bases.insert(g.seqs.back().bases.end(), txt.begin() + pos, txt.begin() + le);
+            }
+            pos = eol + 1;
+        }
+        u8 seq_id = 0;   // u8 counter wraps after 255 sequences exactly as build.rs:170,207
+        for (HostSeq& q : g.seqs) {
+            q.len = q.bases.size();
+            const u64 L = q.len;
+            if (L >= k) {
+                const u64 kmask = (1ull << (2 * k)) - 1;
+                u64 fwd = 0;
+                for (u64 i = 0; i < L; i++) {
+                    fwd = ((fwd << 2) | nt_to_bits_host(q.bases[i])) & kmask;
+                    if (i + 1 < k) continue;
+                    const u64 start = i + 1 - k;
+                    const u64 rev = revcomp_host(fwd, (int)k);
+                    const bool rc = !(fwd < rev);               // lcb.rs:87-95
+                    assign_buckets_host(rc ? rev : fwd, (int)k, ids);
+                    for (u32 j = 0; j < k; j++) {
+                        KeyedEntry ke; memset(&ke, 0, sizeof ke);
+                        ke.key = ids[j];
+                        ke.e.file_id = (u16)file_id; ke.e.seq_id = seq_id; ke.e.location = (u32)start;
+                        ke.e.idx = (u8)j; ke.e.canonical = rc;
+                        pairs.push_back(ke);
+                    }
+                }
+            }
+            seq_id++;
+        }
+        ix.genomes.push_back(std::move(g));
+    }
+    index_from_pairs(ix, pairs);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Derived device tables
+// ---------------------------------------------------------------------------------------------
+static u32 log2_cap(u64 n_items) {
+    u32 l = 10;
+    while ((1ull << l) < 2 * n_items + 16) l++;
+    return l;
+}
+
+void derive_index(const HostIndex& ix, DerivedIndex& d) {
+    d = DerivedIndex();
+    d.k = ix.k;
+    const u32 k = ix.k;
+    d.n_genomes = (u32)ix.genomes.size();
+    u32 row = 0, seq = 0;
+    for (const HostGenome& g : ix.genomes) {
+        d.genome_row0.push_back(row);
+        d.genome_seq_off.push_back(seq);
+        u64 glen = 0;
+        for (const HostSeq& q : g.seqs) {
+            d.seq_row0.push_back(row);
+            for (u64 i = 0; i < q.bases.size(); i++) d.ref_code.push_back(nt_to_bits_host(q.bases[i]));
+            row += (u32)q.bases.size();
+            glen += q.len;
+            seq++;
+        }
+        d.genome_len.push_back(glen);
+        d.max_genome_rows = std::max(d.max_genome_rows, row - d.genome_row0.back());
+    }
+    d.genome_row0.push_back(row);
+    d.genome_seq_off.push_back(seq);
+    d.seq_row0.push_back(row);
+    d.n_seqs = seq;
+
+    // bucket table
+    d.bucket_log2 = log2_cap(ix.keys.size());
+    d.bucket_slots.assign(1ull << d.bucket_log2, BucketSlot{~0ull, 0, 0});
+    d.bucket_entries.resize(ix.entries.size());
+    for (size_t i = 0; i < ix.entries.size(); i++) {
+        const bk_bucket_info& e = ix.entries[i];
+        BucketEntry be;
+        u32 r = 0xFFFFFFFFu;
+        if (e.file_id < d.n_genomes) {
+            const u32 s0 = d.genome_seq_off[e.file_id], s1 = d.genome_seq_off[e.file_id + 1];
+            if (s0 + e.seq_id < s1) {
+                const u32 sr0 = d.seq_row0[s0 + e.seq_id], sr1 = d.seq_row0[s0 + e.seq_id + 1];
+                // the reference would index out of bounds (panic) on such an entry; it is skipped here
+                if ((u64)sr0 + e.location + e.idx < sr1) r = sr0 + e.location;
+            }
+        }
+        be.row = r; be.file_id = e.file_id; be.idx = e.idx; be.canonical = e.canonical ? 1 : 0;
+        d.bucket_entries[i] = be;
+    }
+    const u64 bmask = (1ull << d.bucket_log2) - 1;
+    for (size_t i = 0; i < ix.keys.size(); i++) {
+        u64 h = hash_slot_host(ix.keys[i], 64 - d.bucket_log2);
+        while (d.bucket_slots[h].key != ~0ull) h = (h + 1) & bmask;
+        d.bucket_slots[h] = BucketSlot{ix.keys[i], (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
+    }
+
+    // oriented reference store
+    struct Occ { u64 kmer; u32 gidx; u32 oseq; };
+    std::vector<Occ> occ;
+    u32 g_base = REF_PAD_BASES;
+    std::vector<u8> codes;   // global base index → 2-bit code
+    codes.assign(REF_PAD_BASES, 0);
+    const u64 kmask = (1ull << (2 * k)) - 1;
+    for (const HostGenome& g : ix.genomes) {
+        for (const HostSeq& q : g.seqs) {
+            const u32 L = (u32)q.bases.size();
+            for (int orient = 0; orient < 2; orient++) {
+                const u32 oseq = (u32)d.oseq_start.size();
+                d.oseq_start.push_back(g_base);
+                d.oseq_len.push_back(L);
+                u64 cur = 0;
+                for (u32 i = 0; i < L; i++) {
+                    const u8 c = orient == 0 ? nt_to_bits_host(q.bases[i]) : (u8)(3 ^ nt_to_bits_host(q.bases[L - 1 - i]));
+                    codes.push_back(c);
+                    cur = ((cur << 2) | c) & kmask;
+                    if (i + 1 >= k) occ.push_back(Occ{cur, g_base + i + 1 - k, oseq});
+                }
+                g_base += L;
+            }
+        }
+    }
+    codes.resize(codes.size() + REF_PAD_BASES, 0);
+    d.n_raw = (u32)codes.size();
+    d.refpk.assign((codes.size() + 31) / 32 + 2, 0);
+    for (size_t i = 0; i < codes.size(); i++) d.refpk[i >> 5] |= (u64)codes[i] << (62 - 2 * (i & 31));
+
+    std::sort(occ.begin(), occ.end(), [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.gidx < b.gidx; });
+    d.slot2id.assign(d.n_raw, 0xFFFFFFFFu);
+    for (size_t i = 0; i < occ.size(); i++) {
+        if (i == 0 || occ[i].kmer != occ[i - 1].kmer) d.id_kmer.push_back(occ[i].kmer);
+        d.slot2id[occ[i].gidx] = (u32)d.id_kmer.size() - 1;
+    }
+    d.exact_log2 = log2_cap(d.id_kmer.size());
+    d.exact_slots.assign(1ull << d.exact_log2, ExactSlot{~0ull, 0, 0});
+    const u64 emask = (1ull << d.exact_log2) - 1;
+    for (size_t i = 0; i < occ.size(); i++) {
+        if (i != 0 && occ[i].kmer == occ[i - 1].kmer) continue;
+        u64 h = hash_slot_host(occ[i].kmer, 64 - d.exact_log2);
+        while (d.exact_slots[h].key != ~0ull) h = (h + 1) & emask;
+        d.exact_slots[h] = ExactSlot{occ[i].kmer, occ[i].gidx, occ[i].oseq};
+    }
+}
+
+}  // namespace bk

@@ -1,0 +1,189 @@
+/* bronko_b200.h — C ABI of libbronko_b200.so: the B200 (sm_100a) k-mer→pileup path of bronko.
+ *
+ * The reference (treangenlab/bronko v0.1.0, Rust) has no FFI/plugin interface: the hot path sits
+ * behind an internal Rust seam inside call::call (src/call.rs:151-402).  Each entry point below
+ * names the reference function(s) it replaces (paths relative to the reference tree).  A Rust
+ * `extern "C"` crate binds these unchanged (INTEGRATION.md shows the stub); in this image (no
+ * rustc) the callers are the C++ `bronko` CLI (bronko_b200/csrc/bronko_main.cpp) and the Python
+ * ctypes mirror (bronko_b200/api.py).
+ *
+ * Conventions: every call returns 0 on success or a negative bk_status; nothing ever exits or
+ * throws across the ABI (the reference logs `error!` and calls std::process::exit(1); the host maps
+ * a negative status to exactly that).  bk_last_error() gives the message.  The caller owns every
+ * input buffer (valid until the call returns); the library owns all device memory.  One bk_ctx per
+ * GPU, not thread-safe, samples are sequential per ctx (mirrors the sequential sample loop at
+ * src/call.rs:213,298).  There is NO CPU fallback: bk_create fails if no sm_100 device is usable.
+ */
+#ifndef BRONKO_B200_H
+#define BRONKO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bk_ctx bk_ctx;
+
+typedef enum {
+    BK_OK = 0,
+    BK_ERR_ARG = -1,      /* invalid argument / call order */
+    BK_ERR_CUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+    BK_ERR_IO = -3,       /* file could not be opened / parsed */
+    BK_ERR_NO_GENOME = -4,/* pick_best_genome returned None (src/call.rs:230-233): host must exit(1) */
+    BK_ERR_OVERFLOW = -5, /* a device table overflowed its capacity; re-run with a larger table */
+    BK_ERR_NO_DEVICE = -6
+} bk_status;
+
+/* #[repr(C)] BucketInfo, src/build.rs:52-60 — 12 bytes including padding. */
+typedef struct {
+    uint16_t file_id;
+    uint8_t seq_id;
+    uint8_t _pad0;
+    uint32_t location;
+    uint8_t idx;
+    uint8_t canonical;
+    uint8_t _pad1[2];
+} bk_bucket_info;
+
+/* The CallArgs fields the path consumes (src/cli.rs:61-166, defaults src/consts.rs:1-20). */
+typedef struct {
+    uint32_t k;                       /* -k / --kmer-size (odd, 15..31) */
+    uint32_t min_kmers;               /* --min-kmers: KMC -ci */
+    uint32_t counter_max;             /* KMC -cs (src/call.rs:1173: 1000000) */
+    uint32_t use_full_kmer;           /* --use-full-kmer */
+    uint32_t n_fixed;                 /* --n-fixed */
+    uint32_t no_end_filter;           /* --no-end-filter */
+    uint32_t no_strand_filter;        /* --no-strand-filter */
+    uint32_t no_strand_balance_filter;/* --no-strand-balance-filter */
+    uint32_t n_per_strand;            /* --n-per-strand */
+    uint32_t table_log2;              /* log2 slots of the novel-k-mer hash table; 0 = auto */
+    uint64_t min_depth;               /* --min-depth */
+    uint64_t min_variant_depth;       /* --min-variant-depth */
+    double min_af;                    /* --min-af */
+    double strand_balance_ratio;      /* --balance-ratio */
+    double strand_odds_max;           /* --strand_odds */
+    double variant_multiplier;        /* --noise-multiplier */
+} bk_params;
+
+/* The four numbers bronko parses from KMC's stdout (src/call.rs:1190-1200). */
+typedef struct {
+    uint64_t total_reads, total_kmers, unique_kmers, unique_counted;
+} bk_kmc_stats;
+
+/* Value of FxHashMap<u16,(usize,usize,usize)> returned by map_kmers (src/call.rs:1257). */
+typedef struct {
+    uint64_t perfect, variant, unique_perfect;
+    uint32_t present;                 /* genome has an entry in the reference's map (>=1 bucket hit) */
+    uint32_t _pad;
+} bk_genome_stats;
+
+/* VCFRecord, src/call.rs:776-789 (seq = index of the sequence inside the selected genome). */
+typedef struct {
+    uint32_t seq;
+    uint32_t pos;                     /* 1-based */
+    uint8_t ref_base, alt_base;
+    uint8_t _pad[6];
+    uint64_t fwd_ref, rev_ref, fwd_alt, rev_alt, depth;
+    double af, sor;
+} bk_variant;
+
+/* What call() keeps per sample: OutputInfo (src/call.rs:138-149) + the call_variants tuple. */
+typedef struct {
+    int32_t best_genome;              /* index into the db's files */
+    uint32_t n_files;                 /* 1 = single-end, 2 = paired */
+    uint64_t n_variants;
+    uint64_t num_major_variants, num_minor_variants;
+    double breadth_coverage, depth_coverage;
+    uint64_t num_perfect_kmers, num_variant_kmers, num_unmapped_kmers;
+    bk_kmc_stats kmc[2];
+} bk_sample_result;
+
+/* Per-stage device time of the last sample (CUDA events on the ctx stream), milliseconds. */
+typedef struct {
+    float scan_ms;      /* pack + seed/extend scan kernel(s)        */
+    float leftover_ms;  /* novel / mismatching k-mer counting        */
+    float finalize_ms;  /* prefix-sum, fold, compaction              */
+    float map_ms;       /* bucket lookup, stats and pileup           */
+    float score_ms;     /* select + noise + variant kernels          */
+    float total_ms;     /* bk_sample_begin → end of bk_sample_finish */
+    uint32_t launches;  /* kernels launched for this sample          */
+    uint32_t scan_launches;
+} bk_stage_times;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int bk_create(bk_ctx** out, int device);
+void bk_destroy(bk_ctx* ctx);
+const char* bk_last_error(bk_ctx* ctx);      /* ctx may be NULL: last bk_create error */
+void* bk_stream(bk_ctx* ctx);                /* cudaStream_t all work is enqueued on */
+const char* bk_version(void);
+
+/* ---- index: replaces the bincode decode at src/call.rs:179-200 / build_indexes at 170-178 ---- */
+/* From flat arrays (what a Rust host holds after decoding BronkoIndex, src/build.rs:23-60):
+ * keys[n_keys], entry_off[n_keys+1], entries[entry_off[n_keys]] in per-key order;
+ * genome g owns sequences [genome_seq_off[g], genome_seq_off[g+1]); sequence s has seq_len[s] bases
+ * at ref_bases + seq_base_off[s] (raw FASTA bytes, SeqMeta.seq). */
+int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys,
+                  const uint64_t* entry_off, const bk_bucket_info* entries, uint32_t n_genomes,
+                  const uint32_t* genome_seq_off, const uint64_t* seq_len,
+                  const uint64_t* seq_base_off, const uint8_t* ref_bases);
+/* .bkdb file (bincode 2 standard config). */
+int bk_index_load_file(bk_ctx* ctx, const char* bkdb_path);
+/* build_indexes (src/build.rs:145-231) from FASTA(.gz) files, then load it. */
+int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const* fasta_paths);
+/* save_index (src/build.rs:122-143); keys are written in ascending order. */
+int bk_index_save(bk_ctx* ctx, const char* bkdb_path);
+int bk_index_info(bk_ctx* ctx, uint32_t* k, uint64_t* n_keys, uint64_t* n_entries, uint32_t* n_genomes);
+const char* bk_genome_name(bk_ctx* ctx, uint32_t genome);
+uint32_t bk_genome_n_seqs(bk_ctx* ctx, uint32_t genome);
+const char* bk_seq_name(bk_ctx* ctx, uint32_t genome, uint32_t seq);
+uint64_t bk_seq_len(bk_ctx* ctx, uint32_t genome, uint32_t seq);
+const uint8_t* bk_seq_bases(bk_ctx* ctx, uint32_t genome, uint32_t seq);
+/* parity hook: the decoded map, keys ascending (same layout as bk_index_load's inputs). */
+int bk_index_export(bk_ctx* ctx, uint64_t* keys, uint64_t* entry_off, bk_bucket_info* entries);
+
+/* ---- one sample: replaces src/call.rs:213-292 (SE) / 298-387 (PE) ------------------------- */
+void bk_params_default(bk_params* p);                       /* src/consts.rs defaults, k = 21 */
+int bk_sample_begin(bk_ctx* ctx, const bk_params* params);
+/* get_kmers / count_kmers_kmc (src/call.rs:630-646, 1152-1226): feed decoded reads of one file.
+ * file_slot 0 = the -r file or R1, 1 = R2 (counted and thresholded separately, src/call.rs:302-307).
+ * bases = concatenated sequence lines (ASCII), read r = bases[read_off[r] .. read_off[r+1]).
+ * Host buffers (pinned recommended: bk_host_alloc); may be called repeatedly per file (chunks). */
+int bk_reads_push(bk_ctx* ctx, int file_slot, const uint8_t* bases, const uint32_t* read_off,
+                  uint64_t n_reads);
+/* Same, buffers already in device memory (16-byte aligned, readable up to the next multiple of 16). */
+int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
+                         const uint32_t* d_read_off, uint64_t n_reads, uint64_t n_bases,
+                         uint32_t max_read_len);
+/* Decode a FASTQ(.gz) file on the host (KMC reader contract) and push it. */
+int bk_reads_push_fastq(bk_ctx* ctx, int file_slot, const char* fastq_path);
+/* map_kmers ×n_files → pick_best_genome(_paired) → call_variants (src/call.rs:224-268 / 314-360).
+ * Returns BK_ERR_NO_GENOME where the reference exits with "Unable to pick a best genome". */
+int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out);
+/* Results of the last finished sample. */
+int bk_sample_variants(bk_ctx* ctx, bk_variant* out, uint64_t cap);          /* sorted seq,pos,alt */
+int bk_sample_genome_stats(bk_ctx* ctx, int file_slot, bk_genome_stats* out);/* n_genomes entries */
+/* OutputData.counts of the selected genome (src/call.rs:1235-1239), widened to u64:
+ * arr 0 = output (fwd depth), 1 = output_rev, 2 = output_counts (fwd support), 3 = output_rev_counts;
+ * out = rows*4 u64 where rows = sum of the genome's sequence lengths. */
+int bk_sample_pileup(bk_ctx* ctx, int arr, uint64_t* out, uint64_t cap_rows);
+int bk_sample_noise_max(bk_ctx* ctx, double* out, uint64_t cap_rows);        /* Noise.max per row */
+/* parity hook: the KMC dump of one file (kept k-mers, capped counts), ascending by k-mer.
+ * Pass NULL pointers to query the count. */
+int bk_kmer_counts_get(bk_ctx* ctx, int file_slot, uint64_t* kmers, uint32_t* counts, uint64_t* n);
+int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out);
+
+/* ---- writers: src/call.rs:648-774 (formats in SURVEY.md Appendix D) ------------------------ */
+int bk_write_vcf(bk_ctx* ctx, const char* reads_path, const char* out_path);
+int bk_write_pileup(bk_ctx* ctx, const char* out_path);
+/* clean_sample_id (src/util.rs:30-50) → buf; returns needed size incl. NUL */
+uint64_t bk_clean_sample_id(const char* path, char* buf, uint64_t cap);
+
+/* ---- pinned host memory helpers ---------------------------------------------------------- */
+void* bk_host_alloc(uint64_t bytes);
+void bk_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRONKO_B200_H */
