@@ -194,10 +194,11 @@ BK_HD u32 count_stretch(const CountView& v, const Ld& ld, u32 byte_off, u32 cnt,
 }
 
 // Leftover stretch: k-mers starting at read bases [a, a+cnt) of the read at byte offset o0.
+// gofs = byte offset of the word source inside the pushed buffer (descriptors use buffer offsets).
 template <class Ld>
-BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt) {
+BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt, u32 gofs) {
     const u32 slot = fetch_add_u32(v.n_desc, 1u);
-    if (slot < v.desc_cap) { v.desc[slot] = make_uint2(o0 + a, cnt); return 0; }
+    if (slot < v.desc_cap) { v.desc[slot] = make_uint2(gofs + o0 + a, cnt); return 0; }
     return count_stretch(v, ld, o0 + a, cnt, 0, 1);   // queue full: count in place (slow, still exact)
 }
 
@@ -216,7 +217,7 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 #define BK_BAIL_MISMATCHES 8  // this many bad bases inside one 32-base word ends the diagonal
 #endif
 
-// One read: bytes [o0, o0+len) of the word source.  Returns number of new novel keys created by the
+// One read: bytes [o0, o0+len) of the word source (which starts gofs bytes into the pushed buffer).  Returns number of new novel keys created by the
 // in-place fallback (normally 0).
 //
 // State: k-mers are indexed by their start base.  `c` = first k-mer start not classified yet (every
@@ -225,7 +226,7 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 // overlap with the oriented sequence, end of read) closes the stretch [ms, e): if it holds >= k bases
 // its k-mers [ms, e-k] become a run, everything pending before ms a leftover stretch.
 template <class Ld, class LdRef>
-BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len) {
+BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len, u32 gofs) {
     const u32 k = v.k;
     if (len < k) return 0;                       // shorter than k: contributes no k-mer
     const u32 nk = len - k + 1;
@@ -252,7 +253,7 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, 
     do {                                                                                  \
         const i32 e__ = (e_);                                                             \
         if (e__ - ms >= (i32)k) {                                                         \
-            if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c));       \
+            if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c), gofs);       \
             emit_run(v, g0, (u32)ms, (u32)(e__ - (i32)k + 1 - ms));                       \
             c = e__ - (i32)k + 1;                                                         \
         }                                                                                 \
@@ -301,7 +302,7 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, 
         if (!bailed) { BK_EVENT(i_hi); break; }
 #undef BK_EVENT
     }
-    if ((i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c);
+    if ((i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c, gofs);
     return created;
 }
 

@@ -1,0 +1,804 @@
+// bk_device.cu — bk_ctx, device memory, kernel launches and the C ABI of libbronko_b200.so
+// (include/bronko_b200.h).  There is no CPU fallback anywhere in this file: every stage of a sample
+// runs as a CUDA kernel from bk_kernels.cuh, and bk_create fails without an sm_100 device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bk_host.h"
+#include "bk_kernels.cuh"
+
+using namespace bk;
+
+static std::string g_create_error;
+
+#define BK_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) return ctx->fail(BK_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    template <class V>
+    cudaError_t upload(const V& v, cudaStream_t st) {
+        cudaError_t e = reserve(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum Stage { ST_SCAN = 0, ST_LEFTOVER, ST_FINALIZE, ST_MAP, ST_SCORE, ST_N };
+
+struct FileState {
+    DevBuf<u32> diff, idcnt;
+    DevBuf<GenSlot> gen;
+    DevBuf<u64> ckmers;
+    DevBuf<u32> ccounts;
+    DevBuf<u32> gstats;
+    u32 gen_log2 = 0;
+    bool used = false, finalized = false;
+    u64 total_reads = 0, total_bases = 0;
+};
+
+}  // namespace
+
+struct bk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    HostIndex ix;
+    DerivedIndex d;
+    bool have_index = false;
+    // device copies of the derived index
+    DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
+    DevBuf<u64> d_refpk; DevBuf<u32> d_oseq_start, d_oseq_len;
+    DevBuf<ExactSlotD> d_exact;
+    DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
+    DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
+    u32 max_seqs_per_genome = 1;
+
+    // per-sample state
+    bk_params params;
+    bool in_sample = false, finished = false;
+    FileState file[2];
+    DevBuf<Counters> d_ctr;
+    Counters* h_ctr = nullptr;              // pinned
+    DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
+    DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
+    DevBuf<double> d_maf, d_msq, d_st_s, d_st_s2, d_st_max, d_noise;
+    DevBuf<u32> d_st_n;
+    DevBuf<bk_variant> d_vars;
+    // staging for host pushes (double buffered)
+    DevBuf<u8> d_stage[2]; DevBuf<u32> d_stage_off;
+    cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
+    int stage_next = 0;
+    u32 shard_rank = 0, shard_n = 1;
+
+    // results
+    bk_sample_result result;
+    std::vector<bk_variant> variants;
+    std::vector<bk_genome_stats> gstats[2];
+
+    // timing
+    struct Span { cudaEvent_t a, b; int stage; };
+    std::vector<Span> spans; size_t spans_used = 0;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    u32 launches = 0, scan_launches = 0;
+    bk_stage_times times;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[1024];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+    int span_begin(int stage) {
+        if (spans_used == spans.size()) {
+            Span s; s.stage = stage;
+            if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return -1;
+            spans.push_back(s);
+        }
+        spans[spans_used].stage = stage;
+        cudaEventRecord(spans[spans_used].a, stream);
+        return (int)spans_used++;
+    }
+    void span_end(int id) { if (id >= 0) cudaEventRecord(spans[id].b, stream); }
+};
+
+static int grid_for(const bk_ctx* ctx, u64 items, u32 per_block, u32 max_waves = 8) {
+    u64 g = (items + per_block - 1) / per_block;
+    const u64 cap = (u64)ctx->sm_count * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" {
+
+const char* bk_version(void) { return "bronko_b200 0.1.0 (sm_100a)"; }
+
+int bk_create(bk_ctx** out, int device) {
+    if (!out) return BK_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libbronko_b200 has no CPU path)";
+        return BK_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return BK_ERR_ARG; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not sm_100 (B200); the kernels are built for sm_100a only";
+        return BK_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return BK_ERR_CUDA; }
+    bk_ctx* ctx = new bk_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->stage_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+        double tau[301];
+        tau_table(tau);
+        ok = cudaMemcpyToSymbol(c_tau, tau, sizeof tau) == cudaSuccess;
+    }
+    if (ok) ok = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_map<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
+    memset(&ctx->times, 0, sizeof ctx->times);
+    memset(&ctx->result, 0, sizeof ctx->result);
+    bk_params_default(&ctx->params);
+    *out = ctx;
+    return BK_OK;
+}
+
+void bk_destroy(bk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->d_bucket_slots.release(); ctx->d_bucket_entries.release(); ctx->d_refpk.release(); ctx->d_oseq_start.release();
+    ctx->d_oseq_len.release(); ctx->d_exact.release(); ctx->d_slot2id.release(); ctx->d_id_kmer.release();
+    ctx->d_genome_row0.release(); ctx->d_genome_seq_off.release(); ctx->d_seq_row0.release(); ctx->d_genome_len.release();
+    ctx->d_ref_code.release();
+    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); }
+    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
+    ctx->d_maf.release(); ctx->d_msq.release(); ctx->d_st_s.release(); ctx->d_st_s2.release(); ctx->d_st_max.release();
+    ctx->d_noise.release(); ctx->d_st_n.release(); ctx->d_vars.release();
+    ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
+    for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (int i = 0; i < 2; i++) { if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]); if (ctx->stage_copied[i]) cudaEventDestroy(ctx->stage_copied[i]); }
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char* bk_last_error(bk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void* bk_stream(bk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void* bk_host_alloc(uint64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+void bk_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void bk_params_default(bk_params* p) {    // reference src/consts.rs:1-20, src/call.rs:1173
+    memset(p, 0, sizeof *p);
+    p->k = 21; p->min_kmers = 3; p->counter_max = 1000000; p->use_full_kmer = 0; p->n_fixed = 2;
+    p->n_per_strand = 2; p->table_log2 = 0; p->min_depth = 300; p->min_variant_depth = 3;
+    p->min_af = 0.03; p->strand_balance_ratio = 0.1; p->strand_odds_max = 6.0; p->variant_multiplier = 1.5;
+}
+
+uint64_t bk_clean_sample_id(const char* path, char* buf, uint64_t cap) {
+    const std::string t = clean_sample_id(path ? path : "");
+    if (buf && cap) { const u64 n = std::min<u64>(cap - 1, t.size()); memcpy(buf, t.data(), n); buf[n] = 0; }
+    return t.size() + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------
+static int upload_index(bk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    if (ctx->ix.k < 15 || ctx->ix.k > 31 || (ctx->ix.k & 1) == 0)
+        return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
+    derive_index(ctx->ix, ctx->d);
+    const DerivedIndex& d = ctx->d;
+    if (d.n_genomes == 0 || d.n_genomes > 4096) return ctx->fail(BK_ERR_ARG, "index holds %u genomes (supported: 1..4096)", d.n_genomes);
+    if ((u64)d.n_raw + 2 >= 0x7FFFFFFFull) return ctx->fail(BK_ERR_ARG, "reference set too large for 32-bit slot indices");
+    cudaStream_t st = ctx->stream;
+    static_assert(sizeof(BucketSlot) == sizeof(BucketSlotD) && sizeof(BucketEntry) == sizeof(BucketEntryD) && sizeof(ExactSlot) == sizeof(ExactSlotD), "layout");
+    BK_CUDA(ctx->d_bucket_slots.reserve(d.bucket_slots.size()));
+    BK_CUDA(cudaMemcpyAsync(ctx->d_bucket_slots.p, d.bucket_slots.data(), d.bucket_slots.size() * 16, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->d_bucket_entries.reserve(d.bucket_entries.size()));
+    if (!d.bucket_entries.empty())
+        BK_CUDA(cudaMemcpyAsync(ctx->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->d_exact.reserve(d.exact_slots.size()));
+    BK_CUDA(cudaMemcpyAsync(ctx->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->d_refpk.upload(d.refpk, st));
+    BK_CUDA(ctx->d_oseq_start.upload(d.oseq_start, st));
+    BK_CUDA(ctx->d_oseq_len.upload(d.oseq_len, st));
+    BK_CUDA(ctx->d_slot2id.upload(d.slot2id, st));
+    BK_CUDA(ctx->d_id_kmer.upload(d.id_kmer, st));
+    BK_CUDA(ctx->d_genome_row0.upload(d.genome_row0, st));
+    BK_CUDA(ctx->d_genome_seq_off.upload(d.genome_seq_off, st));
+    BK_CUDA(ctx->d_seq_row0.upload(d.seq_row0, st));
+    BK_CUDA(ctx->d_genome_len.upload(d.genome_len, st));
+    BK_CUDA(ctx->d_ref_code.upload(d.ref_code, st));
+    ctx->max_seqs_per_genome = 1;
+    for (u32 g = 0; g < d.n_genomes; g++) ctx->max_seqs_per_genome = std::max(ctx->max_seqs_per_genome, d.genome_seq_off[g + 1] - d.genome_seq_off[g]);
+    const size_t rows = std::max<u32>(d.max_genome_rows, 1);
+    BK_CUDA(ctx->d_pile.reserve(rows * 16));
+    BK_CUDA(ctx->d_maf.reserve(rows * 3)); BK_CUDA(ctx->d_msq.reserve(rows * 3));
+    BK_CUDA(ctx->d_st_n.reserve(rows)); BK_CUDA(ctx->d_st_s.reserve(rows)); BK_CUDA(ctx->d_st_s2.reserve(rows));
+    BK_CUDA(ctx->d_st_max.reserve(rows * BK_NOISE_TABLE)); BK_CUDA(ctx->d_noise.reserve(rows));
+    BK_CUDA(ctx->d_vars.reserve(rows * 3));
+    BK_CUDA(ctx->d_ctr.reserve(1));
+    BK_CUDA(ctx->d_bsum.reserve(((size_t)d.n_raw + 2 + BK_PS_BLOCK - 1) / BK_PS_BLOCK + 1));
+    for (FileState& f : ctx->file) {
+        BK_CUDA(f.diff.reserve((size_t)d.n_raw + 2));
+        BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
+        BK_CUDA(f.gstats.reserve((size_t)d.n_genomes * 4));
+    }
+    BK_CUDA(cudaStreamSynchronize(st));
+    ctx->have_index = true;
+    ctx->in_sample = false; ctx->finished = false;
+    return BK_OK;
+}
+
+int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys, const uint64_t* entry_off,
+                  const bk_bucket_info* entries, uint32_t n_genomes, const uint32_t* genome_seq_off,
+                  const uint64_t* seq_len, const uint64_t* seq_base_off, const uint8_t* ref_bases) {
+    if (!ctx) return BK_ERR_ARG;
+    if (!keys || !entry_off || !entries || !genome_seq_off || !seq_len || !seq_base_off || !ref_bases)
+        return ctx->fail(BK_ERR_ARG, "bk_index_load: null argument");
+    HostIndex& ix = ctx->ix;
+    ix = HostIndex();
+    ix.k = k; ix.meta_k = k;
+    std::vector<KeyedEntry> pairs;
+    pairs.reserve(entry_off[n_keys]);
+    for (u64 i = 0; i < n_keys; i++)
+        for (u64 j = entry_off[i]; j < entry_off[i + 1]; j++) pairs.push_back(KeyedEntry{keys[i], entries[j]});
+    index_from_pairs(ix, pairs);
+    for (u32 g = 0; g < n_genomes; g++) {
+        HostGenome hg;
+        hg.name = "genome" + std::to_string(g);
+        for (u32 s = genome_seq_off[g]; s < genome_seq_off[g + 1]; s++) {
+            HostSeq q;
+            q.name = "seq" + std::to_string(s - genome_seq_off[g]);
+            q.len = seq_len[s];
+            q.bases.assign(ref_bases + seq_base_off[s], ref_bases + seq_base_off[s] + seq_len[s]);
+            hg.seqs.push_back(std::move(q));
+        }
+        ix.genomes.push_back(std::move(hg));
+    }
+    return upload_index(ctx);
+}
+
+int bk_index_load_file(bk_ctx* ctx, const char* path) {
+    if (!ctx || !path) return BK_ERR_ARG;
+    std::string err;
+    if (!bkdb_read(path, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    return upload_index(ctx);
+}
+
+int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const* fasta_paths) {
+    if (!ctx || !fasta_paths || n_files == 0) return BK_ERR_ARG;
+    if (k < 15 || k > 31 || (k & 1) == 0) return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
+    std::vector<std::string> paths(fasta_paths, fasta_paths + n_files);
+    std::string err;
+    if (!index_build_from_fasta(k, paths, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    return upload_index(ctx);
+}
+
+int bk_index_save(bk_ctx* ctx, const char* path) {
+    if (!ctx || !path || !ctx->have_index) return BK_ERR_ARG;
+    std::string err;
+    if (!bkdb_write(path, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    return BK_OK;
+}
+
+int bk_index_info(bk_ctx* ctx, uint32_t* k, uint64_t* n_keys, uint64_t* n_entries, uint32_t* n_genomes) {
+    if (!ctx || !ctx->have_index) return BK_ERR_ARG;
+    if (k) *k = ctx->ix.k;
+    if (n_keys) *n_keys = ctx->ix.keys.size();
+    if (n_entries) *n_entries = ctx->ix.entries.size();
+    if (n_genomes) *n_genomes = (u32)ctx->ix.genomes.size();
+    return BK_OK;
+}
+const char* bk_genome_name(bk_ctx* ctx, uint32_t g) { return (ctx && g < ctx->ix.genomes.size()) ? ctx->ix.genomes[g].name.c_str() : nullptr; }
+uint32_t bk_genome_n_seqs(bk_ctx* ctx, uint32_t g) { return (ctx && g < ctx->ix.genomes.size()) ? (u32)ctx->ix.genomes[g].seqs.size() : 0; }
+const char* bk_seq_name(bk_ctx* ctx, uint32_t g, uint32_t s) {
+    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].name.c_str() : nullptr;
+}
+uint64_t bk_seq_len(bk_ctx* ctx, uint32_t g, uint32_t s) {
+    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].len : 0;
+}
+const uint8_t* bk_seq_bases(bk_ctx* ctx, uint32_t g, uint32_t s) {
+    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].bases.data() : nullptr;
+}
+int bk_index_export(bk_ctx* ctx, uint64_t* keys, uint64_t* entry_off, bk_bucket_info* entries) {
+    if (!ctx || !ctx->have_index || !keys || !entry_off || !entries) return BK_ERR_ARG;
+    memcpy(keys, ctx->ix.keys.data(), ctx->ix.keys.size() * 8);
+    memcpy(entry_off, ctx->ix.entry_off.data(), ctx->ix.entry_off.size() * 8);
+    memcpy(entries, ctx->ix.entries.data(), ctx->ix.entries.size() * sizeof(bk_bucket_info));
+    return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample
+// ---------------------------------------------------------------------------------------------
+int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
+    if (!ctx) return BK_ERR_ARG;
+    if (!ctx->have_index) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: no index loaded");
+    if (!params) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: null params");
+    if (params->k != ctx->ix.k)
+        return ctx->fail(BK_ERR_ARG, "Database k is not the same as provided, please set -k to %u or build a new index", ctx->ix.k);
+    if (params->table_log2 != 0 && (params->table_log2 < 10 || params->table_log2 > 31))
+        return ctx->fail(BK_ERR_ARG, "table_log2 must be 0 (auto) or in [10, 31]");
+    cudaSetDevice(ctx->device);
+    ctx->params = *params;
+    ctx->in_sample = true; ctx->finished = false;
+    for (FileState& f : ctx->file) { f.used = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; }
+    ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0;
+    ctx->variants.clear();
+    memset(&ctx->result, 0, sizeof ctx->result);
+    ctx->result.best_genome = -1;
+    cudaEventRecord(ctx->ev_begin, ctx->stream);
+    BK_CUDA(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), ctx->stream));
+    return BK_OK;
+}
+
+static CountView make_count_view(bk_ctx* ctx, FileState& f) {
+    CountView v;
+    v.k = ctx->ix.k;
+    v.refpk = ctx->d_refpk.p; v.ref_words = (u32)ctx->d.refpk.size();
+    v.oseq_start = ctx->d_oseq_start.p; v.oseq_len = ctx->d_oseq_len.p;
+    v.exact = ctx->d_exact.p; v.exact_shift = 64 - ctx->d.exact_log2; v.exact_mask = (1u << ctx->d.exact_log2) - 1;
+    v.diff = f.diff.p;
+    v.gen = f.gen.p; v.gen_shift = 64 - f.gen_log2; v.gen_mask = (u32)((1ull << f.gen_log2) - 1);
+    v.gen_full = &ctx->d_ctr.p->gen_full;
+    v.desc = ctx->d_desc.p; v.desc_cap = (u32)std::min<size_t>(ctx->d_desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->n_desc;
+    return v;
+}
+
+// first use of a file slot in this sample: zero its difference array and (re)initialise its table
+static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
+    FileState& f = ctx->file[slot];
+    if (f.used) return BK_OK;
+    u32 lg = ctx->params.table_log2;
+    if (lg == 0) {            // auto: ~1 slot per 16 read bases of this first push, clamped to [2^22, 2^27]
+        lg = 22;
+        while (lg < 27 && (1ull << lg) < bases_hint / 16) lg++;
+    }
+    f.gen_log2 = lg;
+    BK_CUDA(f.gen.reserve(1ull << lg));
+    BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->d.n_raw + 2) * 4, ctx->stream));
+    BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->d.id_kmer.size(), 1) * 4, ctx->stream));
+    k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
+    ctx->launches++;
+    BK_CUDA(cudaGetLastError());
+    f.used = true;
+    return BK_OK;
+}
+
+// scan + leftover kernels over reads [r_begin, r_end) whose bytes live in d_bases (offset by off_bias)
+static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_off, u32 off_bias, u32 r_begin, u32 r_end, u32 max_len) {
+    FileState& f = ctx->file[slot];
+    const u32 n = r_end - r_begin;
+    if (n == 0) return BK_OK;
+    BK_CUDA(ctx->d_desc.reserve((size_t)n * 2 + 4096));
+    BK_CUDA(cudaMemsetAsync(&ctx->d_ctr.p->n_desc, 0, 4, ctx->stream));
+    CountView v = make_count_view(ctx, f);
+    const u32 tile_bytes = 40 * 1024;
+    u32 tile_reads = BK_SCAN_THREADS;
+    if (max_len > 0) tile_reads = std::min<u32>(BK_SCAN_THREADS, std::max<u32>(1, tile_bytes / (max_len + 16)));
+    if (tile_reads < 32) tile_reads = BK_SCAN_THREADS;   // long reads: tiles will not fit; kernel reads global memory
+    const u32 n_tiles = (n + tile_reads - 1) / tile_reads;
+    int sp = ctx->span_begin(ST_SCAN);
+    k_scan<<<grid_for(ctx, n_tiles, 1, 16), BK_SCAN_THREADS, tile_bytes + 64, ctx->stream>>>(
+        v, d_bases, d_off, off_bias, r_begin, r_end, tile_reads, tile_bytes, &ctx->d_ctr.p->f[slot].gen_new);
+    ctx->span_end(sp);
+    ctx->launches++; ctx->scan_launches++;
+    BK_CUDA(cudaGetLastError());
+    sp = ctx->span_begin(ST_LEFTOVER);
+    k_leftover<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    ctx->span_end(sp);
+    ctx->launches++;
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+static int check_push(bk_ctx* ctx, int slot) {
+    if (!ctx) return BK_ERR_ARG;
+    if (!ctx->in_sample || ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_reads_push: call bk_sample_begin first");
+    if (slot < 0 || slot > 1) return ctx->fail(BK_ERR_ARG, "bk_reads_push: file_slot must be 0 or 1");
+    if (ctx->file[slot].finalized) return ctx->fail(BK_ERR_ARG, "bk_reads_push: file already finalized");
+    cudaSetDevice(ctx->device);
+    return BK_OK;
+}
+
+int bk_reads_push_device(bk_ctx* ctx, int slot, const uint8_t* d_bases, const uint32_t* d_off, uint64_t n_reads,
+                         uint64_t n_bases, uint32_t max_read_len) {
+    int rc = check_push(ctx, slot);
+    if (rc) return rc;
+    if (n_reads == 0) { return file_prepare(ctx, slot, 0); }
+    if (!d_bases || !d_off) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: null buffer");
+    if (((uintptr_t)d_bases & 15) != 0) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: bases must be 16-byte aligned");
+    if (n_reads >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFF0ull) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: push at most 2^32-16 bases / reads at a time");
+    if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
+    ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
+    return launch_count(ctx, slot, d_bases, d_off, 0, 0, (u32)n_reads, max_read_len);
+}
+
+int bk_reads_push(bk_ctx* ctx, int slot, const uint8_t* bases, const uint32_t* read_off, uint64_t n_reads) {
+    int rc = check_push(ctx, slot);
+    if (rc) return rc;
+    if (n_reads == 0) return file_prepare(ctx, slot, 0);
+    if (!bases || !read_off) return ctx->fail(BK_ERR_ARG, "bk_reads_push: null buffer");
+    if (n_reads >= 0xFFFFFFFFull) return ctx->fail(BK_ERR_ARG, "bk_reads_push: too many reads in one push");
+    const u64 n_bases = read_off[n_reads];
+    if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
+    ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
+    // offsets once, bases in chunks through two staging buffers so H2D overlaps the kernels
+    BK_CUDA(ctx->d_stage_off.reserve(n_reads + 1));
+    BK_CUDA(cudaMemcpyAsync(ctx->d_stage_off.p, read_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const u64 CHUNK = 64ull << 20;
+    u64 r = 0;
+    while (r < n_reads) {
+        u64 r_end = r;
+        const u32 c_begin = read_off[r] & ~15u;          // chunk starts at a 16-byte boundary of the host buffer
+        u32 max_len = 0;
+        while (r_end < n_reads && (u64)read_off[r_end + 1] - c_begin <= CHUNK) {
+            max_len = std::max(max_len, read_off[r_end + 1] - read_off[r_end]);
+            r_end++;
+        }
+        if (r_end == r) { max_len = read_off[r + 1] - read_off[r]; r_end = r + 1; }   // a single read larger than CHUNK
+        const u64 c_bytes = (u64)read_off[r_end] - c_begin;
+        const int b = ctx->stage_next; ctx->stage_next ^= 1;
+        BK_CUDA(ctx->d_stage[b].reserve(std::max<u64>(c_bytes, CHUNK) + 256));
+        BK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+        BK_CUDA(cudaMemcpyAsync(ctx->d_stage[b].p, bases + c_begin, c_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BK_CUDA(cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
+        BK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_copied[b], 0));
+        if ((rc = launch_count(ctx, slot, ctx->d_stage[b].p, ctx->d_stage_off.p, c_begin, (u32)r, (u32)r_end, max_len))) return rc;
+        BK_CUDA(cudaEventRecord(ctx->stage_free[b], ctx->stream));
+        r = r_end;
+    }
+    // the caller may reuse its buffers once we return: wait for the copies (not for the kernels)
+    BK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    BK_CUDA(cudaEventSynchronize(ctx->stage_copied[ctx->stage_next ^ 1]));
+    return BK_OK;
+}
+
+int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
+    int rc = check_push(ctx, slot);
+    if (rc) return rc;
+    if (!path) return ctx->fail(BK_ERR_ARG, "bk_reads_push_fastq: null path");
+    std::vector<HostReads> chunks;
+    std::string err;
+    if (!fastq_read(path, chunks, 1ull << 30, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    for (HostReads& c : chunks) {
+        c.bases.resize(c.bases.size() + 64, '*');       // readable slack past the last read
+        if ((rc = bk_reads_push(ctx, slot, c.bases.data(), c.off.data(), c.off.size() - 1))) return rc;
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));    // pageable source: the driver staged it, buffers die with `chunks`
+    }
+    if (chunks.empty() || (chunks.size() == 1 && chunks[0].off.size() == 1)) return file_prepare(ctx, slot, 0);
+    return BK_OK;
+}
+
+// prefix sum + fold + compaction of one file (the KMC "database" of that file)
+static int finalize_counts(bk_ctx* ctx, int slot) {
+    FileState& f = ctx->file[slot];
+    if (f.finalized) return BK_OK;
+    const DerivedIndex& d = ctx->d;
+    const u32 n = d.n_raw;
+    const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
+    const u32 n_ids = (u32)d.id_kmer.size();
+    const size_t out_cap = (size_t)n_ids + (1ull << f.gen_log2);
+    BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
+    int sp = ctx->span_begin(ST_FINALIZE);
+    k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p);
+    k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
+    k_diff_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p, ctx->d_slot2id.p, f.idcnt.p);
+    CompactArgs a;
+    a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n;
+    a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
+    a.fc = &ctx->d_ctr.p->f[slot];
+    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->d_id_kmer.p, n_ids);
+    k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
+    ctx->span_end(sp);
+    ctx->launches += 5;
+    BK_CUDA(cudaGetLastError());
+    f.finalized = true;
+    return BK_OK;
+}
+
+static MapView make_map_view(bk_ctx* ctx) {
+    MapView m;
+    const u32 k = ctx->ix.k;
+    m.k = k;
+    // src/call.rs:1291-1300: buckets[n_fixed .. k - n_fixed - 1) unless --use-full-kmer
+    if (ctx->params.use_full_kmer) { m.b0 = 0; m.b1 = k; }
+    else if ((u64)ctx->params.n_fixed * 2 + 1 >= k) { m.b0 = 0; m.b1 = 0; }
+    else { m.b0 = ctx->params.n_fixed; m.b1 = k - ctx->params.n_fixed - 1; }
+    m.slots = ctx->d_bucket_slots.p; m.shift = 64 - ctx->d.bucket_log2; m.mask = (1u << ctx->d.bucket_log2) - 1;
+    m.entries = ctx->d_bucket_entries.p;
+    m.n_genomes = ctx->d.n_genomes; m.genome_row0 = ctx->d_genome_row0.p;
+    return m;
+}
+
+int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
+    if (!ctx) return BK_ERR_ARG;
+    if (!ctx->in_sample || ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: no sample in progress");
+    if (!ctx->file[0].used) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: no reads were pushed to file slot 0");
+    cudaSetDevice(ctx->device);
+    const int n_files = ctx->file[1].used ? 2 : 1;
+    const DerivedIndex& d = ctx->d;
+    cudaStream_t st = ctx->stream;
+    int rc;
+    for (int f = 0; f < n_files; f++) if ((rc = finalize_counts(ctx, f))) return rc;
+
+    const MapView m = make_map_view(ctx);
+    const u32 pile_stride = d.max_genome_rows * 4;
+    const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
+    Counters* dc = ctx->d_ctr.p;
+    int sp = ctx->span_begin(ST_MAP);
+    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
+    for (int f = 0; f < n_files; f++) {
+        FileState& fs = ctx->file[f];
+        BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
+        k_map<0><<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu),
+                                                           fs.gstats.p, nullptr, nullptr, 0);
+        ctx->launches++;
+    }
+    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
+    ctx->launches++;
+    for (int f = 0; f < n_files; f++) {
+        FileState& fs = ctx->file[f];
+        k_map<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu),
+                                                    nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        ctx->launches++;
+    }
+    ctx->span_end(sp);
+    BK_CUDA(cudaGetLastError());
+
+    sp = ctx->span_begin(ST_SCORE);
+    ScoreView sv;
+    sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
+    sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
+    const u32 row_blocks = (d.max_genome_rows + 255) / 256;
+    k_noise_prep<<<row_blocks, 256, 0, st>>>(sv, ctx->d_maf.p, ctx->d_msq.p);
+    k_noise_seq<<<ctx->max_seqs_per_genome, 64, 0, st>>>(sv, ctx->d_maf.p, ctx->d_msq.p, ctx->d_st_n.p, ctx->d_st_s.p, ctx->d_st_s2.p, ctx->d_st_max.p);
+    k_noise_tau<<<row_blocks, 256, 0, st>>>(sv, ctx->d_st_n.p, ctx->d_st_s.p, ctx->d_st_s2.p, ctx->d_st_max.p, ctx->d_noise.p);
+    CallParams cp;
+    const bk_params& p = ctx->params;
+    cp.k = p.k; cp.no_end_filter = p.no_end_filter; cp.no_strand_filter = p.no_strand_filter;
+    cp.no_strand_balance_filter = p.no_strand_balance_filter; cp.n_per_strand = p.n_per_strand;
+    cp.min_depth = p.min_depth; cp.min_variant_depth = p.min_variant_depth; cp.min_af = p.min_af;
+    cp.strand_balance_ratio = p.strand_balance_ratio; cp.strand_odds_max = p.strand_odds_max; cp.variant_multiplier = p.variant_multiplier;
+    k_call<<<row_blocks, 256, 0, st>>>(sv, cp, ctx->d_noise.p, ctx->d_vars.p, (u32)std::min<size_t>(ctx->d_vars.cap, 0xFFFFFFFFu), dc);
+    ctx->span_end(sp);
+    ctx->launches += 4;
+    BK_CUDA(cudaGetLastError());
+
+    BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    std::vector<u32> hg[2];
+    for (int f = 0; f < n_files; f++) {
+        hg[f].resize((size_t)d.n_genomes * 4);
+        BK_CUDA(cudaMemcpyAsync(hg[f].data(), ctx->file[f].gstats.p, hg[f].size() * 4, cudaMemcpyDeviceToHost, st));
+    }
+    BK_CUDA(cudaStreamSynchronize(st));
+    const Counters& c = *ctx->h_ctr;
+    ctx->finished = true;
+    if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "novel k-mer table (2^%u slots) is full; set bk_params.table_log2 higher", ctx->file[0].gen_log2);
+    if (c.var_overflow) return ctx->fail(BK_ERR_OVERFLOW, "variant buffer overflow");
+    for (int f = 0; f < n_files; f++) {
+        if ((size_t)c.f[f].n_counted > ctx->file[f].ckmers.cap) return ctx->fail(BK_ERR_OVERFLOW, "counted k-mer list overflow");
+        ctx->gstats[f].assign(d.n_genomes, bk_genome_stats());
+        for (u32 g = 0; g < d.n_genomes; g++) {
+            bk_genome_stats& s = ctx->gstats[f][g];
+            s.perfect = hg[f][g * 4]; s.variant = hg[f][g * 4 + 1]; s.unique_perfect = hg[f][g * 4 + 2]; s.present = hg[f][g * 4 + 3]; s._pad = 0;
+        }
+    }
+    bk_sample_result& r = ctx->result;
+    memset(&r, 0, sizeof r);
+    r.best_genome = c.best; r.n_files = n_files;
+    for (int f = 0; f < n_files; f++) {
+        r.kmc[f].total_reads = ctx->file[f].total_reads; r.kmc[f].total_kmers = c.f[f].total_kmers;
+        r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = c.f[f].n_counted;
+    }
+    cudaEventRecord(ctx->ev_end, st);
+    if (c.best < 0) {
+        if (out) *out = r;
+        cudaEventSynchronize(ctx->ev_end);
+        return ctx->fail(BK_ERR_NO_GENOME, "Unable to pick a best genome");
+    }
+    r.n_variants = c.n_var; r.num_major_variants = c.n_major; r.num_minor_variants = c.n_minor;
+    u64 total_positions = 0;
+    for (const HostSeq& q : ctx->ix.genomes[c.best].seqs) total_positions += q.bases.size();
+    r.breadth_coverage = (double)c.pos_covered / (double)total_positions;      // src/call.rs:1144-1145
+    r.depth_coverage = (double)c.total_cov / (double)c.pos_covered;
+    u64 uc = 0, pv = 0;
+    for (int f = 0; f < n_files; f++) {
+        uc += r.kmc[f].unique_counted;
+        r.num_perfect_kmers += ctx->gstats[f][c.best].perfect; r.num_variant_kmers += ctx->gstats[f][c.best].variant;
+    }
+    pv = r.num_perfect_kmers + r.num_variant_kmers;
+    r.num_unmapped_kmers = uc - pv;                                             // src/call.rs:242, 336 (usize arithmetic)
+    ctx->variants.resize(c.n_var);
+    if (c.n_var) {
+        BK_CUDA(cudaMemcpyAsync(ctx->variants.data(), ctx->d_vars.p, (size_t)c.n_var * sizeof(bk_variant), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(ctx->ev_end, st);
+        BK_CUDA(cudaStreamSynchronize(st));
+        std::sort(ctx->variants.begin(), ctx->variants.end(), [](const bk_variant& a, const bk_variant& b) {
+            if (a.seq != b.seq) return a.seq < b.seq;
+            if (a.pos != b.pos) return a.pos < b.pos;
+            return a.alt_base < b.alt_base;
+        });
+    } else {
+        cudaEventSynchronize(ctx->ev_end);
+    }
+    // stage times
+    bk_stage_times& t = ctx->times;
+    memset(&t, 0, sizeof t);
+    float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms};
+    for (size_t i = 0; i < ctx->spans_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b) == cudaSuccess) *acc[ctx->spans[i].stage] += ms;
+    }
+    cudaEventElapsedTime(&t.total_ms, ctx->ev_begin, ctx->ev_end);
+    t.launches = ctx->launches; t.scan_launches = ctx->scan_launches;
+    if (out) *out = r;
+    return BK_OK;
+}
+
+int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out) {
+    if (!ctx || !out) return BK_ERR_ARG;
+    *out = ctx->times;
+    return BK_OK;
+}
+
+int bk_sample_variants(bk_ctx* ctx, bk_variant* out, uint64_t cap) {
+    if (!ctx || !ctx->finished) return BK_ERR_ARG;
+    if (cap < ctx->variants.size()) return ctx->fail(BK_ERR_ARG, "bk_sample_variants: buffer too small");
+    if (!ctx->variants.empty()) memcpy(out, ctx->variants.data(), ctx->variants.size() * sizeof(bk_variant));
+    return BK_OK;
+}
+
+int bk_sample_genome_stats(bk_ctx* ctx, int slot, bk_genome_stats* out) {
+    if (!ctx || !ctx->finished || slot < 0 || slot > 1 || !out) return BK_ERR_ARG;
+    if (ctx->gstats[slot].size() != ctx->d.n_genomes) return ctx->fail(BK_ERR_ARG, "no stats for file slot %d", slot);
+    memcpy(out, ctx->gstats[slot].data(), ctx->gstats[slot].size() * sizeof(bk_genome_stats));
+    return BK_OK;
+}
+
+int bk_sample_pileup(bk_ctx* ctx, int arr, uint64_t* out, uint64_t cap_rows) {
+    if (!ctx || !ctx->finished || arr < 0 || arr > 3 || !out) return BK_ERR_ARG;
+    const int best = ctx->result.best_genome;
+    if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
+    cudaSetDevice(ctx->device);
+    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_pileup: buffer too small (%u rows)", rows);
+    std::vector<u32> tmp((size_t)rows * 4);
+    BK_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_pile.p + (size_t)arr * ctx->d.max_genome_rows * 4, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < tmp.size(); i++) out[i] = tmp[i];
+    return BK_OK;
+}
+
+int bk_sample_noise_max(bk_ctx* ctx, double* out, uint64_t cap_rows) {
+    if (!ctx || !ctx->finished || !out) return BK_ERR_ARG;
+    const int best = ctx->result.best_genome;
+    if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
+    cudaSetDevice(ctx->device);
+    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_noise_max: buffer too small");
+    BK_CUDA(cudaMemcpyAsync(out, ctx->d_noise.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BK_OK;
+}
+
+int bk_kmer_counts_get(bk_ctx* ctx, int slot, uint64_t* kmers, uint32_t* counts, uint64_t* n) {
+    if (!ctx || !ctx->finished || slot < 0 || slot > 1 || !n) return BK_ERR_ARG;
+    if (!ctx->file[slot].finalized) return ctx->fail(BK_ERR_ARG, "file slot %d has no counts", slot);
+    cudaSetDevice(ctx->device);
+    const u64 have = ctx->result.kmc[slot].unique_counted;
+    if (!kmers || !counts) { *n = have; return BK_OK; }
+    if (*n < have) return ctx->fail(BK_ERR_ARG, "bk_kmer_counts_get: buffer too small");
+    *n = have;
+    if (!have) return BK_OK;
+    std::vector<u64> hk(have); std::vector<u32> hc(have);
+    BK_CUDA(cudaMemcpyAsync(hk.data(), ctx->file[slot].ckmers.p, have * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(hc.data(), ctx->file[slot].ccounts.p, have * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<u32> order(have);
+    for (u64 i = 0; i < have; i++) order[i] = (u32)i;
+    std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return hk[a] < hk[b]; });
+    for (u64 i = 0; i < have; i++) { kmers[i] = hk[order[i]]; counts[i] = hc[order[i]]; }
+    return BK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// writers — reference src/call.rs:735-774 (VCF) and 648-695 (pileup TSV)
+// ---------------------------------------------------------------------------------------------
+static bool write_all(const char* path, const std::string& s) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return false;
+    const size_t w = fwrite(s.data(), 1, s.size(), f);
+    fclose(f);
+    return w == s.size();
+}
+
+int bk_write_vcf(bk_ctx* ctx, const char* reads_path, const char* out_path) {
+    if (!ctx || !ctx->finished || !reads_path || !out_path) return BK_ERR_ARG;
+    const int best = ctx->result.best_genome;
+    if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
+    const HostGenome& g = ctx->ix.genomes[best];
+    std::string o;
+    o += "##fileformat=VCFv4.5\n##source=bronko-v0.1.0\n";
+    o += std::string("##reference=file://") + reads_path + "\n";
+    for (const HostSeq& q : g.seqs) o += "##contig=<ID=" + first_token(q.name) + ",length=" + std::to_string(q.len) + ">\n";
+    o += "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"Total Depth\">\n";
+    o += "##INFO=<ID=AF,Number=1,Type=Float,Description=\"Allele Frequency\">\n";
+    o += "##INFO=<ID=DP4,Number=4,Type=Integer,Description=\"Fwd_ref,Rev_ref,Fwd_alt,Rev_alt\">\n";
+    o += "##INFO=<ID=SOR,Number=4,Type=Float,Description=\"SOR\">\n";
+    o += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n";
+    for (const bk_variant& v : ctx->variants) {
+        o += first_token(g.seqs[v.seq].name) + "\t" + std::to_string(v.pos) + "\t.\t";
+        o += "ACGT"[v.ref_base & 3]; o += "\t"; o += "ACGT"[v.alt_base & 3];
+        o += "\t.\tPASS\tDP=" + std::to_string(v.depth) + ";AF=" + fmt_fixed(v.af, 3) + ";DP4=" + std::to_string(v.fwd_ref) + "," +
+             std::to_string(v.rev_ref) + "," + std::to_string(v.fwd_alt) + "," + std::to_string(v.rev_alt) + ";SOR=" + fmt_fixed(v.sor, 3) + "\n";
+    }
+    if (!write_all(out_path, o)) return ctx->fail(BK_ERR_IO, "Failed to create vcf output file %s", out_path);
+    return BK_OK;
+}
+
+int bk_write_pileup(bk_ctx* ctx, const char* out_path) {
+    if (!ctx || !ctx->finished || !out_path) return BK_ERR_ARG;
+    const int best = ctx->result.best_genome;
+    if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
+    const HostGenome& g = ctx->ix.genomes[best];
+    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    std::vector<u64> fw((size_t)rows * 4), rv((size_t)rows * 4);
+    int rc;
+    if ((rc = bk_sample_pileup(ctx, 0, fw.data(), rows)) || (rc = bk_sample_pileup(ctx, 1, rv.data(), rows))) return rc;
+    std::string o = "reference\tindex\tref\tA\tC\tG\tT\ta\tc\tg\tt\n";
+    size_t row = 0;
+    for (const HostSeq& q : g.seqs) {
+        for (size_t i = 0; i < q.bases.size(); i++, row++) {
+            o += q.name + "\t" + std::to_string(i + 1) + "\t"; o += (char)q.bases[i];
+            for (int b = 0; b < 4; b++) o += "\t" + std::to_string(fw[row * 4 + b]);
+            for (int b = 0; b < 4; b++) o += "\t" + std::to_string(rv[row * 4 + b]);
+            o += "\n";
+        }
+    }
+    if (!write_all(out_path, o)) return ctx->fail(BK_ERR_IO, "Failed to create tsv pileup file %s", out_path);
+    return BK_OK;
+}
+
+}  // extern "C"
