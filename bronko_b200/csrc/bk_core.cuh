@@ -20,10 +20,16 @@
 #define BK_HD __device__ __forceinline__
 #define BK_CLZLL(x) __clzll((long long)(x))
 #define BK_POPCLL(x) __popcll((unsigned long long)(x))
+#define BK_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#define BK_SYNCWARP() __syncwarp()
+#define BK_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
 #else
 #define BK_HD static inline
 #define BK_CLZLL(x) __builtin_clzll((unsigned long long)(x))
 #define BK_POPCLL(x) __builtin_popcountll((unsigned long long)(x))
+#define BK_ANY(p) (p)
+#define BK_SYNCWARP() do {} while (0)
+#define BK_FUNNEL_R(lo, hi, sh) ((sh) ? (((lo) >> (sh)) | ((hi) << (32 - (sh)))) : (lo))
 struct uint2 { unsigned int x, y; };
 static inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 r; r.x = x; r.y = y; return r; }
 #endif
@@ -66,28 +72,20 @@ BK_HD u32 load_unaligned(const Ld& ld, u32 byte_off) {
     return (lo >> sh) | (hi << (32 - sh));
 }
 
-// 32 bases starting at byte_off (nb = how many of them belong to the read, 1..32) → 64 packed bits
-// MSB-first; *bad != 0 iff one of the nb bytes is not ACGT.  Bits of bases >= nb are zero.
+// 32 bases starting at byte_off, all of them inside the read → 64 packed bits MSB-first; *bad != 0 iff
+// one of the 32 bytes is not ACGT.  Branch-free: 9 aligned word loads, 8 funnel shifts, 8 pack4.
+// (Reads up to 7 bytes past the 32 bases: buffers carry >= 16 bytes of slack.)
 template <class Ld>
-BK_HD u64 pack32(const Ld& ld, u32 byte_off, u32 nb, u32* bad) {
+BK_HD u64 pack32_full(const Ld& ld, u32 byte_off, u32* bad) {
     const u32 wi = byte_off >> 2, sh = (byte_off & 3) * 8;
-    u32 prev = ld(wi);
+    u32 w[9];
+#pragma unroll
+    for (u32 i = 0; i < 9; i++) w[i] = ld(wi + i);
     u32 hi32 = 0, lo32 = 0, acc = 0;
-    const u32 nwords = (nb + 3) >> 2;
 #pragma unroll
     for (u32 i = 0; i < 8; i++) {
-        u32 w = 0;
-        if (i < nwords) {
-            if (sh) { const u32 nxt = ld(wi + i + 1); w = (prev >> sh) | (nxt << (32 - sh)); prev = nxt; }
-            else { w = prev; prev = ld(wi + i + 1); }
-        }
         u32 err;
-        u32 p = pack4(w, &err);
-        if (nb < 32) {                     // tail word: ignore bytes past the end of the read
-            const i32 vb = (i32)nb - (i32)(4 * i);
-            if (vb <= 0) { err = 0; p = 0; }
-            else if (vb < 4) { err &= (1u << (8 * vb)) - 1u; p &= 0xFFu << (8 - 2 * vb); }
-        }
+        const u32 p = pack4(BK_FUNNEL_R(w[i], w[i + 1], sh), &err);
         acc |= err;
         if (i < 4) hi32 |= p << (24 - 8 * i); else lo32 |= p << (56 - 8 * i);
     }
@@ -95,12 +93,40 @@ BK_HD u64 pack32(const Ld& ld, u32 byte_off, u32 nb, u32* bad) {
     return ((u64)hi32 << 32) | lo32;
 }
 
+// Same for the last word of a read: nb (1..31) bases belong to the read; bits of bases >= nb are zero
+// and bytes past the read never count as bad.
+template <class Ld>
+BK_HD u64 pack32_tail(const Ld& ld, u32 byte_off, u32 nb, u32* bad) {
+    const u32 wi = byte_off >> 2, sh = (byte_off & 3) * 8;
+    u32 prev = ld(wi);
+    u32 hi32 = 0, lo32 = 0, acc = 0;
+    const u32 nwords = (nb + 3) >> 2;
+    for (u32 i = 0; i < nwords; i++) {
+        const u32 nxt = ld(wi + i + 1);
+        const u32 w = BK_FUNNEL_R(prev, nxt, sh);
+        prev = nxt;
+        u32 err;
+        u32 p = pack4(w, &err);
+        const u32 vb = nb - 4 * i;
+        if (vb < 4) { err &= (1u << (8 * vb)) - 1u; p &= 0xFFu << (8 - 2 * vb); }
+        acc |= err;
+        if (i < 4) hi32 |= p << (24 - 8 * i); else lo32 |= p << (56 - 8 * i);
+    }
+    *bad = acc;
+    return ((u64)hi32 << 32) | lo32;
+}
+
+template <class Ld>
+BK_HD u64 pack32(const Ld& ld, u32 byte_off, u32 nb, u32* bad) {
+    return nb >= 32 ? pack32_full(ld, byte_off, bad) : pack32_tail(ld, byte_off, nb, bad);
+}
+
 // k bases starting at byte_off → k-mer value (first base most significant, src/lcb.rs:67-74);
 // returns false if a byte is not ACGT.
 template <class Ld>
 BK_HD bool pack_kmer(const Ld& ld, u32 byte_off, u32 k, u64* out) {
     u32 bad;
-    const u64 v = pack32(ld, byte_off, k, &bad);
+    const u64 v = pack32_tail(ld, byte_off, k, &bad);
     *out = v >> (64 - 2 * k);
     return bad == 0;
 }
@@ -193,13 +219,26 @@ BK_HD u32 count_stretch(const CountView& v, const Ld& ld, u32 byte_off, u32 cnt,
     return created;
 }
 
-// Leftover stretch: k-mers starting at read bases [a, a+cnt) of the read at byte offset o0.
-// gofs = byte offset of the word source inside the pushed buffer (descriptors use buffer offsets).
-template <class Ld>
-BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt, u32 gofs) {
+// Leftover stretches of one read wait here until the caller flushes them (one warp-aggregated atomic
+// per warp on the device).  More than two per read are rare and go to the queue directly.
+struct Pending { u32 n; uint2 d0, d1; };
+
+BK_HD void queue_push(const CountView& v, uint2 d, u32* overflow) {
     const u32 slot = fetch_add_u32(v.n_desc, 1u);
-    if (slot < v.desc_cap) { v.desc[slot] = make_uint2(gofs + o0 + a, cnt); return 0; }
-    return count_stretch(v, ld, o0 + a, cnt, 0, 1);   // queue full: count in place (slow, still exact)
+    if (slot < v.desc_cap) v.desc[slot] = d; else *overflow = 1;
+}
+
+// Leftover stretch: k-mers starting at read bases [a, a+cnt) of the read at byte offset o0 of the word
+// source, which itself starts gofs bytes into the pushed buffer (descriptors use buffer offsets).
+// Returns new novel keys if the queue was full and the stretch had to be counted in place.
+template <class Ld>
+BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt, u32 gofs, Pending& pend) {
+    const uint2 d = make_uint2(gofs + o0 + a, cnt);
+    if (pend.n == 0) { pend.d0 = d; pend.n = 1; return 0; }
+    if (pend.n == 1) { pend.d1 = d; pend.n = 2; return 0; }
+    u32 overflow = 0;
+    queue_push(v, d, &overflow);
+    return overflow ? count_stretch(v, ld, o0 + a, cnt, 0, 1) : 0;     // queue full: count in place (slow, exact)
 }
 
 BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
@@ -217,8 +256,10 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 #define BK_BAIL_MISMATCHES 8  // this many bad bases inside one 32-base word ends the diagonal
 #endif
 
-// One read: bytes [o0, o0+len) of the word source (which starts gofs bytes into the pushed buffer).  Returns number of new novel keys created by the
-// in-place fallback (normally 0).
+// One read: bytes [o0, o0+len) of the word source.  On the device EVERY lane of the warp must call
+// this (lanes without a read pass len = 0): the loops run a warp-uniform number of rounds and
+// reconverge after every round, so a mismatch in one lane's read does not split the warp for the
+// rest of the read.  Returns the number of novel keys created by in-place fallbacks (normally 0).
 //
 // State: k-mers are indexed by their start base.  `c` = first k-mer start not classified yet (every
 // k-mer below c has been put in a run or a leftover stretch), `ms` = start of the current stretch of
@@ -226,83 +267,104 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 // overlap with the oriented sequence, end of read) closes the stretch [ms, e): if it holds >= k bases
 // its k-mers [ms, e-k] become a run, everything pending before ms a leftover stretch.
 template <class Ld, class LdRef>
-BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len, u32 gofs) {
+BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len, u32 gofs, Pending& pend) {
     const u32 k = v.k;
-    if (len < k) return 0;                       // shorter than k: contributes no k-mer
-    const u32 nk = len - k + 1;
+    const bool has = len >= k;                   // shorter than k: contributes no k-mer
+    const u32 nk = has ? len - k + 1 : 0;
     u32 created = 0;
     i32 c = 0;
     i32 seed_from = 0;
+    bool active = has;                           // still looking for / following a diagonal
     for (u32 diag = 0; diag < BK_MAX_DIAGS; diag++) {
+        if (!BK_ANY(active)) break;
+        // ---- seed: first k-mer at or after seed_from that is an exact reference k-mer ----
         u32 gidx = 0, oseq = 0, q = (u32)seed_from;
         bool found = false;
-        for (u32 t = 0; t < BK_MAX_SEEDS && q + k <= len; t++, q += k) {
-            u64 km;
-            if (!pack_kmer(ld, o0 + q, k, &km)) continue;
-            if (exact_lookup(v, km, &gidx, &oseq)) { found = true; break; }
+        for (u32 t = 0; t < BK_MAX_SEEDS; t++) {
+            const bool need = active && !found && q + k <= len;
+            if (!BK_ANY(need)) break;
+            if (need) {
+                u64 km;
+                if (pack_kmer(ld, o0 + q, k, &km) && exact_lookup(v, km, &gidx, &oseq)) found = true;
+                else q += k;
+            }
+            BK_SYNCWARP();
         }
-        if (!found) break;
-        const i32 g0 = (i32)gidx - (i32)q;       // global base index of read base 0 on this diagonal
-        const i32 os = (i32)v.oseq_start[oseq], oe = os + (i32)v.oseq_len[oseq];
-        i32 i_lo = os > g0 ? os - g0 : 0;                                  // read bases inside the
-        const i32 i_hi = (oe - g0) < (i32)len ? (oe - g0) : (i32)len;      // oriented sequence
-        if (i_lo < seed_from) i_lo = seed_from;
-        i32 ms = i_lo;
+        if (!found) active = false;              // no seed: what is left of the read is leftover
+        // ---- extend along the diagonal, 32 bases per round ----
+        i32 g0 = 0, i_lo = 0, i_hi = 0, ms = 0, w = 0, w_end = 0;
+        if (active) {
+            g0 = (i32)gidx - (i32)q;             // global base index of read base 0 on this diagonal
+            const i32 os = (i32)v.oseq_start[oseq], oe = os + (i32)v.oseq_len[oseq];
+            i_lo = os > g0 ? os - g0 : 0;                              // read bases inside the
+            i_hi = (oe - g0) < (i32)len ? (oe - g0) : (i32)len;        // oriented sequence
+            if (i_lo < seed_from) i_lo = seed_from;
+            ms = i_lo;
+            w = i_lo >> 5;
+            w_end = (i_hi + 31) >> 5;
+        }
         bool bailed = false;
-#define BK_EVENT(e_)                                                                      \
-    do {                                                                                  \
-        const i32 e__ = (e_);                                                             \
-        if (e__ - ms >= (i32)k) {                                                         \
-            if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c), gofs);       \
-            emit_run(v, g0, (u32)ms, (u32)(e__ - (i32)k + 1 - ms));                       \
-            c = e__ - (i32)k + 1;                                                         \
-        }                                                                                 \
-        ms = e__ + 1;                                                                     \
+#define BK_EVENT(e_)                                                                        \
+    do {                                                                                    \
+        const i32 e__ = (e_);                                                               \
+        if (e__ - ms >= (i32)k) {                                                           \
+            if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c), gofs, pend); \
+            emit_run(v, g0, (u32)ms, (u32)(e__ - (i32)k + 1 - ms));                         \
+            c = e__ - (i32)k + 1;                                                           \
+        }                                                                                   \
+        ms = e__ + 1;                                                                       \
     } while (0)
-        for (i32 w = i_lo >> 5; 32 * w < i_hi; w++) {
-            const i32 b0 = 32 * w;
-            const u32 nb = (u32)((i32)len - b0 < 32 ? (i32)len - b0 : 32);
-            u32 bad;
-            const u64 rd = pack32(ld, o0 + (u32)b0, nb, &bad);
-            const u64 rf = ref_word(ldr, g0 + b0, v.ref_words);
-            u64 x = rd ^ rf;
-            const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
-            const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
-            u64 mask = ~0ull;
-            if (lo > 0) mask &= ~0ull >> (2 * lo);
-            if (hi < 32) mask &= ~(~0ull >> (2 * hi));
-            x &= mask;
-            if ((x | bad) == 0) continue;        // the common case: 32 bases extend the run
-            u64 t = (x | (x >> 1)) & 0x5555555555555555ull;
-            if (bad) {                           // rare: flag all 4 bases of a word holding a non-ACGT byte
-                for (u32 i = 0; i < 8 && 4 * i < nb; i++) {
-                    u32 err;
-                    const u32 nbi = nb - 4 * i;
-                    const u32 wv = load_unaligned(ld, o0 + (u32)b0 + 4 * i);
-                    (void)pack4(wv, &err);
-                    if (nbi < 4) err &= (1u << (8 * nbi)) - 1u;
-                    if (err) t |= 0x55ull << (56 - 8 * i);
+        for (;;) {
+            const bool go = active && !bailed && w < w_end;
+            if (!BK_ANY(go)) break;
+            if (go) {
+                const i32 b0 = 32 * w;
+                const u32 nb = (u32)((i32)len - b0 < 32 ? (i32)len - b0 : 32);
+                u32 bad;
+                const u64 rd = pack32(ld, o0 + (u32)b0, nb, &bad);
+                const u64 rf = ref_word(ldr, g0 + b0, v.ref_words);
+                u64 x = rd ^ rf;
+                const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
+                const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
+                u64 mask = ~0ull;
+                if (lo > 0) mask &= ~0ull >> (2 * lo);
+                if (hi < 32) mask &= ~(~0ull >> (2 * hi));
+                x &= mask;
+                if ((x | bad) != 0) {                // the uncommon case: something in these 32 bases is off
+                    u64 t = (x | (x >> 1)) & 0x5555555555555555ull;
+                    if (bad) {                       // flag all 4 bases of a word holding a non-ACGT byte
+                        for (u32 i = 0; i < 8 && 4 * i < nb; i++) {
+                            u32 err;
+                            const u32 nbi = nb - 4 * i;
+                            const u32 wv = load_unaligned(ld, o0 + (u32)b0 + 4 * i);
+                            (void)pack4(wv, &err);
+                            if (nbi < 4) err &= (1u << (8 * nbi)) - 1u;
+                            if (err) t |= 0x55ull << (56 - 8 * i);
+                        }
+                        t &= mask;
+                    }
+                    if (BK_POPCLL(t) >= BK_BAIL_MISMATCHES) {   // wrong diagonal from here on: close, re-seed
+                        const u32 p = 63 - (u32)BK_CLZLL(t);
+                        const i32 e = b0 + (i32)(31 - (p >> 1));
+                        BK_EVENT(e);
+                        seed_from = e + 1;
+                        bailed = true;
+                    } else {
+                        while (t) {
+                            const u32 p = 63 - (u32)BK_CLZLL(t);
+                            t ^= 1ull << p;
+                            BK_EVENT(b0 + (i32)(31 - (p >> 1)));
+                        }
+                    }
                 }
-                t &= mask;
+                w++;
             }
-            if (BK_POPCLL(t) >= BK_BAIL_MISMATCHES) {   // wrong diagonal from here on: close and re-seed
-                const u32 p = 63 - (u32)BK_CLZLL(t);
-                const i32 e = b0 + (i32)(31 - (p >> 1));
-                BK_EVENT(e);
-                seed_from = e + 1;
-                bailed = true;
-                break;
-            }
-            while (t) {
-                const u32 p = 63 - (u32)BK_CLZLL(t);
-                t ^= 1ull << p;
-                BK_EVENT(b0 + (i32)(31 - (p >> 1)));
-            }
+            BK_SYNCWARP();
         }
-        if (!bailed) { BK_EVENT(i_hi); break; }
+        if (active && !bailed) { BK_EVENT(i_hi); active = false; }
 #undef BK_EVENT
     }
-    if ((i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c, gofs);
+    if (has && (i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c, gofs, pend);
     return created;
 }
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,14 +84,14 @@ struct bk_ctx {
     Counters* h_ctr = nullptr;              // pinned
     DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
-    DevBuf<double> d_maf, d_msq, d_st_s, d_st_s2, d_st_max, d_noise;
-    DevBuf<u32> d_st_n;
+    DevBuf<double> d_noise, d_noise_vers;
     DevBuf<bk_variant> d_vars;
     // staging for host pushes (double buffered)
     DevBuf<u8> d_stage[2]; DevBuf<u32> d_stage_off;
     cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
     int stage_next = 0;
     u32 shard_rank = 0, shard_n = 1;
+    bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
 
     // results
     bk_sample_result result;
@@ -168,11 +169,13 @@ int bk_create(bk_ctx** out, int device) {
         ok = cudaMemcpyToSymbol(c_tau, tau, sizeof tau) == cudaSuccess;
     }
     if (ok) ok = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_map<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+                 cudaFuncSetAttribute(k_map<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_noise, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NOISE_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
     memset(&ctx->result, 0, sizeof ctx->result);
     bk_params_default(&ctx->params);
+    ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     *out = ctx;
     return BK_OK;
 }
@@ -187,8 +190,7 @@ void bk_destroy(bk_ctx* ctx) {
     ctx->d_ref_code.release();
     for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); }
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
-    ctx->d_maf.release(); ctx->d_msq.release(); ctx->d_st_s.release(); ctx->d_st_s2.release(); ctx->d_st_max.release();
-    ctx->d_noise.release(); ctx->d_st_n.release(); ctx->d_vars.release();
+    ctx->d_noise.release(); ctx->d_noise_vers.release(); ctx->d_vars.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < 2; i++) { if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]); if (ctx->stage_copied[i]) cudaEventDestroy(ctx->stage_copied[i]); }
@@ -253,9 +255,8 @@ static int upload_index(bk_ctx* ctx) {
     for (u32 g = 0; g < d.n_genomes; g++) ctx->max_seqs_per_genome = std::max(ctx->max_seqs_per_genome, d.genome_seq_off[g + 1] - d.genome_seq_off[g]);
     const size_t rows = std::max<u32>(d.max_genome_rows, 1);
     BK_CUDA(ctx->d_pile.reserve(rows * 16));
-    BK_CUDA(ctx->d_maf.reserve(rows * 3)); BK_CUDA(ctx->d_msq.reserve(rows * 3));
-    BK_CUDA(ctx->d_st_n.reserve(rows)); BK_CUDA(ctx->d_st_s.reserve(rows)); BK_CUDA(ctx->d_st_s2.reserve(rows));
-    BK_CUDA(ctx->d_st_max.reserve(rows * BK_NOISE_TABLE)); BK_CUDA(ctx->d_noise.reserve(rows));
+    BK_CUDA(ctx->d_noise.reserve(rows));
+    BK_CUDA(ctx->d_noise_vers.reserve((size_t)ctx->max_seqs_per_genome * BK_NOISE_VERS * BK_NOISE_TABLE));
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
     BK_CUDA(ctx->d_bsum.reserve(((size_t)d.n_raw + 2 + BK_PS_BLOCK - 1) / BK_PS_BLOCK + 1));
@@ -391,9 +392,9 @@ static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
     FileState& f = ctx->file[slot];
     if (f.used) return BK_OK;
     u32 lg = ctx->params.table_log2;
-    if (lg == 0) {            // auto: ~1 slot per 16 read bases of this first push, clamped to [2^22, 2^27]
+    if (lg == 0) {            // auto: ~1 slot per 32 read bases of this first push, clamped to [2^22, 2^27]
         lg = 22;
-        while (lg < 27 && (1ull << lg) < bases_hint / 16) lg++;
+        while (lg < 27 && (1ull << lg) < bases_hint / 32) lg++;
     }
     f.gen_log2 = lg;
     BK_CUDA(f.gen.reserve(1ull << lg));
@@ -566,22 +567,25 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     const MapView m = make_map_view(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
     const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
+    const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
     Counters* dc = ctx->d_ctr.p;
     int sp = ctx->span_begin(ST_MAP);
     BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
-        k_map<0><<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu),
-                                                           fs.gstats.p, nullptr, nullptr, 0);
+        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+        if (small_db) k_map_small<0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        else k_map<0><<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
     k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
     ctx->launches++;
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
-        k_map<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu),
-                                                    nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+        if (small_db) k_map_small<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        else k_map<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         ctx->launches++;
     }
     ctx->span_end(sp);
@@ -592,9 +596,7 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
     sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
     const u32 row_blocks = (d.max_genome_rows + 255) / 256;
-    k_noise_prep<<<row_blocks, 256, 0, st>>>(sv, ctx->d_maf.p, ctx->d_msq.p);
-    k_noise_seq<<<ctx->max_seqs_per_genome, 64, 0, st>>>(sv, ctx->d_maf.p, ctx->d_msq.p, ctx->d_st_n.p, ctx->d_st_s.p, ctx->d_st_s2.p, ctx->d_st_max.p);
-    k_noise_tau<<<row_blocks, 256, 0, st>>>(sv, ctx->d_st_n.p, ctx->d_st_s.p, ctx->d_st_s2.p, ctx->d_st_max.p, ctx->d_noise.p);
+    k_noise<<<ctx->max_seqs_per_genome, BK_NOISE_THREADS, BK_NOISE_SMEM, st>>>(sv, ctx->d_noise.p, ctx->d_noise_vers.p);
     CallParams cp;
     const bk_params& p = ctx->params;
     cp.k = p.k; cp.no_end_filter = p.no_end_filter; cp.no_strand_filter = p.no_strand_filter;
@@ -603,7 +605,7 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     cp.strand_balance_ratio = p.strand_balance_ratio; cp.strand_odds_max = p.strand_odds_max; cp.variant_multiplier = p.variant_multiplier;
     k_call<<<row_blocks, 256, 0, st>>>(sv, cp, ctx->d_noise.p, ctx->d_vars.p, (u32)std::min<size_t>(ctx->d_vars.cap, 0xFFFFFFFFu), dc);
     ctx->span_end(sp);
-    ctx->launches += 4;
+    ctx->launches += 2;
     BK_CUDA(cudaGetLastError());
 
     BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -4,7 +4,7 @@
 //              k_diff_* (prefix sum + fold onto distinct reference k-mers), k_compact_* (the "KMC dump")
 //  mapping   : k_map<STATS|PILEUP>   — reference src/call.rs:1257-1434
 //  selection : k_select               — src/call.rs:422-502
-//  scoring   : k_noise_prep / k_noise_seq / k_noise_tau — src/call.rs:799-967 ; k_call — src/call.rs:969-1150
+//  scoring   : k_noise — src/call.rs:799-967 ; k_call — src/call.rs:969-1150
 #pragma once
 #include <cuda_runtime.h>
 
@@ -52,6 +52,26 @@ __device__ __forceinline__ u32 warp_append(u32* counter, bool pred) {
 //   bases + off_bias-relative offsets: read r = bytes [off[r]-off_bias, off[r+1]-off_bias) of `bases`.
 // ------------------------------------------------------------------------------------------------
 #define BK_SCAN_THREADS 256
+
+// Flush the leftover stretches the lanes of this warp collected for their reads: one atomic per warp
+// reserves the queue slots.  If the queue is full the stretch is counted in place (slow, still exact).
+template <class Ld>
+__device__ __forceinline__ u32 flush_pending(const CountView& v, const Ld& ld, const Pending& pend, u32 gofs) {
+    const u32 lane = threadIdx.x & 31;
+    u32 incl = pend.n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += t; }
+    const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return 0;
+    u32 base = 0;
+    if (lane == 31) base = atomicAdd(v.n_desc, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - pend.n;
+    u32 created = 0;
+    if (pend.n > 0) { if (base < v.desc_cap) v.desc[base] = pend.d0; else created += count_stretch(v, ld, pend.d0.x - gofs, pend.d0.y, 0, 1); }
+    if (pend.n > 1) { if (base + 1 < v.desc_cap) v.desc[base + 1] = pend.d1; else created += count_stretch(v, ld, pend.d1.x - gofs, pend.d1.y, 0, 1); }
+    return created;
+}
+
 __global__ void __launch_bounds__(BK_SCAN_THREADS)
 k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u32 off_bias, u32 r_begin, u32 r_end,
        u32 tile_reads, u32 tile_bytes, u32* gen_new) {
@@ -67,8 +87,9 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
         const u32 e = (__ldg(off + r1) - off_bias + 15u) & ~15u;
         const bool staged = (e - a) <= tile_bytes;          // uniform over the CTA
         const u32 r = r0 + threadIdx.x;
-        u32 o0 = 0, len = 0;
+        u32 o0 = 0, len = 0;                                 // lanes without a read scan an empty one
         if (r < r1) { o0 = __ldg(off + r) - off_bias; len = __ldg(off + r + 1) - off_bias - o0; }
+        Pending pend; pend.n = 0; pend.d0 = make_uint2(0, 0); pend.d1 = make_uint2(0, 0);
         if (staged) {
             __syncthreads();                                 // previous tile fully consumed
             const uint4* src = reinterpret_cast<const uint4*>(bases + a);
@@ -81,15 +102,15 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
                 dst[i] = q;
             }
             __syncthreads();
-            if (r < r1) {
-                const u32* sw = reinterpret_cast<const u32*>(smem);
-                auto ld = [sw](u32 i) { return sw[i]; };
-                created += scan_read(v, ld, ldr, o0 - a, len, a);
-            }
-        } else if (r < r1) {
+            const u32* sw = reinterpret_cast<const u32*>(smem);
+            auto ld = [sw](u32 i) { return sw[i]; };
+            created += scan_read(v, ld, ldr, r < r1 ? o0 - a : 0u, len, a, pend);
+            created += flush_pending(v, ld, pend, a);
+        } else {
             const u32* gw = reinterpret_cast<const u32*>(bases);
             auto ld = [gw](u32 i) { return __ldg(gw + i); };
-            created += scan_read(v, ld, ldr, o0, len, 0);
+            created += scan_read(v, ld, ldr, o0, len, 0, pend);
+            created += flush_pending(v, ld, pend, 0);
         }
     }
     created = warp_sum_u32(created);
@@ -208,13 +229,33 @@ __global__ void __launch_bounds__(256) k_compact_ids(CompactArgs a, const u32* _
     if ((threadIdx.x & 31) == 0 && uniq) { atomicAdd(&a.fc->unique, uniq); atomicAdd((unsigned long long*)&a.fc->total_kmers, (unsigned long long)total); }
 }
 
+// The novel table is big (millions of slots) and most warps hold a kept k-mer, so the output slots are
+// reserved once per CTA round (1024 table slots) instead of once per warp: one hot atomic address
+// would otherwise serialise the whole kernel.
 __global__ void __launch_bounds__(256) k_compact_gen(CompactArgs a, const GenSlot* __restrict__ gen, u32 n_slots) {
-    const u32 stride = gridDim.x * blockDim.x;
+    __shared__ u32 s_base;
     u32 uniq = 0; u64 total = 0;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {   // n_slots is a power of two >= 1024
-        const uint4 s = __ldg(reinterpret_cast<const uint4*>(gen) + i);
-        const u64 key = ((u64)s.y << 32) | s.x;
-        compact_emit(a, key != BK_EMPTY, key, s.z, true, uniq, total);
+    for (u32 base = blockIdx.x * 1024u; base < n_slots; base += gridDim.x * 1024u) {   // n_slots: power of two >= 1024
+        u64 key[4]; u32 cnt[4]; bool keep[4];
+        u32 mine = 0;
+#pragma unroll
+        for (u32 q = 0; q < 4; q++) {
+            const uint4 sl = __ldg(reinterpret_cast<const uint4*>(gen) + base + q * 256u + threadIdx.x);
+            key[q] = ((u64)sl.y << 32) | sl.x; cnt[q] = sl.z;
+            const bool have = key[q] != BK_EMPTY;
+            if (have) { uniq++; total += cnt[q]; }
+            keep[q] = have && cnt[q] >= a.ci && cnt[q] <= 1000000000u;
+            mine += keep[q] ? 1u : 0u;
+        }
+        u32 tot;
+        u32 o = block_excl_scan_256(mine, &tot);
+        if (threadIdx.x == 0) s_base = tot ? atomicAdd(&a.fc->n_counted, tot) : 0u;
+        __syncthreads();
+        o += s_base;
+#pragma unroll
+        for (u32 q = 0; q < 4; q++)
+            if (keep[q]) { if (o < a.out_cap) { a.out_kmers[o] = key[q]; a.out_counts[o] = min(cnt[q], a.cs); } o++; }
+        __syncthreads();
     }
     uniq = warp_sum_u32(uniq); total = warp_sum_u64(total);
     if ((threadIdx.x & 31) == 0 && uniq) { atomicAdd(&a.fc->unique, uniq); atomicAdd((unsigned long long*)&a.fc->total_kmers, (unsigned long long)total); }
@@ -339,6 +380,113 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
     }
 }
 
+// k_map_small — the same computation with ONE THREAD per counted k-mer, for databases of at most four
+// genomes (per-genome hit counts fit four 16-bit fields of a register).  The bucket ids come from the
+// incremental form of src/lcb.rs:1-45 (two passes over the k digits, u64 wrap-around), each queried
+// bucket is probed as soon as its id is known.  ~25x fewer warp instructions per k-mer than the
+// warp-per-k-mer kernel; the counted list keeps reference k-mers and novel k-mers in separate runs,
+// so warps stay homogeneous.
+template <int PILEUP>
+__global__ void __launch_bounds__(256)
+k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
+            u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
+    const u32 n = min(*n_ptr, n_cap);
+    const u32 k = m.k;
+    const u32 lane = threadIdx.x & 31;
+    i32 best = -1; u32 g_row0 = 0;
+    if (PILEUP) {
+        best = *best_ptr;
+        if (best < 0) return;
+        g_row0 = m.genome_row0[best];
+    }
+    const u32 nb = m.b1 - m.b0;
+    u32 acc[12];                      // lane 0: [g*3 + {perfect, variant, unique}] ; presence = any of them
+#pragma unroll
+    for (u32 i = 0; i < 12; i++) acc[i] = 0;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (n + 31) & ~31u;
+    for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+        const bool live = t < n;
+        u64 hits4 = 0;                // 4 x 16-bit per-genome hit counts (saturating is unnecessary: <= 31*entries)
+        if (live) {
+            const u64 fwd = kmers[t];
+            const u32 cnt = counts[t];
+            const u64 rev = revcomp_dev(fwd, k);
+            const bool rc = !(fwd < rev);
+            const u64 kb = rc ? rev : fwd;
+            // pass 1: sum of mu
+            u64 mask = 3ull << (2 * (k - 1)), p = 1ull << (2 * (k - 1));
+            u64 val = kb, sum_mu = 0;
+            for (u32 i = 0; i < k; i++) {
+                const u64 cur = kb & mask;
+                val -= cur;
+                sum_mu += cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val;
+                mask >>= 2; p >>= 2;
+            }
+            // pass 2: ids of the queried buckets, probe, walk entries
+            mask = 3ull << (2 * (k - 1)); p = 1ull << (2 * (k - 1));
+            val = kb;
+            u64 num_a = 0;
+            for (u32 i = 0; i < m.b1; i++) {
+                const u64 cur = kb & mask;
+                val -= cur;
+                if (i >= m.b0) {
+                    const u64 mu = cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val;
+                    const u64 bucket = sum_mu - mu + val - num_a * cur + 1 + num_a;
+                    u32 h = hash_slot(bucket, m.shift);
+                    u32 off = 0, len = 0;
+                    for (;;) {
+                        const uint4 sl = __ldg(reinterpret_cast<const uint4*>(m.slots) + h);
+                        const u64 key = ((u64)sl.y << 32) | sl.x;
+                        if (key == bucket) { off = sl.z; len = sl.w; break; }
+                        if (key == BK_EMPTY) break;
+                        h = (h + 1) & m.mask;
+                    }
+                    for (u32 j = 0; j < len; j++) {
+                        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+                        const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
+                        if (row == 0xFFFFFFFFu) continue;
+                        if (!PILEUP) {
+                            hits4 += 1ull << (16 * file_id);                  // src/call.rs:1316-1318
+                        } else if ((i32)file_id == best) {
+                            u32 bit; bool to_fwd;
+                            if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
+                            else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
+                            const u32 cell = (row + idx - g_row0) * 4 + bit;
+                            atomicAdd(pile + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
+                            atomicMax(pile + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
+                        }
+                    }
+                }
+                num_a += (cur == 0) ? 1 : 0;
+                mask >>= 2; p >>= 2;
+            }
+        }
+        if (!PILEUP) {                                                       // src/call.rs:1389-1419
+            u32 n_perfect = 0;
+#pragma unroll
+            for (u32 g = 0; g < 4; g++) n_perfect += (((hits4 >> (16 * g)) & 0xFFFFu) == nb && nb != 0) ? 1u : 0u;
+#pragma unroll
+            for (u32 g = 0; g < 4; g++) {
+                const u32 h = (u32)((hits4 >> (16 * g)) & 0xFFFFu);
+                const bool perfect = h != 0 && h == nb;
+                const u32 mp = __ballot_sync(0xFFFFFFFFu, perfect);
+                const u32 mv = __ballot_sync(0xFFFFFFFFu, h != 0 && !perfect);
+                const u32 mu_ = __ballot_sync(0xFFFFFFFFu, perfect && n_perfect == 1);
+                if (lane == 0) { acc[g * 3] += __popc(mp); acc[g * 3 + 1] += __popc(mv); acc[g * 3 + 2] += __popc(mu_); }
+            }
+        }
+    }
+    if (!PILEUP && lane == 0) {
+        for (u32 g = 0; g < m.n_genomes && g < 4; g++) {
+            if (acc[g * 3]) atomicAdd(gstats + g * 4, acc[g * 3]);
+            if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
+            if (acc[g * 3 + 2]) atomicAdd(gstats + g * 4 + 2, acc[g * 3 + 2]);
+            if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
+        }
+    }
+}
+
 // k_select — pick_best_genome / pick_best_genome_paired (src/call.rs:422-502): argmax of
 // perfect / genome_len / 2.0 with strict '>' from 0.0; ties keep the lowest file index (the
 // reference's tie order is FxHashMap iteration order, unpinned).
@@ -358,11 +506,8 @@ __global__ void k_select(const u32* gstats0, const u32* gstats1, u32 n_files, u3
 // ------------------------------------------------------------------------------------------------
 // Noise baseline, src/call.rs:799-967 (quirks: SURVEY.md Appendix C, Q12).  The reference is one
 // sequential loop; here it is split so that only what is inherently sequential runs on one thread:
-//   k_noise_prep : per position, sorted minor-allele fractions (and their squares)      [parallel]
-//   k_noise_seq  : the running n / s / s2 sums (exact same addition order, FP64, no FMA) on one
-//                  thread and the 10-entry max table (with its evict-by-value quirk) on another,
-//                  snapshotting both for every output position                          [sequential]
-//   k_noise_tau  : the Thompson-tau rejection loop per position from the snapshots      [parallel]
+// (k_noise below: fractions in parallel, the two state chains on two threads out of shared memory,
+// the Thompson-tau loop in parallel).
 // ------------------------------------------------------------------------------------------------
 struct ScoreView {
     u32 n_genomes; const u32* genome_row0; const u32* genome_seq_off; const u32* seq_row0;
@@ -370,144 +515,203 @@ struct ScoreView {
     const u32* pile; u32 pile_stride;
 };
 
-__global__ void __launch_bounds__(256) k_noise_prep(ScoreView sv, double* maf, double* msq) {
-    const i32 best = sv.ctr->best;
-    if (best < 0) return;
-    const u32 rows = sv.genome_row0[best + 1] - sv.genome_row0[best];
-    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    const uint4 f = *reinterpret_cast<const uint4*>(sv.pile + row * 4);
-    const uint4 r = *reinterpret_cast<const uint4*>(sv.pile + sv.pile_stride + row * 4);
-    u64 c0 = (u64)f.x + r.x, c1 = (u64)f.y + r.y, c2 = (u64)f.z + r.z, c3 = (u64)f.w + r.w;
-    u64 t;
-#define BK_CSWAP(a, b) if (a < b) { t = a; a = b; b = t; }
-    BK_CSWAP(c0, c1) BK_CSWAP(c2, c3) BK_CSWAP(c0, c2) BK_CSWAP(c1, c3) BK_CSWAP(c1, c2)
-#undef BK_CSWAP
-    const u64 total = c0 + c1 + c2 + c3;
-    double m1 = 0.0, m2 = 0.0, m3 = 0.0;
-    if (total != 0) { const double td = (double)total; m1 = (double)c1 / td; m2 = (double)c2 / td; m3 = (double)c3 / td; }
-    maf[row * 3 + 0] = m1; maf[row * 3 + 1] = m2; maf[row * 3 + 2] = m3;
-    msq[row * 3 + 0] = __dmul_rn(m1, m1); msq[row * 3 + 1] = __dmul_rn(m2, m2); msq[row * 3 + 2] = __dmul_rn(m3, m3);
-}
-
 #define BK_NOISE_WINDOW 100
 #define BK_NOISE_HALF 50
 #define BK_NOISE_TABLE 10
+#define BK_NOISE_TILE 512
+#define BK_NOISE_THREADS 256
+// dynamic shared memory of k_noise, bytes
+#define BK_NOISE_SMEM ((BK_NOISE_TILE + BK_NOISE_WINDOW) * 3 * 8 + BK_NOISE_TILE * (8 + 8 + 4) + 16)
+// table versions a tile can create (one per window update at most) + the one it starts with
+#define BK_NOISE_VERS (BK_NOISE_TILE * 3 + 1)
 
-__global__ void __launch_bounds__(64)
-k_noise_seq(ScoreView sv, const double* __restrict__ maf, const double* __restrict__ msq,
-            u32* st_n, double* st_s, double* st_s2, double* st_max) {
+__constant__ double c_tau[301];
+
+// One CTA per sequence of the selected genome; the iteration space i in [0, len+50) of the reference
+// loop is walked in tiles of BK_NOISE_TILE:
+//   phase 1 (all threads)  sorted minor-allele fractions of positions [t0-100, t0+T) into shared memory
+//   phase 2 (three warps)  warp 0 / lane 0: s, warp 1 / lane 0: s2 — the reference's exact operation order
+//                          (FP64, no FMA; adding or subtracting an exact +0.0 where the reference skips the
+//                          update leaves every bit unchanged, so the chains are branch-free);
+//                          warp 2 (all lanes): the 10-entry max table with its evict-by-value quirk — 32
+//                          window updates are tested per step against the current table, only the ones
+//                          that can change it are replayed serially (lane q owns entry q);
+//                          all snapshot their state after every iteration
+//   phase 3 (all threads)  n by counting (integer, order-free), then the Thompson-tau rejection loop per
+//                          output position from the snapshots
+__device__ __forceinline__ bool noise_table_event(double old, double nw, double m_last) {
+    // evict (src/call.rs:857-869) can only hit if some entry is within 1e-12 of `old`: impossible when the
+    // table is full and its smallest entry exceeds `old` by more than 1e-9; insert (src/call.rs:872-890)
+    // happens iff nw > last entry.
+    const bool ev = old > 0.0 && !(m_last > 0.0 && old < m_last - 1e-9);
+    const bool in = nw > 0.0 && nw > m_last;
+    return ev || in;
+}
+
+__global__ void __launch_bounds__(BK_NOISE_THREADS)
+k_noise(ScoreView sv, double* noise_max, double* vers_all) {
+    extern __shared__ __align__(16) u8 nsm[];
+    double* maf = reinterpret_cast<double*>(nsm);                               // (T+100)*3
+    double* snap_s = maf + (BK_NOISE_TILE + BK_NOISE_WINDOW) * 3;               // T
+    double* snap_s2 = snap_s + BK_NOISE_TILE;                                   // T
+    u32* pos_ver = reinterpret_cast<u32*>(snap_s2 + BK_NOISE_TILE);             // T: table version seen by iteration li
     const i32 best = sv.ctr->best;
     if (best < 0) return;
     const u32 s = sv.genome_seq_off[best] + blockIdx.x;
     if (s >= sv.genome_seq_off[best + 1]) return;
-    if (threadIdx.x != 0 && threadIdx.x != 32) return;
     const u32 r0 = sv.seq_row0[s] - sv.genome_row0[best];
     const u32 len = sv.seq_row0[s + 1] - sv.seq_row0[s];
-    const double* mf = maf + (size_t)r0 * 3;
-    const double* mq = msq + (size_t)r0 * 3;
     if (len < BK_NOISE_WINDOW) {     // the reference indexes out of bounds (panics) here; report zero noise
-        if (threadIdx.x == 0) for (u32 i = 0; i < len; i++) { st_n[r0 + i] = 0; st_s[r0 + i] = 0.0; st_s2[r0 + i] = 0.0; }
-        else for (u32 i = 0; i < len * BK_NOISE_TABLE; i++) st_max[(size_t)r0 * BK_NOISE_TABLE + i] = 0.0;
+        for (u32 i = threadIdx.x; i < len; i += blockDim.x) noise_max[r0 + i] = 0.0;
         return;
     }
     const u32 iters = len + BK_NOISE_HALF;
-    if (threadIdx.x == 0) {
-        // running sums: identical operation order to src/call.rs:845-895 (adding/subtracting an
-        // exact 0.0 where the reference skips the update leaves every bit unchanged)
-        u32 n = 0; double sum = 0.0, sum2 = 0.0;
-        for (u32 i = 0; i < iters; i++) {
-            const bool has_old = i >= BK_NOISE_WINDOW;          // position i-100 < len always holds
-            const bool has_new = i < len;
-#pragma unroll
-            for (u32 j = 0; j < 3; j++) {
-                const double old = has_old ? mf[(size_t)(i - BK_NOISE_WINDOW) * 3 + j] : 0.0;
-                const double old2 = has_old ? mq[(size_t)(i - BK_NOISE_WINDOW) * 3 + j] : 0.0;
-                const double nw = has_new ? mf[(size_t)i * 3 + j] : 0.0;
-                const double nw2 = has_new ? mq[(size_t)i * 3 + j] : 0.0;
-                if (old > 0.0) { n -= 1; sum = __dsub_rn(sum, old); sum2 = __dsub_rn(sum2, old2); }
-                if (nw > 0.0) { n += 1; sum = __dadd_rn(sum, nw); sum2 = __dadd_rn(sum2, nw2); }
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double sum = 0.0;                 // warp 0 lane 0: s ; warp 1 lane 0: s2
+    double mt = 0.0, m_last = 0.0;    // warp 2: lane q < 10 owns table entry q; m_last = entry 9 (uniform)
+    double* vers = vers_all + (size_t)blockIdx.x * BK_NOISE_VERS * BK_NOISE_TABLE;
+
+    for (u32 t0 = 0; t0 < iters; t0 += BK_NOISE_TILE) {
+        const u32 tn = min((u32)BK_NOISE_TILE, iters - t0);
+        // ---- phase 1: fractions of positions p = t0 - 100 + x, x in [0, tn + 100) ----
+        for (u32 x = threadIdx.x; x < tn + BK_NOISE_WINDOW; x += blockDim.x) {
+            const i32 p = (i32)t0 - BK_NOISE_WINDOW + (i32)x;
+            double m1 = 0.0, m2 = 0.0, m3 = 0.0;
+            if (p >= 0 && p < (i32)len) {
+                const u32 row = r0 + (u32)p;
+                const uint4 f = *reinterpret_cast<const uint4*>(sv.pile + row * 4);
+                const uint4 r = *reinterpret_cast<const uint4*>(sv.pile + sv.pile_stride + row * 4);
+                u64 c0 = (u64)f.x + r.x, c1 = (u64)f.y + r.y, c2 = (u64)f.z + r.z, c3 = (u64)f.w + r.w;
+                u64 t;
+#define BK_CSWAP(a, b) if (a < b) { t = a; a = b; b = t; }
+                BK_CSWAP(c0, c1) BK_CSWAP(c2, c3) BK_CSWAP(c0, c2) BK_CSWAP(c1, c3) BK_CSWAP(c1, c2)
+#undef BK_CSWAP
+                const u64 total = c0 + c1 + c2 + c3;
+                if (total != 0) { const double td = (double)total; m1 = (double)c1 / td; m2 = (double)c2 / td; m3 = (double)c3 / td; }
             }
-            if (i >= BK_NOISE_HALF) { const u32 w = r0 + i - BK_NOISE_HALF; st_n[w] = n; st_s[w] = sum; st_s2[w] = sum2; }
+            maf[x * 3 + 0] = m1; maf[x * 3 + 1] = m2; maf[x * 3 + 2] = m3;
         }
-    } else {
-        // max table, src/call.rs:857-892: evict the first entry within 1e-12 of the value leaving the
-        // window (never refilled), insert by bubbling up with strict '>'.
-        double m[BK_NOISE_TABLE];
+        __syncthreads();
+        // ---- phase 2 ----
+        if (wid == 0) {
+            if (lane == 0) {                                                     // src/call.rs:845-895, s
+                const double* __restrict__ mf = maf;
+                double* __restrict__ out = snap_s;
+#pragma unroll 8
+                for (u32 li = 0; li < tn; li++) {
+                    const double* po = mf + li * 3;                              // position i - 100
+                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;          // position i
 #pragma unroll
-        for (u32 q = 0; q < BK_NOISE_TABLE; q++) m[q] = 0.0;
-        for (u32 i = 0; i < iters; i++) {
-            const bool has_old = i >= BK_NOISE_WINDOW;
-            const bool has_new = i < len;
+                    for (u32 j = 0; j < 3; j++) { sum = __dsub_rn(sum, po[j]); sum = __dadd_rn(sum, pn[j]); }
+                    out[li] = sum;
+                }
+            }
+        } else if (wid == 1) {
+            if (lane == 0) {                                                     // s2
+                const double* __restrict__ mf = maf;
+                double* __restrict__ out = snap_s2;
+#pragma unroll 8
+                for (u32 li = 0; li < tn; li++) {
+                    const double* po = mf + li * 3;
+                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;
 #pragma unroll
-            for (u32 j = 0; j < 3; j++) {
-                const double old = has_old ? mf[(size_t)(i - BK_NOISE_WINDOW) * 3 + j] : 0.0;
-                const double nw = has_new ? mf[(size_t)i * 3 + j] : 0.0;
-                if (old > 0.0) {
-                    // exact-safe shortcut: every entry is either >= m[9]+... ; if old is well below the
-                    // smallest entry nothing can be within 1e-12 of it
-                    if (!(m[BK_NOISE_TABLE - 1] > 0.0 && old < m[BK_NOISE_TABLE - 1] - 1e-9)) {
-                        u32 pos = BK_NOISE_TABLE;
-#pragma unroll
-                        for (u32 q = BK_NOISE_TABLE; q-- > 0;) if (fabs(__dsub_rn(m[q], old)) < 1e-12) pos = q;
-                        if (pos < BK_NOISE_TABLE) {
-#pragma unroll
-                            for (u32 q = 0; q < BK_NOISE_TABLE - 1; q++) if (q >= pos) m[q] = m[q + 1];
-                            m[BK_NOISE_TABLE - 1] = 0.0;
+                    for (u32 j = 0; j < 3; j++) {
+                        const double o = po[j], w = pn[j];
+                        sum = __dsub_rn(sum, __dmul_rn(o, o)); sum = __dadd_rn(sum, __dmul_rn(w, w));
+                    }
+                    out[li] = sum;
+                }
+            }
+        } else if (wid == 2) {
+            // max table: lane q < 10 owns entry q.  32 window updates are tested per step against the
+            // current table; only those that can change it are replayed (in order), each replay costs a
+            // couple of ballots/shuffles.  Every table state of the tile is kept as a "version" in a
+            // global scratch area; positions only record which version they see.
+            u32 ver = 0;
+            if (lane < BK_NOISE_TABLE) vers[lane] = mt;
+            const u32 n_ops = tn * 3;
+            for (u32 u0 = 0; u0 < n_ops; u0 += 32) {
+                const u32 u = u0 + lane;
+                const bool in_range = u < n_ops;
+                const u32 li = u / 3, j = u - li * 3;
+                const double old = in_range ? maf[li * 3 + j] : 0.0;
+                const double nw = in_range ? maf[(li + BK_NOISE_WINDOW) * 3 + j] : 0.0;
+                u32 done = 0;                                                    // lanes below `done` are finished
+                for (;;) {
+                    const bool cand = in_range && lane >= done && noise_table_event(old, nw, m_last);
+                    const u32 mask = __ballot_sync(0xFFFFFFFFu, cand);
+                    const u32 first = mask ? (u32)__ffs(mask) - 1 : 32u;
+                    // ops [done, first) leave the table as it is
+                    if (in_range && lane >= done && lane < first && j == 2) pos_ver[li] = ver;
+                    if (first == 32u) break;
+                    const double e_old = __shfl_sync(0xFFFFFFFFu, old, first);
+                    const double e_new = __shfl_sync(0xFFFFFFFFu, nw, first);
+                    bool changed = false;
+                    if (e_old > 0.0) {                                           // evict: src/call.rs:857-869
+                        const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && fabs(__dsub_rn(mt, e_old)) < 1e-12);
+                        const double nxt = __shfl_down_sync(0xFFFFFFFFu, mt, 1);
+                        if (hm) {
+                            const u32 pos = (u32)__ffs(hm) - 1;
+                            if (lane >= pos && lane < BK_NOISE_TABLE) mt = (lane == BK_NOISE_TABLE - 1) ? 0.0 : nxt;
+                            changed = true;
                         }
                     }
-                }
-                if (nw > 0.0 && nw > m[BK_NOISE_TABLE - 1]) {
-                    u32 gt = 0;
-#pragma unroll
-                    for (u32 q = 0; q < BK_NOISE_TABLE; q++) gt += (nw > m[q]) ? 1u : 0u;
-                    const u32 pos = BK_NOISE_TABLE - gt;      // table is non-increasing: '>' holds on a suffix
-#pragma unroll
-                    for (u32 q = BK_NOISE_TABLE; q-- > 1;) if (q > pos) m[q] = m[q - 1];
-#pragma unroll
-                    for (u32 q = 0; q < BK_NOISE_TABLE; q++) if (q == pos) m[q] = nw;
+                    const double last = __shfl_sync(0xFFFFFFFFu, mt, BK_NOISE_TABLE - 1);
+                    if (e_new > 0.0 && e_new > last) {                           // insert: src/call.rs:872-890
+                        const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_new > mt);
+                        const u32 pos = (u32)__ffs(gm) - 1;                      // non-increasing table: '>' holds on a suffix
+                        const double prv = __shfl_up_sync(0xFFFFFFFFu, mt, 1);
+                        if (lane < BK_NOISE_TABLE && lane > pos) mt = prv;
+                        if (lane == pos) mt = e_new;
+                        changed = true;
+                    }
+                    if (changed) {
+                        m_last = __shfl_sync(0xFFFFFFFFu, mt, BK_NOISE_TABLE - 1);
+                        ver++;
+                        if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = mt;
+                    }
+                    if (lane == first && j == 2) pos_ver[li] = ver;
+                    done = first + 1;
                 }
             }
-            if (i >= BK_NOISE_HALF) {
-                double* o = st_max + (size_t)(r0 + i - BK_NOISE_HALF) * BK_NOISE_TABLE;
-#pragma unroll
-                for (u32 q = 0; q < BK_NOISE_TABLE; q++) o[q] = m[q];
-            }
+            __threadfence_block();
         }
-    }
-}
+        __syncthreads();
+        // ---- phase 3: n, then Thompson tau per output position w = i - 50 (src/call.rs:898-961) ----
+        for (u32 li = threadIdx.x; li < tn; li += blockDim.x) {
+            const u32 i = t0 + li;
+            if (i < BK_NOISE_HALF) continue;
+            // n after iteration i = number of positive fractions among positions [i-99, i]
+            u32 cn0 = 0;
+            for (u32 x = 0; x < BK_NOISE_WINDOW; x++) {
+                const double* pp = maf + (li + 1 + x) * 3;
+                cn0 += (pp[0] > 0.0 ? 1u : 0u) + (pp[1] > 0.0 ? 1u : 0u) + (pp[2] > 0.0 ? 1u : 0u);
+            }
+            const double s0 = snap_s[li], s20 = snap_s2[li];
+            const double* mxp = vers + (size_t)pos_ver[li] * BK_NOISE_TABLE;   // written this tile by warp 2: read through L2
 
-__constant__ double c_tau[301];
-
-__global__ void __launch_bounds__(256)
-k_noise_tau(ScoreView sv, const u32* __restrict__ st_n, const double* __restrict__ st_s, const double* __restrict__ st_s2,
-            const double* __restrict__ st_max, double* noise_max) {
-    const i32 best = sv.ctr->best;
-    if (best < 0) return;
-    const u32 rows = sv.genome_row0[best + 1] - sv.genome_row0[best];
-    const u32 row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    const u32 n = st_n[row];
-    const double s = st_s[row], s2 = st_s2[row];
-    const double* mx = st_max + (size_t)row * BK_NOISE_TABLE;
-    double mu = 0.0, var = 0.0;
-    if (n != 0) { mu = __ddiv_rn(s, (double)n); var = __dsub_rn(__ddiv_rn(s2, (double)n), __dmul_rn(mu, mu)); }
-    u32 idx = 0, cn = n;
-    double cs = s, cs2 = s2, cmu = mu, cvar = var;
-    while (idx < BK_NOISE_TABLE && mx[idx] != 0.0) {              // src/call.rs:915-950
-        const double cand = mx[idx];
-        const double sd = sqrt(cvar);
-        const double tau = (cn > 2) ? c_tau[cn <= 300 ? cn : 300] : __longlong_as_double(0x7FF0000000000000ll);
-        if (fabs(__dsub_rn(cand, cmu)) > __dmul_rn(tau, sd)) {
-            cs = __dsub_rn(cs, cand);
-            cs2 = __dsub_rn(cs2, cand);                           // sic: candidate, not its square (src/call.rs:936)
-            cn -= 1;
-            if (cn > 0) { cmu = __ddiv_rn(cs, (double)cn); cvar = __dsub_rn(__ddiv_rn(cs2, (double)cn), __dmul_rn(cmu, cmu)); }
-            else { cmu = 0.0; cvar = 0.0; }
-            idx += 1;
-        } else break;
+            double mu = 0.0, var = 0.0;
+            if (cn0 != 0) { mu = __ddiv_rn(s0, (double)cn0); var = __dsub_rn(__ddiv_rn(s20, (double)cn0), __dmul_rn(mu, mu)); }
+            u32 idx = 0, cn = cn0;
+            double cs = s0, cs2 = s20, cmu = mu, cvar = var;
+            double cand = __ldcg(mxp);
+            while (cand != 0.0) {
+                const double sd = sqrt(cvar);
+                const double tau = (cn > 2) ? c_tau[cn <= 300 ? cn : 300] : __longlong_as_double(0x7FF0000000000000ll);
+                if (fabs(__dsub_rn(cand, cmu)) > __dmul_rn(tau, sd)) {
+                    cs = __dsub_rn(cs, cand);
+                    cs2 = __dsub_rn(cs2, cand);                       // sic: candidate, not its square (src/call.rs:936)
+                    cn -= 1;
+                    if (cn > 0) { cmu = __ddiv_rn(cs, (double)cn); cvar = __dsub_rn(__ddiv_rn(cs2, (double)cn), __dmul_rn(cmu, cmu)); }
+                    else { cmu = 0.0; cvar = 0.0; }
+                    idx += 1;
+                    cand = idx < BK_NOISE_TABLE ? __ldcg(mxp + idx) : 0.0;   // the reference would panic at idx == 10
+                } else break;
+            }
+            noise_max[r0 + i - BK_NOISE_HALF] = cand;
+        }
+        __syncthreads();
     }
-    noise_max[row] = idx < BK_NOISE_TABLE ? mx[idx] : 0.0;        // the reference would panic at idx == 10
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -151,7 +151,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params);
  * Host buffers (pinned recommended: bk_host_alloc); may be called repeatedly per file (chunks). */
 int bk_reads_push(bk_ctx* ctx, int file_slot, const uint8_t* bases, const uint32_t* read_off,
                   uint64_t n_reads);
-/* Same, buffers already in device memory (16-byte aligned, readable up to the next multiple of 16). */
+/* Same, buffers already in device memory (16-byte aligned, readable for 16 bytes past n_bases). */
 int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
                          const uint32_t* d_read_off, uint64_t n_reads, uint64_t n_bases,
                          uint32_t max_read_len);

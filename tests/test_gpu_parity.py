@@ -129,6 +129,20 @@ def test_n_fixed_too_large_queries_no_bucket(ctx_sars, oracle):
     assert e.value.code == -4
 
 
+def test_many_genome_map_kernel_on_small_db(sars_paths, oracle, monkeypatch):
+    """The warp-per-k-mer map kernel (used for > 4 genomes) must agree with the thread-per-k-mer one."""
+    import bronko_b200
+    monkeypatch.setenv("BK_FORCE_WARP_MAP", "1")
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, sars_paths)
+        oi = oracle.Index.build(21, sars_paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[3]), 500, sim.SEED0 + 41)
+        run_both(c, oi, [(r1, o1), (r2, o2)])
+    finally:
+        c.close()
+
+
 def test_edge_reads(ctx_hpv):
     """Ragged input: empty reads, reads shorter than k, N / lower-case / junk bytes, a read longer than a
     tile, reads hanging over both genome ends, foreign reads, an indel."""
