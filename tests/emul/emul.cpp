@@ -80,12 +80,15 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     auto ldr = [&](u32 i) { return d.refpk[i]; };
     u64 novel = 0, left_kmers = 0;
     for (u64 r = 0; r < n_reads; r++) {
-        Pending pend; pend.n = 0;
+        Pending pend; pend.n = 0; pend.d0 = make_uint2(0, 0); pend.d1 = make_uint2(0, 0);
         novel += scan_read(v, ld, ldr, off[r], off[r + 1] - off[r], 0, pend);
-        u32 overflow = 0;
-        if (pend.n > 0) queue_push(v, pend.d0, &overflow);
-        if (pend.n > 1) queue_push(v, pend.d1, &overflow);
-        if (overflow) return ~0ull - 3;
+        // same policy as flush_pending() on the device: a full queue means counting in place
+        for (u32 q = 0; q < pend.n; q++) {
+            const uint2 d = q == 0 ? pend.d0 : pend.d1;
+            u32 overflow = 0;
+            queue_push(v, d, &overflow);
+            if (overflow) novel += count_stretch(v, ld, d.x, d.y, 0, 1);
+        }
     }
     const u32 nd = std::min(n_desc, desc_cap);
     for (u32 i = 0; i < nd; i++) { left_kmers += desc[i].y; novel += count_stretch(v, ld, desc[i].x, desc[i].y, 0, 1); }

@@ -1,0 +1,161 @@
+"""CPU tests of the product's host logic and of the counting-stage algorithm the CUDA kernels are built
+from (stepped on the CPU by tests/emul), each against the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bronko_b200 import sim
+from emul_lib import Emul, lib as emul_lib, ptr
+from util import reads_from_strings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sars_emul(sars_paths):
+    return Emul.from_fasta(21, sars_paths)
+
+
+@pytest.fixture(scope="module")
+def hpv_emul(hpv_bkdb_path):
+    return Emul.from_bkdb(hpv_bkdb_path)
+
+
+def test_builder_matches_oracle_and_bundled_db(oracle, sars_paths, sars_emul, hpv_fasta, hpv_bkdb_bytes):
+    a, b = oracle.Index.build(21, sars_paths).export(), sars_emul.export()
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2].tobytes() == b[2].tobytes()
+    assert len(a[0]) == 703025 and len(a[2]) == 2501142
+    h = Emul.from_fasta(21, [hpv_fasta]).export()
+    g = oracle.Index.decode(hpv_bkdb_bytes).export()
+    assert (h[0] == g[0]).all() and (h[1] == g[1]).all() and h[2].tobytes() == g[2].tobytes()
+
+
+@pytest.mark.parametrize("k", [15, 19, 31])
+def test_builder_other_k(oracle, hpv_fasta, k):
+    a, b = oracle.Index.build(k, [hpv_fasta]).export(), Emul.from_fasta(k, [hpv_fasta]).export()
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2].tobytes() == b[2].tobytes()
+
+
+def test_bkdb_reader_and_writer(oracle, hpv_emul, hpv_bkdb_bytes, tmp_path):
+    g = oracle.Index.decode(hpv_bkdb_bytes).export()
+    h = hpv_emul.export()
+    assert (h[0] == g[0]).all() and (h[1] == g[1]).all() and h[2].tobytes() == g[2].tobytes()
+    p = str(tmp_path / "w.bkdb")
+    hpv_emul.save(p)
+    back = oracle.Index.load(p)                         # the oracle's reader decodes what the product wrote
+    assert back.consumed == back.file_size
+    r = back.export()
+    assert (r[0] == g[0]).all() and r[2].tobytes() == g[2].tobytes()
+    assert back.genomes() == oracle.Index.decode(hpv_bkdb_bytes).genomes()
+
+
+def test_assign_buckets_closed_form_matches_loop_form(oracle):
+    rng = np.random.default_rng(1)
+    for k in (15, 21, 27, 31):                          # k = 31 exercises the u64 wrap-around (Q20)
+        for _ in range(200):
+            kmer = int(rng.integers(0, 2 ** 62, dtype=np.uint64)) & ((1 << (2 * k)) - 1)
+            out = np.zeros(k, dtype=np.uint64)
+            emul_lib().emul_assign_buckets(kmer, k, ptr(out))
+            assert [int(x) for x in out] == oracle.assign_buckets(kmer, k)
+            assert emul_lib().emul_revcomp(kmer, k) == oracle.lib().orc_reverse_complement(kmer, k)
+
+
+def test_tau_table_matches_oracle(oracle):
+    t = np.zeros(301)
+    emul_lib().emul_tau_table(ptr(t))
+    for n in range(3, 301):
+        assert t[n] == oracle.thompson_tau(n)
+    assert (t[:3] == 0).all()
+
+
+def test_clean_sample_id_matches_oracle(oracle):
+    buf = C.create_string_buffer(512)
+    for p in ["a/b/rep1_R1.fastq.gz", "x.fq", "x.fq.gz", "s.fastq.fastq", "weird.fna.gz", "reads.txt", "noext",
+              "a.b.fasta", "q.fnq", "/abs/dir.d/file.fa", ".hidden", "double.fq.fq"]:
+        emul_lib().emul_clean_sample_id(p.encode(), buf, 512)
+        assert buf.value.decode() == oracle.clean_sample_id(p), p
+
+
+@pytest.mark.parametrize("strain,depth", [(0, 200), (1, 200), (3, 120)])
+def test_counting_logic_matches_oracle(oracle, sars_emul, strain, depth):
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[strain]), depth, 100 + strain)
+    for b, o in ((r1, o1), (r2, o2)):
+        want = oracle.Counts.count(21, b, o.astype(np.uint64), 3, 1000000, 2)
+        km, ct, st, dbg = sars_emul.count(b, o)
+        wk, wc = want.get()
+        assert st == want.stats()
+        assert len(km) == len(wk) and (km == wk).all() and (ct.astype(np.uint64) == wc).all()
+        assert dbg[1] < 0.2 * st[1]                     # most k-mers ride on runs, not the leftover path
+
+
+def test_counting_edge_cases(oracle, hpv_emul):
+    g = sim.load_genome(sim.HPV16).tobytes().decode()
+    rcg = g[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    rng = np.random.default_rng(5)
+    seqs = ["", "A", g[100:120], g[100:121], g[200:350], g[200:350].lower(), g[400:470] + "N" + g[471:560],
+            g[600:640] + "n*" + g[642:700], "N" * 40, "GATTACA" * 30, g[1000:1100] + g[1103:1250],
+            g[1500:1560] + "ACGT" + g[1560:1700], "TTTTTTTTTT" + g[0:140], g[-140:] + "GGGGGGGGGG", rcg[0:150],
+            "CCCCC" + rcg[-100:] + "AAAAA", g[3000:3800], g, g[2000:2021], g[2001:2022],
+            "".join("ACGT"[i] for i in rng.integers(0, 4, size=300))]
+    for ci in (1, 2):
+        b, off = reads_from_strings(seqs * 2)
+        want = oracle.Counts.count(21, b, off.astype(np.uint64), ci, 1000000, 1)
+        km, ct, st, _ = hpv_emul.count(b, off, ci=ci)
+        wk, wc = want.get()
+        assert st == want.stats()
+        assert (km == wk).all() and (ct.astype(np.uint64) == wc).all()
+
+
+def test_counting_with_full_leftover_queue(oracle, hpv_emul):
+    """Queue overflow falls back to in-place counting: still exact."""
+    r1, o1, _, _, _ = sim.simulate_pairs(sim.load_genome(sim.HPV16), 60, 7)
+    want = oracle.Counts.count(21, r1, o1.astype(np.uint64), 3, 1000000, 1)
+    km, ct, st, _ = hpv_emul.count(r1, o1, desc_cap=8)
+    wk, wc = want.get()
+    assert st == want.stats() and (km == wk).all() and (ct.astype(np.uint64) == wc).all()
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from bronko_b200 import _lib
+    header = open(_lib.HEADER).read()
+    declared = set(re.findall(r"\b(bk_[a-z_0-9]+)\s*\(", header))
+    declared -= {"bk_ctx"}
+    assert declared == set(_lib.SIGNATURES), "header and ctypes signatures disagree"
+    L = _lib.lib()                                      # loads without a GPU
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.bk_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a B200 the context must fail loudly (no silent CPU path)."""
+    import bronko_b200
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(bronko_b200.BkError) as e:
+        bronko_b200.Bronko(0)
+    assert e.value.code in (-6, -2)
+
+
+def test_product_does_not_reference_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bronko_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower() or f in ("__init__.py",) and "oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_simulator_is_seeded_and_shaped():
+    a = sim.simulate_pairs(sim.load_genome(sim.HPV16), 50, 3)
+    b = sim.simulate_pairs(sim.load_genome(sim.HPV16), 50, 3)
+    assert (a[0] == b[0]).all() and (a[2] == b[2]).all()
+    n = round(50 * 7906 / 300)
+    assert len(a[1]) == n + 1 and len(a[0]) == n * 150 and set(np.unique(a[0]).tolist()) <= set(b"ACGT")
+    assert len(a[4]["pos"]) == 30 and sorted(set(a[4]["af"].tolist())) == [0.03, 0.05, 0.1, 0.2, 0.4, 1.0]
