@@ -85,6 +85,12 @@ SIGNATURES = {
     "bk_write_vcf": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bk_write_pileup": (C.c_int, [P, C.c_char_p]),
     "bk_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),
+    "bk_shard_config": (C.c_int, [P, u32, u32]),
+    "bk_shard_begin": (C.c_int, [P, C.c_int, P, P, P, P, P]),
+    "bk_shard_import_novel": (C.c_int, [P, C.c_int, P, P, u64]),
+    "bk_shard_map_stats": (C.c_int, [P, P, P, P, P]),
+    "bk_shard_select_pileup": (C.c_int, [P, P, P, P]),
+    "bk_shard_score": (C.c_int, [P, C.POINTER(SampleResult)]),
     "bk_host_alloc": (P, [u64]),
     "bk_host_free": (None, [P]),
 }
@@ -94,10 +100,9 @@ _lib = None
 
 def build(force=False):
     """Compile libbronko_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    if force or not os.path.exists(SO_PATH):
-        subprocess.check_call(["make", "-C", CSRC, "-s", "libbronko_b200.so"])
-    else:
-        subprocess.check_call(["make", "-C", CSRC, "-s", "-q", "libbronko_b200.so"]) if False else None
+    if force and os.path.exists(SO_PATH):
+        os.remove(SO_PATH)
+    subprocess.check_call(["make", "-C", CSRC, "-s", "libbronko_b200.so"])
     return SO_PATH
 
 

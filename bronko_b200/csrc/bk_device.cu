@@ -53,7 +53,8 @@ struct FileState {
     DevBuf<u32> ccounts;
     DevBuf<u32> gstats;
     u32 gen_log2 = 0;
-    bool used = false, finalized = false;
+    DevBuf<u64> xk; DevBuf<u32> xc;          // sharded mode: novel (k-mer, count) pairs grouped by owner rank
+    bool used = false, folded = false, finalized = false;
     u64 total_reads = 0, total_bases = 0;
 };
 
@@ -91,6 +92,8 @@ struct bk_ctx {
     cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
     int stage_next = 0;
     u32 shard_rank = 0, shard_n = 1;
+    bk_kmc_stats shard_kmc[2];
+    DevBuf<u32> d_part;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
 
     // results
@@ -188,7 +191,8 @@ void bk_destroy(bk_ctx* ctx) {
     ctx->d_oseq_len.release(); ctx->d_exact.release(); ctx->d_slot2id.release(); ctx->d_id_kmer.release();
     ctx->d_genome_row0.release(); ctx->d_genome_seq_off.release(); ctx->d_seq_row0.release(); ctx->d_genome_len.release();
     ctx->d_ref_code.release();
-    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); }
+    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
+    ctx->d_part.release();
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
     ctx->d_noise.release(); ctx->d_noise_vers.release(); ctx->d_vars.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
@@ -364,7 +368,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     cudaSetDevice(ctx->device);
     ctx->params = *params;
     ctx->in_sample = true; ctx->finished = false;
-    for (FileState& f : ctx->file) { f.used = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; }
+    for (FileState& f : ctx->file) { f.used = false; f.folded = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; }
     ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0;
     ctx->variants.clear();
     memset(&ctx->result, 0, sizeof ctx->result);
@@ -438,7 +442,7 @@ static int check_push(bk_ctx* ctx, int slot) {
     if (!ctx) return BK_ERR_ARG;
     if (!ctx->in_sample || ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_reads_push: call bk_sample_begin first");
     if (slot < 0 || slot > 1) return ctx->fail(BK_ERR_ARG, "bk_reads_push: file_slot must be 0 or 1");
-    if (ctx->file[slot].finalized) return ctx->fail(BK_ERR_ARG, "bk_reads_push: file already finalized");
+    if (ctx->file[slot].folded) return ctx->fail(BK_ERR_ARG, "bk_reads_push: file already finalized");
     cudaSetDevice(ctx->device);
     return BK_OK;
 }
@@ -512,20 +516,35 @@ int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
     return BK_OK;
 }
 
-// prefix sum + fold + compaction of one file (the KMC "database" of that file)
-static int finalize_counts(bk_ctx* ctx, int slot) {
+// ---- stages of bk_sample_finish (also driven one by one in the read-sharded mode) ---------------
+
+// stage 1: prefix sum of the difference array + fold onto distinct reference k-mers → idcnt
+static int stage_fold(bk_ctx* ctx, int slot) {
     FileState& f = ctx->file[slot];
-    if (f.finalized) return BK_OK;
+    if (f.folded) return BK_OK;
     const DerivedIndex& d = ctx->d;
     const u32 n = d.n_raw;
     const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
-    const u32 n_ids = (u32)d.id_kmer.size();
-    const size_t out_cap = (size_t)n_ids + (1ull << f.gen_log2);
-    BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
     int sp = ctx->span_begin(ST_FINALIZE);
     k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p);
     k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
     k_diff_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p, ctx->d_slot2id.p, f.idcnt.p);
+    ctx->span_end(sp);
+    ctx->launches += 3;
+    BK_CUDA(cudaGetLastError());
+    f.folded = true;
+    return BK_OK;
+}
+
+// stage 2: compaction = the KMC dump of one file (threshold, cap, the four stdout numbers)
+static int stage_compact(bk_ctx* ctx, int slot) {
+    FileState& f = ctx->file[slot];
+    if (f.finalized) return BK_OK;
+    const DerivedIndex& d = ctx->d;
+    const u32 n_ids = (u32)d.id_kmer.size();
+    const size_t out_cap = (size_t)n_ids + (1ull << f.gen_log2);
+    BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
+    int sp = ctx->span_begin(ST_FINALIZE);
     CompactArgs a;
     a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n;
     a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
@@ -533,7 +552,7 @@ static int finalize_counts(bk_ctx* ctx, int slot) {
     k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->d_id_kmer.p, n_ids);
     k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
     ctx->span_end(sp);
-    ctx->launches += 5;
+    ctx->launches += 2;
     BK_CUDA(cudaGetLastError());
     f.finalized = true;
     return BK_OK;
@@ -553,25 +572,18 @@ static MapView make_map_view(bk_ctx* ctx) {
     return m;
 }
 
-int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
-    if (!ctx) return BK_ERR_ARG;
-    if (!ctx->in_sample || ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: no sample in progress");
-    if (!ctx->file[0].used) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: no reads were pushed to file slot 0");
-    cudaSetDevice(ctx->device);
-    const int n_files = ctx->file[1].used ? 2 : 1;
-    const DerivedIndex& d = ctx->d;
-    cudaStream_t st = ctx->stream;
-    int rc;
-    for (int f = 0; f < n_files; f++) if ((rc = finalize_counts(ctx, f))) return rc;
+static int n_files_used(bk_ctx* ctx) { return ctx->file[1].used ? 2 : 1; }
 
+// stage 3: map_kmers tallies of every file (src/call.rs:1389-1430)
+static int stage_map_stats(bk_ctx* ctx) {
+    const DerivedIndex& d = ctx->d;
     const MapView m = make_map_view(ctx);
-    const u32 pile_stride = d.max_genome_rows * 4;
     const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
     const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
     Counters* dc = ctx->d_ctr.p;
+    cudaStream_t st = ctx->stream;
     int sp = ctx->span_begin(ST_MAP);
-    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
-    for (int f = 0; f < n_files; f++) {
+    for (int f = 0; f < n_files_used(ctx); f++) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
@@ -579,6 +591,22 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
         else k_map<0><<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
+    ctx->span_end(sp);
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+// stage 4: pick_best_genome(_paired) + the selected genome's pileup (src/call.rs:1324-1385)
+static int stage_select_pileup(bk_ctx* ctx) {
+    const DerivedIndex& d = ctx->d;
+    const MapView m = make_map_view(ctx);
+    const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
+    const u32 pile_stride = d.max_genome_rows * 4;
+    const int n_files = n_files_used(ctx);
+    Counters* dc = ctx->d_ctr.p;
+    cudaStream_t st = ctx->stream;
+    int sp = ctx->span_begin(ST_MAP);
+    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
     k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
     ctx->launches++;
     for (int f = 0; f < n_files; f++) {
@@ -590,8 +618,17 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     }
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
 
-    sp = ctx->span_begin(ST_SCORE);
+// stage 5: noise baseline + call_variants, read everything back, fill bk_sample_result
+static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
+    const DerivedIndex& d = ctx->d;
+    const int n_files = n_files_used(ctx);
+    const u32 pile_stride = d.max_genome_rows * 4;
+    Counters* dc = ctx->d_ctr.p;
+    cudaStream_t st = ctx->stream;
+    int sp = ctx->span_begin(ST_SCORE);
     ScoreView sv;
     sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
     sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
@@ -624,15 +661,18 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
         ctx->gstats[f].assign(d.n_genomes, bk_genome_stats());
         for (u32 g = 0; g < d.n_genomes; g++) {
             bk_genome_stats& s = ctx->gstats[f][g];
-            s.perfect = hg[f][g * 4]; s.variant = hg[f][g * 4 + 1]; s.unique_perfect = hg[f][g * 4 + 2]; s.present = hg[f][g * 4 + 3]; s._pad = 0;
+            s.perfect = hg[f][g * 4]; s.variant = hg[f][g * 4 + 1]; s.unique_perfect = hg[f][g * 4 + 2]; s.present = hg[f][g * 4 + 3] ? 1 : 0; s._pad = 0;
         }
     }
     bk_sample_result& r = ctx->result;
     memset(&r, 0, sizeof r);
     r.best_genome = c.best; r.n_files = n_files;
     for (int f = 0; f < n_files; f++) {
-        r.kmc[f].total_reads = ctx->file[f].total_reads; r.kmc[f].total_kmers = c.f[f].total_kmers;
-        r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = c.f[f].n_counted;
+        if (ctx->shard_n > 1) r.kmc[f] = ctx->shard_kmc[f];      // globally reduced numbers supplied by the host
+        else {
+            r.kmc[f].total_reads = ctx->file[f].total_reads; r.kmc[f].total_kmers = c.f[f].total_kmers;
+            r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = c.f[f].n_counted;
+        }
     }
     cudaEventRecord(ctx->ev_end, st);
     if (c.best < 0) {
@@ -665,7 +705,6 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     } else {
         cudaEventSynchronize(ctx->ev_end);
     }
-    // stage times
     bk_stage_times& t = ctx->times;
     memset(&t, 0, sizeof t);
     float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms};
@@ -677,6 +716,144 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     t.launches = ctx->launches; t.scan_launches = ctx->scan_launches;
     if (out) *out = r;
     return BK_OK;
+}
+
+static int check_finish(bk_ctx* ctx, const char* who) {
+    if (!ctx) return BK_ERR_ARG;
+    if (!ctx->in_sample || ctx->finished) return ctx->fail(BK_ERR_ARG, "%s: no sample in progress", who);
+    if (!ctx->file[0].used) return ctx->fail(BK_ERR_ARG, "%s: no reads were pushed to file slot 0", who);
+    cudaSetDevice(ctx->device);
+    return BK_OK;
+}
+
+int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
+    int rc = check_finish(ctx, "bk_sample_finish");
+    if (rc) return rc;
+    if (ctx->shard_n > 1) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: context is in sharded mode; drive the bk_shard_* stages");
+    for (int f = 0; f < n_files_used(ctx); f++) {
+        if ((rc = stage_fold(ctx, f))) return rc;
+        if ((rc = stage_compact(ctx, f))) return rc;
+    }
+    if ((rc = stage_map_stats(ctx))) return rc;
+    if ((rc = stage_select_pileup(ctx))) return rc;
+    return stage_score(ctx, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// read-sharded deep sample.  Every rank scans its share of the reads of ONE sample;
+// k-mer counts are merged across ranks before the threshold / cap / max-pileup:
+//   bk_shard_begin            per-rank partial counts are folded; novel k-mers are compacted and
+//                             partitioned by owner rank
+//   (host)                    all-reduce(SUM) the dense reference-k-mer counts; all-to-all the novel
+//                             (k-mer, count) pairs to their owners
+//   bk_shard_import_novel     the owner rebuilds its novel table from the merged pairs
+//   bk_shard_map_stats        threshold + cap on the merged counts (each reference k-mer id and each
+//                             novel k-mer is owned by exactly one rank), per-genome tallies
+//   (host)                    all-reduce(SUM) the tallies and the KMC numbers
+//   bk_shard_select_pileup    selection (same on every rank) + this rank's pileup contribution
+//   (host)                    all-reduce(MAX) the two depth arrays, all-reduce(SUM) the two support arrays
+//   bk_shard_score            noise + variants (every rank gets the same result)
+// ---------------------------------------------------------------------------------------------
+int bk_shard_config(bk_ctx* ctx, uint32_t rank, uint32_t n_ranks) {
+    if (!ctx) return BK_ERR_ARG;
+    if (ctx->in_sample && !ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_shard_config: call between samples");
+    if (n_ranks == 0 || rank >= n_ranks || n_ranks > 1024) return ctx->fail(BK_ERR_ARG, "bk_shard_config: bad rank / n_ranks");
+    ctx->shard_rank = rank; ctx->shard_n = n_ranks;
+    return BK_OK;
+}
+
+int bk_shard_begin(bk_ctx* ctx, int file_slot, void** d_ref_counts, uint64_t* n_ref_counts, void** d_novel_kmers,
+                   void** d_novel_counts, uint64_t* part_off) {
+    int rc = check_finish(ctx, "bk_shard_begin");
+    if (rc) return rc;
+    if (file_slot < 0 || file_slot > 1 || !ctx->file[file_slot].used) return ctx->fail(BK_ERR_ARG, "bk_shard_begin: file slot %d has no reads", file_slot);
+    if (!d_ref_counts || !n_ref_counts || !d_novel_kmers || !d_novel_counts || !part_off) return ctx->fail(BK_ERR_ARG, "bk_shard_begin: null argument");
+    FileState& f = ctx->file[file_slot];
+    if ((rc = stage_fold(ctx, file_slot))) return rc;
+    const u32 n_slots = (u32)(1ull << f.gen_log2);
+    const u32 nr = ctx->shard_n;
+    BK_CUDA(ctx->d_part.reserve((size_t)nr * 2));
+    BK_CUDA(cudaMemsetAsync(ctx->d_part.p, 0, (size_t)nr * 2 * 4, ctx->stream));
+    k_novel_partition<0><<<grid_for(ctx, n_slots, 256), 256, nr * 4, ctx->stream>>>(f.gen.p, n_slots, nr, ctx->d_part.p, nullptr, nullptr, nullptr);
+    std::vector<u32> cnt(nr);
+    BK_CUDA(cudaMemcpyAsync(cnt.data(), ctx->d_part.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<u32> start(nr);
+    u64 total = 0;
+    for (u32 r = 0; r < nr; r++) { part_off[r] = total; start[r] = (u32)total; total += cnt[r]; }
+    part_off[nr] = total;
+    BK_CUDA(f.xk.reserve(total + 1)); BK_CUDA(f.xc.reserve(total + 1));
+    BK_CUDA(cudaMemsetAsync(ctx->d_part.p, 0, (size_t)nr * 4, ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(ctx->d_part.p + nr, start.data(), nr * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_novel_partition<1><<<grid_for(ctx, n_slots, 256), 256, nr * 4, ctx->stream>>>(f.gen.p, n_slots, nr, ctx->d_part.p, ctx->d_part.p + nr, f.xk.p, f.xc.p);
+    ctx->launches += 2;
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *d_ref_counts = f.idcnt.p; *n_ref_counts = ctx->d.id_kmer.size();
+    *d_novel_kmers = f.xk.p; *d_novel_counts = f.xc.p;
+    return BK_OK;
+}
+
+int bk_shard_import_novel(bk_ctx* ctx, int file_slot, const void* d_kmers, const void* d_counts, uint64_t n) {
+    int rc = check_finish(ctx, "bk_shard_import_novel");
+    if (rc) return rc;
+    if (file_slot < 0 || file_slot > 1 || !ctx->file[file_slot].used) return ctx->fail(BK_ERR_ARG, "bk_shard_import_novel: bad file slot");
+    FileState& f = ctx->file[file_slot];
+    u32 lg = 10;
+    while ((1ull << lg) < 2 * n + 16) lg++;
+    if (lg > 31) return ctx->fail(BK_ERR_OVERFLOW, "too many novel k-mers for one rank");
+    f.gen_log2 = lg;
+    BK_CUDA(f.gen.reserve(1ull << lg));
+    k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
+    if (n) k_novel_insert<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(f.gen.p, 64 - lg, (u32)((1ull << lg) - 1), (const u64*)d_kmers, (const u32*)d_counts, n,
+                                                                           &ctx->d_ctr.p->gen_full);
+    ctx->launches += 2;
+    BK_CUDA(cudaGetLastError());
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));     // the caller may free / reuse its buffers now
+    return BK_OK;
+}
+
+int bk_shard_map_stats(bk_ctx* ctx, void** d_tallies0, void** d_tallies1, uint64_t* n_tallies, bk_kmc_stats* partial) {
+    int rc = check_finish(ctx, "bk_shard_map_stats");
+    if (rc) return rc;
+    const int n_files = n_files_used(ctx);
+    for (int f = 0; f < n_files; f++) {
+        if (!ctx->file[f].folded) return ctx->fail(BK_ERR_ARG, "bk_shard_map_stats: call bk_shard_begin for file %d first", f);
+        if ((rc = stage_compact(ctx, f))) return rc;
+    }
+    if ((rc = stage_map_stats(ctx))) return rc;
+    BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctr->gen_full) return ctx->fail(BK_ERR_OVERFLOW, "novel k-mer table is full; set bk_params.table_log2 higher");
+    for (int f = 0; f < 2; f++) {
+        bk_kmc_stats z; memset(&z, 0, sizeof z);
+        if (f < n_files) {
+            z.total_reads = ctx->file[f].total_reads; z.total_kmers = ctx->h_ctr->f[f].total_kmers;
+            z.unique_kmers = ctx->h_ctr->f[f].unique; z.unique_counted = ctx->h_ctr->f[f].n_counted;
+        }
+        if (partial) partial[f] = z;
+    }
+    if (d_tallies0) *d_tallies0 = ctx->file[0].gstats.p;
+    if (d_tallies1) *d_tallies1 = n_files > 1 ? ctx->file[1].gstats.p : nullptr;
+    if (n_tallies) *n_tallies = (u64)ctx->d.n_genomes * 4;
+    return BK_OK;
+}
+
+int bk_shard_select_pileup(bk_ctx* ctx, const bk_kmc_stats* global_kmc, void** d_pile, uint64_t* n_per_array) {
+    int rc = check_finish(ctx, "bk_shard_select_pileup");
+    if (rc) return rc;
+    if (global_kmc) { ctx->shard_kmc[0] = global_kmc[0]; ctx->shard_kmc[1] = global_kmc[1]; }
+    if ((rc = stage_select_pileup(ctx))) return rc;
+    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (d_pile) *d_pile = ctx->d_pile.p;
+    if (n_per_array) *n_per_array = (u64)ctx->d.max_genome_rows * 4;
+    return BK_OK;
+}
+
+int bk_shard_score(bk_ctx* ctx, bk_sample_result* out) {
+    int rc = check_finish(ctx, "bk_shard_score");
+    if (rc) return rc;
+    return stage_score(ctx, out);
 }
 
 int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out) {

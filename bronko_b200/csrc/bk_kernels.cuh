@@ -210,7 +210,7 @@ k_diff_apply(const u32* __restrict__ diff, u32 n, const u32* __restrict__ bsum, 
 struct CompactArgs { u32 ci, cs; u32 rank, n_ranks; u64* out_kmers; u32* out_counts; u32 out_cap; FileCounters* fc; };
 
 __device__ __forceinline__ void compact_emit(const CompactArgs& a, bool have, u64 kmer, u32 c, bool owned, u32& uniq, u64& total) {
-    if (have) { uniq++; total += c; }
+    if (have && owned) { uniq++; total += c; }
     const bool keep = have && owned && c >= a.ci && c <= 1000000000u;
     const u32 slot = warp_append(&a.fc->n_counted, keep);
     if (keep && slot < a.out_cap) { a.out_kmers[slot] = kmer; a.out_counts[slot] = min(c, a.cs); }
@@ -259,6 +259,59 @@ __global__ void __launch_bounds__(256) k_compact_gen(CompactArgs a, const GenSlo
     }
     uniq = warp_sum_u32(uniq); total = warp_sum_u64(total);
     if ((threadIdx.x & 31) == 0 && uniq) { atomicAdd(&a.fc->unique, uniq); atomicAdd((unsigned long long*)&a.fc->total_kmers, (unsigned long long)total); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// read-sharded mode: novel k-mers grouped by owner rank, and re-insertion of merged (k-mer, count) pairs
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 owner_of(u64 kmer, u32 n_ranks) {
+    return (u32)(((kmer ^ (kmer >> 29)) * 0xD6E8FEB86659FD93ull) >> 33) % n_ranks;
+}
+
+// PASS 0: per-owner counts (counts[n_ranks]); PASS 1: scatter to out[start[owner] + cursor[owner]++]
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_novel_partition(const GenSlot* __restrict__ gen, u32 n_slots, u32 n_ranks, u32* counts, const u32* start, u64* out_k, u32* out_c) {
+    extern __shared__ u32 sh[];
+    if (PASS == 0) {
+        for (u32 i = threadIdx.x; i < n_ranks; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        const uint4 s = __ldg(reinterpret_cast<const uint4*>(gen) + i);
+        const u64 key = ((u64)s.y << 32) | s.x;
+        if (key == BK_EMPTY) continue;
+        const u32 o = owner_of(key, n_ranks);
+        if (PASS == 0) atomicAdd(sh + o, 1u);
+        else {
+            // counts[] was zeroed again by the host after PASS 0 and now serves as the per-owner cursors
+            const u32 pos = start[o] + atomicAdd(counts + o, 1u);
+            out_k[pos] = key; out_c[pos] = s.z;
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n_ranks; i += blockDim.x) if (sh[i]) atomicAdd(counts + i, sh[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_novel_insert(GenSlot* gen, u32 shift, u32 mask, const u64* __restrict__ kmers, const u32* __restrict__ counts, u64 n, u32* full) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 kmer = kmers[i];
+        const u32 c = counts[i];
+        u32 h = hash_slot(kmer, shift);
+        bool done = false;
+        for (u32 probe = 0; probe <= mask && !done; probe++) {
+            u64 cur = load_key(&gen[h].key);
+            if (cur == BK_EMPTY) cur = cas_u64(&gen[h].key, BK_EMPTY, kmer);
+            if (cur == BK_EMPTY || cur == kmer) { atomicAdd(&gen[h].cnt, c); done = true; }
+            h = (h + 1) & mask;
+        }
+        if (!done) *full = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -179,6 +179,31 @@ int bk_write_pileup(bk_ctx* ctx, const char* out_path);
 /* clean_sample_id (src/util.rs:30-50) → buf; returns needed size incl. NUL */
 uint64_t bk_clean_sample_id(const char* path, char* buf, uint64_t cap);
 
+/* ---- read-sharded deep sample (BASELINE config C3) -----------------------------
+ * Every rank scans its share of the reads of ONE sample with bk_reads_push*.  The pileup is a MAX over
+ * globally summed, thresholded (>= min_kmers), saturated counts (src/call.rs:1172-1173, 1342-1343), so the
+ * k-mer counts are merged across ranks BEFORE the threshold and the pileups combined afterwards.  The
+ * library only exposes / re-imports device buffers; the host moves them (NCCL via torch.distributed in
+ * bronko_b200/dist.py).  Call order per sample:
+ *   bk_shard_config (once, between samples) ; bk_sample_begin ; bk_reads_push* ;
+ *   per file: bk_shard_begin → host: all-reduce(SUM) d_ref_counts in place, all-to-all the novel pairs by
+ *             part_off → bk_shard_import_novel(merged pairs this rank owns) ;
+ *   bk_shard_map_stats → host: all-reduce(SUM) the tallies in place and the partial KMC numbers ;
+ *   bk_shard_select_pileup(global KMC numbers) → host: all-reduce(MAX) arrays 0,1 and (SUM) arrays 2,3 ;
+ *   bk_shard_score → the same bk_sample_result on every rank. */
+int bk_shard_config(bk_ctx* ctx, uint32_t rank, uint32_t n_ranks);
+/* d_ref_counts: n_ref_counts u32 (one per distinct reference k-mer); novel pairs: u64 k-mers / u32 counts,
+ * grouped by owner rank, rank r owns [part_off[r], part_off[r+1]) (part_off: n_ranks+1 entries, host). */
+int bk_shard_begin(bk_ctx* ctx, int file_slot, void** d_ref_counts, uint64_t* n_ref_counts,
+                   void** d_novel_kmers, void** d_novel_counts, uint64_t* part_off);
+int bk_shard_import_novel(bk_ctx* ctx, int file_slot, const void* d_kmers, const void* d_counts, uint64_t n);
+/* d_tallies{0,1}: n_tallies u32 per file ([genome][perfect, variant, unique, present]); partial[2]: this
+ * rank's share of the four KMC numbers per file (sum over ranks = the sample's numbers). */
+int bk_shard_map_stats(bk_ctx* ctx, void** d_tallies0, void** d_tallies1, uint64_t* n_tallies, bk_kmc_stats* partial);
+/* d_pile: 4 consecutive u32 arrays of n_per_array elements (fwd depth, rev depth, fwd support, rev support). */
+int bk_shard_select_pileup(bk_ctx* ctx, const bk_kmc_stats* global_kmc, void** d_pile, uint64_t* n_per_array);
+int bk_shard_score(bk_ctx* ctx, bk_sample_result* out);
+
 /* ---- pinned host memory helpers ---------------------------------------------------------- */
 void* bk_host_alloc(uint64_t bytes);
 void bk_host_free(void* p);

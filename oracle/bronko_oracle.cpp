@@ -1069,6 +1069,35 @@ void* orc_sample_run(void* index, const Params* pr, int n_files, void** counts) 
     if (s->best >= 0) call_variants(s, *pr);
     return s;
 }
+// Stages for the read-sharded protocol tests (tests/test_dist_cpu.py): map only (no selection), then
+// call_variants on externally combined pileups of a given genome.
+void* orc_sample_map_only(void* index, const Params* pr, int n_files, void** counts) {
+    Sample* s = new Sample();
+    s->ix = (Index*)index; s->n_files = n_files;
+    initialize_output_maps(s);
+    for (int f = 0; f < n_files; f++) {
+        map_kmers(s, (Counts*)counts[f], *pr, s->stats[f]);
+        s->unique_counted[f] = ((Counts*)counts[f])->unique_counted;
+    }
+    return s;
+}
+// arrays: 4 x rows(best) x 4 u64 replacing the genome's pileups; stats: per file n_genomes x 4 (as orc_sample_stats)
+void orc_sample_call_with(void* h, const Params* pr, int best, const u64* arrays, const u64* stats0, const u64* stats1,
+                          u64 unique_counted0, u64 unique_counted1) {
+    Sample* s = (Sample*)h;
+    const u64 r0 = s->genome_row0[best], rows = s->genome_row0[best + 1] - r0;
+    for (int a = 0; a < 4; a++) memcpy(s->arr[a].data() + r0, arrays + (size_t)a * rows * 4, rows * 32);
+    const u64* st[2] = {stats0, stats1};
+    for (int f = 0; f < s->n_files; f++)
+        for (size_t g = 0; g < s->stats[f].size(); g++) {
+            s->stats[f][g].perfect = st[f][g * 4]; s->stats[f][g].variant = st[f][g * 4 + 1];
+            s->stats[f][g].unique = st[f][g * 4 + 2]; s->stats[f][g].present = st[f][g * 4 + 3] != 0;
+        }
+    s->unique_counted[0] = unique_counted0; s->unique_counted[1] = unique_counted1;
+    s->best = best;
+    if (best >= 0) call_variants(s, *pr);
+}
+int orc_pick_best(void* h) { return pick_best_genome((Sample*)h); }
 void orc_sample_free(void* h) { delete (Sample*)h; }
 int orc_sample_best(void* h) { return ((Sample*)h)->best; }
 // out[g*4 + {0,1,2,3}] = perfect, variant, unique, present

@@ -85,6 +85,8 @@ def lib():
         "orc_counts_stats": (None, [P, P]), "orc_counts_from_list": (P, [P, P, u64]),
         "orc_counts_free": (None, [P]),
         "orc_sample_run": (P, [P, P, C.c_int, P]), "orc_sample_free": (None, [P]),
+        "orc_sample_map_only": (P, [P, P, C.c_int, P]), "orc_pick_best": (C.c_int, [P]),
+        "orc_sample_call_with": (None, [P, P, C.c_int, P, P, P, u64, u64]),
         "orc_sample_best": (C.c_int, [P]), "orc_sample_stats": (None, [P, C.c_int, P]),
         "orc_sample_genome_rows": (u64, [P, C.c_int]), "orc_sample_pileup": (None, [P, C.c_int, C.c_int, P]),
         "orc_sample_n_variants": (u64, [P]), "orc_sample_variants": (None, [P, P]),
@@ -245,12 +247,21 @@ class Counts:
 class Sample:
     """initialize_output_maps → map_kmers per file → pick_best_genome(_paired) → call_variants."""
 
-    def __init__(self, index: Index, params: Params, counts):
+    def __init__(self, index: Index, params: Params, counts, map_only=False):
         self.index = index
         self.n_files = len(counts)
         arr = (P * len(counts))(*[c.h for c in counts])
         self._keep = (counts, params)
-        self.h = lib().orc_sample_run(index.h, C.byref(params), len(counts), arr)
+        self.params = params
+        run = lib().orc_sample_map_only if map_only else lib().orc_sample_run
+        self.h = run(index.h, C.byref(params), len(counts), arr)
+
+    def call_with(self, best, arrays, stats, unique_counted):
+        """Replace genome `best`'s pileups / the tallies with externally combined ones, then call_variants."""
+        arrays = np.ascontiguousarray(arrays, dtype=np.uint64)
+        st = [np.ascontiguousarray(x, dtype=np.uint64) for x in stats] + [np.zeros(1, dtype=np.uint64)]
+        uc = list(unique_counted) + [0]
+        lib().orc_sample_call_with(self.h, C.byref(self.params), best, _ptr(arrays), _ptr(st[0]), _ptr(st[1]), uc[0], uc[1])
 
     def __del__(self):
         try:
