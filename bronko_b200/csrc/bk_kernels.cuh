@@ -583,15 +583,136 @@ __constant__ double c_tau[301];
 // One CTA per sequence of the selected genome; the iteration space i in [0, len+50) of the reference
 // loop is walked in tiles of BK_NOISE_TILE:
 //   phase 1 (all threads)  sorted minor-allele fractions of positions [t0-100, t0+T) into shared memory
-//   phase 2 (three warps)  warp 0 / lane 0: s, warp 1 / lane 0: s2 — the reference's exact operation order
-//                          (FP64, no FMA; adding or subtracting an exact +0.0 where the reference skips the
-//                          update leaves every bit unchanged, so the chains are branch-free);
+//   phase 2 (three warps)  warp 0: s, warp 1: s2 — bit-exact replication of the reference's sequential FP64
+//                          sums by binade-local integer prefix sums (noise_chain_exact; adding or
+//                          subtracting an exact +0.0 where the reference skips the update leaves every bit
+//                          unchanged, so every window slot is an operation);
 //                          warp 2 (all lanes): the 10-entry max table with its evict-by-value quirk — 32
 //                          window updates are tested per step against the current table, only the ones
 //                          that can change it are replayed serially (lane q owns entry q);
 //                          all snapshot their state after every iteration
 //   phase 3 (all threads)  n by counting (integer, order-free), then the Thompson-tau rejection loop per
 //                          output position from the snapshots
+// ------------------------------------------------------------------------------------------------
+// Exact parallel replication of a sequential FP64 accumulation  s_t = fl(s_{t-1} + x_t)  (RN-even).
+//
+// While s stays inside one binade [2^e, 2^(e+1)) its ulp is fixed, so with S = s/ulp (an integer in
+// (2^52, 2^53)) and x = X*ulp:   fl(s + x) = (S + RN(X)) * ulp   whenever X is not an exact tie
+// (fraction .5) and the result stays strictly inside the binade — RN(X) does not depend on S, hence
+// the chain is an INTEGER prefix sum.  A warp takes 256 consecutive operations (8 per lane), rounds
+// every operand to the current ulp with integer arithmetic, prefix-sums, and accepts the longest
+// prefix for which every intermediate stays inside the binade and no tie / oversized operand occurs;
+// the first operation after it is executed in real FP64 (__dadd_rn) and the scan restarts there.
+// The result is bit-identical to the sequential loop of src/call.rs:845-895 for any input.
+//   op u of a tile: position li = u / 6, allele j = (u % 6) / 2, (u & 1) ? +new : -old ; SQUARE → operand^2
+// ------------------------------------------------------------------------------------------------
+#define BK_CHAIN_E 8
+template <bool SQUARE>
+__device__ __forceinline__ double noise_chain_op(const double* __restrict__ maf, u32 u) {
+    const u32 li = u / 6, r = u - li * 6, j = r >> 1;
+    double v = (r & 1) ? maf[(li + BK_NOISE_WINDOW) * 3 + j] : maf[li * 3 + j];
+    if (SQUARE) v = __dmul_rn(v, v);
+    return (r & 1) ? v : -v;
+}
+
+template <bool SQUARE>
+__device__ __forceinline__ double noise_chain_exact(const double* __restrict__ maf, double* __restrict__ snap, u32 n_ops, double s) {
+    const u32 lane = threadIdx.x & 31;
+    u32 u0 = 0;
+    while (u0 < n_ops) {
+        const u64 sb = (u64)__double_as_longlong(s);
+        const u32 ef = (u32)(sb >> 52);                      // sign + exponent field
+        if (ef == 0 || ef >= 0x7FFu) {                       // s is zero / subnormal / negative / non-finite: one real FP64 op
+            s = __dadd_rn(s, noise_chain_op<SQUARE>(maf, u0));
+            if (u0 % 6 == 5 && lane == 0) snap[u0 / 6] = s;
+            u0 += 1;
+            continue;
+        }
+        const i32 e = (i32)ef - 1023;
+        const long long S0 = (long long)((sb & 0xFFFFFFFFFFFFFull) | (1ull << 52));
+        // ---- round this lane's 8 operands to the current ulp (integers), local prefix ----
+        long long pre[BK_CHAIN_E];
+        double xs[BK_CHAIN_E];
+        u32 bad = BK_CHAIN_E;                                // first element of this lane that cannot go the fast way
+        long long run = 0;
+#pragma unroll
+        for (u32 q = 0; q < BK_CHAIN_E; q++) {
+            const u32 u = u0 + lane * BK_CHAIN_E + q;
+            long long r = 0;
+            bool ok = u < n_ops;
+            double x = 0.0;
+            if (ok) {
+                x = noise_chain_op<SQUARE>(maf, u);
+                const u64 xb = (u64)__double_as_longlong(x);
+                const u32 xe = (u32)(xb >> 52) & 0x7FFu;
+                const u64 frac = xb & 0xFFFFFFFFFFFFFull;
+                if (xe == 0) ok = (frac == 0);               // zero contributes nothing; subnormal → slow way
+                else {
+                    const i32 sh = e - ((i32)xe - 1023);
+                    const u64 m = frac | (1ull << 52);
+                    if (sh < 1) ok = false;                  // operand as large as the sum: slow way
+                    else if (sh <= 53) {
+                        const u64 half = 1ull << (sh - 1);
+                        if ((m & ((half << 1) - 1)) == half) ok = false;      // exact tie: parity dependent → slow way
+                        r = (long long)((m + half) >> sh);
+                    }                                        // sh >= 54: |x| < ulp/2, rounds to 0
+                    if (xb >> 63) r = -r;
+                }
+            }
+            xs[q] = x;
+            if (!ok && bad == BK_CHAIN_E) bad = q;
+            run += r;
+            pre[q] = run;
+        }
+        // ---- warp exclusive scan of the lane totals ----
+        long long incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += t; }
+        const long long base = S0 + incl - run;
+        // ---- first element whose intermediate leaves the open binade (2^52, 2^53) ----
+#pragma unroll
+        for (u32 q = 0; q < BK_CHAIN_E; q++) {
+            const long long T = base + pre[q];
+            if (q < bad && !(T > (1ll << 52) && T < (1ll << 53))) bad = q;
+        }
+        const u32 badmask = __ballot_sync(0xFFFFFFFFu, bad < BK_CHAIN_E);
+        const u32 fl = badmask ? (u32)__ffs(badmask) - 1 : 32u;          // first lane with a stop
+        const u32 fq = __shfl_sync(0xFFFFFFFFu, bad, fl & 31);            // its element (valid if fl < 32)
+        const u32 n_ok = fl < 32u ? fl * BK_CHAIN_E + fq : 32u * BK_CHAIN_E;   // operations accepted this round
+        const double ulp = __longlong_as_double((long long)(ef - 52) << 52);   // 2^(e-52); e-52 > -1023 always holds here? checked below
+        // ---- snapshots + new state from the accepted prefix ----
+#pragma unroll
+        for (u32 q = 0; q < BK_CHAIN_E; q++) {
+            const u32 idx = lane * BK_CHAIN_E + q, u = u0 + idx;
+            if (idx < n_ok && u < n_ops && u % 6 == 5) {
+                const u64 T = (u64)(base + pre[q]);
+                snap[u / 6] = __longlong_as_double((long long)(((u64)ef << 52) | (T & 0xFFFFFFFFFFFFFull)));
+            }
+        }
+        (void)ulp;
+        if (n_ok > 0) {
+            const u32 last = n_ok - 1, ll = last / BK_CHAIN_E, lq = last - ll * BK_CHAIN_E;
+            long long Tl = 0;
+#pragma unroll
+            for (u32 q = 0; q < BK_CHAIN_E; q++) if (q == lq) Tl = base + pre[q];
+            Tl = __shfl_sync(0xFFFFFFFFu, Tl, ll);
+            s = __longlong_as_double((long long)(((u64)ef << 52) | ((u64)Tl & 0xFFFFFFFFFFFFFull)));
+        }
+        u0 += n_ok;
+        // ---- the operation that stopped the round, in real FP64 ----
+        if (fl < 32u && u0 < n_ops) {
+            double xe = 0.0;
+#pragma unroll
+            for (u32 q = 0; q < BK_CHAIN_E; q++) if (q == fq) xe = xs[q];
+            xe = __shfl_sync(0xFFFFFFFFu, xe, fl);
+            s = __dadd_rn(s, xe);
+            if (u0 % 6 == 5 && lane == 0) snap[u0 / 6] = s;
+            u0 += 1;
+        }
+    }
+    return s;
+}
+
 __device__ __forceinline__ bool noise_table_event(double old, double nw, double m_last) {
     // evict (src/call.rs:857-869) can only hit if some entry is within 1e-12 of `old`: impossible when the
     // table is full and its smallest entry exceeds `old` by more than 1e-9; insert (src/call.rs:872-890)
@@ -620,7 +741,7 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
     }
     const u32 iters = len + BK_NOISE_HALF;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double sum = 0.0;                 // warp 0 lane 0: s ; warp 1 lane 0: s2
+    double sum = 0.0;                 // warp 0: s ; warp 1: s2 (uniform over the warp)
     double mt = 0.0, m_last = 0.0;    // warp 2: lane q < 10 owns table entry q; m_last = entry 9 (uniform)
     double* vers = vers_all + (size_t)blockIdx.x * BK_NOISE_VERS * BK_NOISE_TABLE;
 
@@ -647,34 +768,9 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
         __syncthreads();
         // ---- phase 2 ----
         if (wid == 0) {
-            if (lane == 0) {                                                     // src/call.rs:845-895, s
-                const double* __restrict__ mf = maf;
-                double* __restrict__ out = snap_s;
-#pragma unroll 8
-                for (u32 li = 0; li < tn; li++) {
-                    const double* po = mf + li * 3;                              // position i - 100
-                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;          // position i
-#pragma unroll
-                    for (u32 j = 0; j < 3; j++) { sum = __dsub_rn(sum, po[j]); sum = __dadd_rn(sum, pn[j]); }
-                    out[li] = sum;
-                }
-            }
+            sum = noise_chain_exact<false>(maf, snap_s, tn * 6, sum);            // src/call.rs:845-895: s
         } else if (wid == 1) {
-            if (lane == 0) {                                                     // s2
-                const double* __restrict__ mf = maf;
-                double* __restrict__ out = snap_s2;
-#pragma unroll 8
-                for (u32 li = 0; li < tn; li++) {
-                    const double* po = mf + li * 3;
-                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;
-#pragma unroll
-                    for (u32 j = 0; j < 3; j++) {
-                        const double o = po[j], w = pn[j];
-                        sum = __dsub_rn(sum, __dmul_rn(o, o)); sum = __dadd_rn(sum, __dmul_rn(w, w));
-                    }
-                    out[li] = sum;
-                }
-            }
+            sum = noise_chain_exact<true>(maf, snap_s2, tn * 6, sum);            // s2
         } else if (wid == 2) {
             // max table: lane q < 10 owns entry q.  32 window updates are tested per step against the
             // current table; only those that can change it are replayed (in order), each replay costs a

@@ -129,6 +129,17 @@ def test_n_fixed_too_large_queries_no_bucket(ctx_sars, oracle):
     assert e.value.code == -4
 
 
+@pytest.mark.parametrize("depth,kw", [(12, dict(min_kmers=1, min_depth=1, min_variant_depth=1)), (40, dict(min_kmers=2, min_depth=1)),
+                                      (150, dict())])
+def test_sparse_coverage_noise_chain(ctx_hpv, depth, kw):
+    """Thin, gappy coverage: the windowed sums keep returning to (near) zero and cross binades all the time —
+    the worst case for the exact parallel replication of the reference's sequential FP64 sums."""
+    import bronko_b200
+    c, oi = ctx_hpv
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.HPV16), depth, sim.SEED0 + 71 + depth)
+    run_both(c, oi, [(r1, o1), (r2, o2)], bronko_b200.CallArgs(**kw))
+
+
 def test_many_genome_map_kernel_on_small_db(sars_paths, oracle, monkeypatch):
     """The warp-per-k-mer map kernel (used for > 4 genomes) must agree with the thread-per-k-mer one."""
     import bronko_b200
