@@ -117,18 +117,49 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
     if ((threadIdx.x & 31) == 0 && created) atomicAdd(gen_new, created);
 }
 
-// k_leftover: one warp per queued stretch; lane j counts k-mers j, j+32, ... of the stretch.
+// k_leftover: one LANE per queued stretch.  The lane rolls the k-mers of its stretch (one byte per
+// k-mer, non-ACGT bytes reset the roll: KMC splits reads there) and counts each with count_one().
+// Stretches longer than BK_LEFT_LONG k-mers (foreign reads, wrong diagonals) are handled by the whole
+// warp afterwards, lane j taking k-mers j, j+32, ...
+#define BK_LEFT_LONG 96
 __global__ void __launch_bounds__(256)
 k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
     const u32 n = min(*v.n_desc, v.desc_cap);
     const u32 lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const u32 stride = gridDim.x * blockDim.x;
     const u32* gw = reinterpret_cast<const u32*>(bases);
     auto ld = [gw](u32 i) { return __ldg(gw + i); };
+    const u32 k = v.k;
+    const u64 kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
     u32 created = 0;
-    for (u32 i = warp; i < n; i += n_warps) {
-        const uint2 d = v.desc[i];
-        created += count_stretch(v, ld, d.x, d.y, lane, 32);
+    const u32 n_round = (n + 31) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        uint2 d = make_uint2(0, 0);
+        if (i < n) d = v.desc[i];
+        const bool is_long = d.y > BK_LEFT_LONG;
+        if (d.y != 0 && !is_long) {
+            const u32 n_bytes = d.y + k - 1;
+            u64 km = 0; u32 run = 0;
+            u32 word = 0;
+            for (u32 b = 0; b < n_bytes; b++) {
+                const u32 addr = d.x + b;
+                if (b == 0 || (addr & 3) == 0) word = ld(addr >> 2);
+                const u32 c = (word >> (8 * (addr & 3))) & 0xFFu;
+                const u32 up = c & 0xDFu;
+                const bool ok = up == 'A' || up == 'C' || up == 'G' || up == 'T';
+                const u32 code = ((up >> 1) ^ (up >> 2)) & 3u;
+                km = ((km << 2) | code) & kmask;
+                run = ok ? run + 1 : 0;
+                if (run >= k) created += count_one(v, km);
+            }
+        }
+        u32 lm = __ballot_sync(0xFFFFFFFFu, is_long);
+        while (lm) {
+            const u32 src = __ffs(lm) - 1;
+            lm &= lm - 1;
+            const u32 off = __shfl_sync(0xFFFFFFFFu, d.x, src), cnt = __shfl_sync(0xFFFFFFFFu, d.y, src);
+            created += count_stretch(v, ld, off, cnt, lane, 32);
+        }
     }
     created = warp_sum_u32(created);
     if (lane == 0 && created) atomicAdd(gen_new, created);
@@ -742,7 +773,7 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
     const u32 iters = len + BK_NOISE_HALF;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double sum = 0.0;                 // warp 0: s ; warp 1: s2 (uniform over the warp)
-    double mt = 0.0, m_last = 0.0;    // warp 2: lane q < 10 owns table entry q; m_last = entry 9 (uniform)
+    double mt = 0.0;                  // warp 2: lane q < 10 owns table entry q
     double* vers = vers_all + (size_t)blockIdx.x * BK_NOISE_VERS * BK_NOISE_TABLE;
 
     for (u32 t0 = 0; t0 < iters; t0 += BK_NOISE_TILE) {
@@ -772,57 +803,81 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
         } else if (wid == 1) {
             sum = noise_chain_exact<true>(maf, snap_s2, tn * 6, sum);            // s2
         } else if (wid == 2) {
-            // max table: lane q < 10 owns entry q.  32 window updates are tested per step against the
-            // current table; only those that can change it are replayed (in order), each replay costs a
-            // couple of ballots/shuffles.  Every table state of the tile is kept as a "version" in a
-            // global scratch area; positions only record which version they see.
+            // max table: lane q < 10 owns entry q (bit pattern; positive doubles order like their bits, so
+            // the hot path is integer-only).  32 window updates are tested per step against the current
+            // table; only those that can change it are replayed (in order).  Every table state of the tile
+            // is kept as a "version" in a global scratch area; positions only record which version they see.
+            //   insert candidate: new > last entry (src/call.rs:872-890)
+            //   evict candidate : old >= thr, where thr is safely below (smallest positive entry - 1e-12):
+            //                     the entry's bit pattern minus 2^36 (>= 7.6e-6 relative) when the entry is
+            //                     >= 1e-6, else 0 — anything below thr cannot be within 1e-12 of an entry
             u32 ver = 0;
+            u64 mtb = (u64)__double_as_longlong(mt);
             if (lane < BK_NOISE_TABLE) vers[lane] = mt;
+#define BK_TALLY()                                                                                   \
+    do {                                                                                             \
+        m_lastb = __shfl_sync(0xFFFFFFFFu, mtb, BK_NOISE_TABLE - 1);                                 \
+        u64 pminb = m_lastb;                                                                         \
+        if (m_lastb == 0) {                                                                          \
+            const u32 nz = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0);            \
+            const u32 cnt = __popc(nz);                                                              \
+            pminb = __shfl_sync(0xFFFFFFFFu, mtb, cnt ? cnt - 1 : 0);                                \
+            if (!cnt) pminb = ~0ull;                                                                 \
+        }                                                                                            \
+        thrb = pminb == ~0ull ? ~0ull : (pminb >= 0x3EB0C6F7A0B5ED8Dull ? pminb - (1ull << 36) : 0ull); \
+    } while (0)
+            u64 m_lastb, thrb;
+            BK_TALLY();
             const u32 n_ops = tn * 3;
             for (u32 u0 = 0; u0 < n_ops; u0 += 32) {
                 const u32 u = u0 + lane;
                 const bool in_range = u < n_ops;
                 const u32 li = u / 3, j = u - li * 3;
                 const double old = in_range ? maf[li * 3 + j] : 0.0;
-                const double nw = in_range ? maf[(li + BK_NOISE_WINDOW) * 3 + j] : 0.0;
+                const u64 oldb = (u64)__double_as_longlong(old);
+                const u64 nwb = in_range ? (u64)__double_as_longlong(maf[(li + BK_NOISE_WINDOW) * 3 + j]) : 0ull;
                 u32 done = 0;                                                    // lanes below `done` are finished
                 for (;;) {
-                    const bool cand = in_range && lane >= done && noise_table_event(old, nw, m_last);
+                    const bool cand = lane >= done && ((oldb != 0 && oldb >= thrb) || nwb > m_lastb);
                     const u32 mask = __ballot_sync(0xFFFFFFFFu, cand);
                     const u32 first = mask ? (u32)__ffs(mask) - 1 : 32u;
                     // ops [done, first) leave the table as it is
                     if (in_range && lane >= done && lane < first && j == 2) pos_ver[li] = ver;
                     if (first == 32u) break;
-                    const double e_old = __shfl_sync(0xFFFFFFFFu, old, first);
-                    const double e_new = __shfl_sync(0xFFFFFFFFu, nw, first);
+                    const u64 e_oldb = __shfl_sync(0xFFFFFFFFu, oldb, first);
+                    const u64 e_newb = __shfl_sync(0xFFFFFFFFu, nwb, first);
                     bool changed = false;
-                    if (e_old > 0.0) {                                           // evict: src/call.rs:857-869
-                        const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && fabs(__dsub_rn(mt, e_old)) < 1e-12);
-                        const double nxt = __shfl_down_sync(0xFFFFFFFFu, mt, 1);
-                        if (hm) {
+                    if (e_oldb != 0 && e_oldb >= thrb) {                         // evict: src/call.rs:857-869
+                        const double e_old = __longlong_as_double((long long)e_oldb);
+                        const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0 &&
+                                                     fabs(__dsub_rn(__longlong_as_double((long long)mtb), e_old)) < 1e-12);
+                        if (hm) {                                                // first (= largest) entry within 1e-12
                             const u32 pos = (u32)__ffs(hm) - 1;
-                            if (lane >= pos && lane < BK_NOISE_TABLE) mt = (lane == BK_NOISE_TABLE - 1) ? 0.0 : nxt;
+                            const u64 nxt = __shfl_down_sync(0xFFFFFFFFu, mtb, 1);
+                            if (lane >= pos && lane < BK_NOISE_TABLE) mtb = (lane == BK_NOISE_TABLE - 1) ? 0ull : nxt;
                             changed = true;
+                            m_lastb = 0;                                         // the hole is never refilled
                         }
                     }
-                    const double last = __shfl_sync(0xFFFFFFFFu, mt, BK_NOISE_TABLE - 1);
-                    if (e_new > 0.0 && e_new > last) {                           // insert: src/call.rs:872-890
-                        const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_new > mt);
+                    if (e_newb > m_lastb) {                                      // insert: src/call.rs:872-890
+                        const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_newb > mtb);
                         const u32 pos = (u32)__ffs(gm) - 1;                      // non-increasing table: '>' holds on a suffix
-                        const double prv = __shfl_up_sync(0xFFFFFFFFu, mt, 1);
-                        if (lane < BK_NOISE_TABLE && lane > pos) mt = prv;
-                        if (lane == pos) mt = e_new;
+                        const u64 prv = __shfl_up_sync(0xFFFFFFFFu, mtb, 1);
+                        if (lane < BK_NOISE_TABLE && lane > pos) mtb = prv;
+                        if (lane == pos) mtb = e_newb;
                         changed = true;
                     }
                     if (changed) {
-                        m_last = __shfl_sync(0xFFFFFFFFu, mt, BK_NOISE_TABLE - 1);
+                        BK_TALLY();
                         ver++;
-                        if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = mt;
+                        if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = __longlong_as_double((long long)mtb);
                     }
                     if (lane == first && j == 2) pos_ver[li] = ver;
                     done = first + 1;
                 }
             }
+#undef BK_TALLY
+            mt = __longlong_as_double((long long)mtb);
             __threadfence_block();
         }
         __syncthreads();
