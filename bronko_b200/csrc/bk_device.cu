@@ -94,6 +94,7 @@ struct bk_ctx {
     u32 shard_rank = 0, shard_n = 1;
     bk_kmc_stats shard_kmc[2];
     DevBuf<u32> d_part;
+    bool noise_debug = false; DevBuf<unsigned long long> d_dbg;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
 
     // results
@@ -179,6 +180,8 @@ int bk_create(bk_ctx** out, int device) {
     memset(&ctx->result, 0, sizeof ctx->result);
     bk_params_default(&ctx->params);
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
+    ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
+    if (ctx->noise_debug) ctx->d_dbg.reserve(16);
     *out = ctx;
     return BK_OK;
 }
@@ -194,7 +197,7 @@ void bk_destroy(bk_ctx* ctx) {
     for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
     ctx->d_part.release();
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
-    ctx->d_noise.release(); ctx->d_noise_vers.release(); ctx->d_vars.release();
+    ctx->d_noise.release(); ctx->d_noise_vers.release(); ctx->d_dbg.release(); ctx->d_vars.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < 2; i++) { if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]); if (ctx->stage_copied[i]) cudaEventDestroy(ctx->stage_copied[i]); }
@@ -633,7 +636,15 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
     sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
     const u32 row_blocks = (d.max_genome_rows + 255) / 256;
-    k_noise<<<ctx->max_seqs_per_genome, BK_NOISE_THREADS, BK_NOISE_SMEM, st>>>(sv, ctx->d_noise.p, ctx->d_noise_vers.p);
+    if (ctx->noise_debug) cudaMemsetAsync(ctx->d_dbg.p, 0, 128, st);
+    k_noise<<<ctx->max_seqs_per_genome, BK_NOISE_THREADS, BK_NOISE_SMEM, st>>>(sv, ctx->d_noise.p, ctx->d_noise_vers.p, ctx->noise_debug ? ctx->d_dbg.p : nullptr);
+    if (ctx->noise_debug) {        // BK_NOISE_DEBUG=1: cycles spent by the three phase-2 roles and by phases 2 / 3
+        unsigned long long h[16];
+        cudaMemcpyAsync(h, ctx->d_dbg.p, 128, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[k_noise cycles] s-chain %llu  s2-chain %llu  table %llu  phase2 %llu  phase3 %llu\n", h[0], h[1], h[2], h[3], h[4]);
+        fprintf(stderr, "[k_noise table] votes %llu  candidates %llu  evict tests %llu  evictions %llu  inserts %llu\n", h[5], h[6], h[7], h[8], h[9]);
+    }
     CallParams cp;
     const bk_params& p = ctx->params;
     cp.k = p.k; cp.no_end_filter = p.no_end_filter; cp.no_strand_filter = p.no_strand_filter;

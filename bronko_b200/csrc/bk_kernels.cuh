@@ -605,7 +605,7 @@ struct ScoreView {
 #define BK_NOISE_TILE 512
 #define BK_NOISE_THREADS 256
 // dynamic shared memory of k_noise, bytes
-#define BK_NOISE_SMEM ((BK_NOISE_TILE + BK_NOISE_WINDOW) * 3 * 8 + BK_NOISE_TILE * (8 + 8 + 4) + 16)
+#define BK_NOISE_SMEM ((BK_NOISE_TILE + BK_NOISE_WINDOW) * 3 * 8 + BK_NOISE_TILE * (8 + 8 + 4) + (BK_NOISE_TILE + BK_NOISE_WINDOW) * 4 + 16)
 // table versions a tile can create (one per window update at most) + the one it starts with
 #define BK_NOISE_VERS (BK_NOISE_TILE * 3 + 1)
 
@@ -614,136 +614,16 @@ __constant__ double c_tau[301];
 // One CTA per sequence of the selected genome; the iteration space i in [0, len+50) of the reference
 // loop is walked in tiles of BK_NOISE_TILE:
 //   phase 1 (all threads)  sorted minor-allele fractions of positions [t0-100, t0+T) into shared memory
-//   phase 2 (three warps)  warp 0: s, warp 1: s2 — bit-exact replication of the reference's sequential FP64
-//                          sums by binade-local integer prefix sums (noise_chain_exact; adding or
-//                          subtracting an exact +0.0 where the reference skips the update leaves every bit
-//                          unchanged, so every window slot is an operation);
+//   phase 2 (three warps)  warp 0 / lane 0: s, warp 1 / lane 0: s2 — the reference's exact operation order
+//                          (FP64, no FMA; adding or subtracting an exact +0.0 where the reference skips the
+//                          update leaves every bit unchanged, so the chains are branch-free; measured
+//                          ~14 cycles per dependent DADD on B200);
 //                          warp 2 (all lanes): the 10-entry max table with its evict-by-value quirk — 32
 //                          window updates are tested per step against the current table, only the ones
 //                          that can change it are replayed serially (lane q owns entry q);
 //                          all snapshot their state after every iteration
 //   phase 3 (all threads)  n by counting (integer, order-free), then the Thompson-tau rejection loop per
 //                          output position from the snapshots
-// ------------------------------------------------------------------------------------------------
-// Exact parallel replication of a sequential FP64 accumulation  s_t = fl(s_{t-1} + x_t)  (RN-even).
-//
-// While s stays inside one binade [2^e, 2^(e+1)) its ulp is fixed, so with S = s/ulp (an integer in
-// (2^52, 2^53)) and x = X*ulp:   fl(s + x) = (S + RN(X)) * ulp   whenever X is not an exact tie
-// (fraction .5) and the result stays strictly inside the binade — RN(X) does not depend on S, hence
-// the chain is an INTEGER prefix sum.  A warp takes 256 consecutive operations (8 per lane), rounds
-// every operand to the current ulp with integer arithmetic, prefix-sums, and accepts the longest
-// prefix for which every intermediate stays inside the binade and no tie / oversized operand occurs;
-// the first operation after it is executed in real FP64 (__dadd_rn) and the scan restarts there.
-// The result is bit-identical to the sequential loop of src/call.rs:845-895 for any input.
-//   op u of a tile: position li = u / 6, allele j = (u % 6) / 2, (u & 1) ? +new : -old ; SQUARE → operand^2
-// ------------------------------------------------------------------------------------------------
-#define BK_CHAIN_E 8
-template <bool SQUARE>
-__device__ __forceinline__ double noise_chain_op(const double* __restrict__ maf, u32 u) {
-    const u32 li = u / 6, r = u - li * 6, j = r >> 1;
-    double v = (r & 1) ? maf[(li + BK_NOISE_WINDOW) * 3 + j] : maf[li * 3 + j];
-    if (SQUARE) v = __dmul_rn(v, v);
-    return (r & 1) ? v : -v;
-}
-
-template <bool SQUARE>
-__device__ __forceinline__ double noise_chain_exact(const double* __restrict__ maf, double* __restrict__ snap, u32 n_ops, double s) {
-    const u32 lane = threadIdx.x & 31;
-    u32 u0 = 0;
-    while (u0 < n_ops) {
-        const u64 sb = (u64)__double_as_longlong(s);
-        const u32 ef = (u32)(sb >> 52);                      // sign + exponent field
-        if (ef == 0 || ef >= 0x7FFu) {                       // s is zero / subnormal / negative / non-finite: one real FP64 op
-            s = __dadd_rn(s, noise_chain_op<SQUARE>(maf, u0));
-            if (u0 % 6 == 5 && lane == 0) snap[u0 / 6] = s;
-            u0 += 1;
-            continue;
-        }
-        const i32 e = (i32)ef - 1023;
-        const long long S0 = (long long)((sb & 0xFFFFFFFFFFFFFull) | (1ull << 52));
-        // ---- round this lane's 8 operands to the current ulp (integers), local prefix ----
-        long long pre[BK_CHAIN_E];
-        double xs[BK_CHAIN_E];
-        u32 bad = BK_CHAIN_E;                                // first element of this lane that cannot go the fast way
-        long long run = 0;
-#pragma unroll
-        for (u32 q = 0; q < BK_CHAIN_E; q++) {
-            const u32 u = u0 + lane * BK_CHAIN_E + q;
-            long long r = 0;
-            bool ok = u < n_ops;
-            double x = 0.0;
-            if (ok) {
-                x = noise_chain_op<SQUARE>(maf, u);
-                const u64 xb = (u64)__double_as_longlong(x);
-                const u32 xe = (u32)(xb >> 52) & 0x7FFu;
-                const u64 frac = xb & 0xFFFFFFFFFFFFFull;
-                if (xe == 0) ok = (frac == 0);               // zero contributes nothing; subnormal → slow way
-                else {
-                    const i32 sh = e - ((i32)xe - 1023);
-                    const u64 m = frac | (1ull << 52);
-                    if (sh < 1) ok = false;                  // operand as large as the sum: slow way
-                    else if (sh <= 53) {
-                        const u64 half = 1ull << (sh - 1);
-                        if ((m & ((half << 1) - 1)) == half) ok = false;      // exact tie: parity dependent → slow way
-                        r = (long long)((m + half) >> sh);
-                    }                                        // sh >= 54: |x| < ulp/2, rounds to 0
-                    if (xb >> 63) r = -r;
-                }
-            }
-            xs[q] = x;
-            if (!ok && bad == BK_CHAIN_E) bad = q;
-            run += r;
-            pre[q] = run;
-        }
-        // ---- warp exclusive scan of the lane totals ----
-        long long incl = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += t; }
-        const long long base = S0 + incl - run;
-        // ---- first element whose intermediate leaves the open binade (2^52, 2^53) ----
-#pragma unroll
-        for (u32 q = 0; q < BK_CHAIN_E; q++) {
-            const long long T = base + pre[q];
-            if (q < bad && !(T > (1ll << 52) && T < (1ll << 53))) bad = q;
-        }
-        const u32 badmask = __ballot_sync(0xFFFFFFFFu, bad < BK_CHAIN_E);
-        const u32 fl = badmask ? (u32)__ffs(badmask) - 1 : 32u;          // first lane with a stop
-        const u32 fq = __shfl_sync(0xFFFFFFFFu, bad, fl & 31);            // its element (valid if fl < 32)
-        const u32 n_ok = fl < 32u ? fl * BK_CHAIN_E + fq : 32u * BK_CHAIN_E;   // operations accepted this round
-        const double ulp = __longlong_as_double((long long)(ef - 52) << 52);   // 2^(e-52); e-52 > -1023 always holds here? checked below
-        // ---- snapshots + new state from the accepted prefix ----
-#pragma unroll
-        for (u32 q = 0; q < BK_CHAIN_E; q++) {
-            const u32 idx = lane * BK_CHAIN_E + q, u = u0 + idx;
-            if (idx < n_ok && u < n_ops && u % 6 == 5) {
-                const u64 T = (u64)(base + pre[q]);
-                snap[u / 6] = __longlong_as_double((long long)(((u64)ef << 52) | (T & 0xFFFFFFFFFFFFFull)));
-            }
-        }
-        (void)ulp;
-        if (n_ok > 0) {
-            const u32 last = n_ok - 1, ll = last / BK_CHAIN_E, lq = last - ll * BK_CHAIN_E;
-            long long Tl = 0;
-#pragma unroll
-            for (u32 q = 0; q < BK_CHAIN_E; q++) if (q == lq) Tl = base + pre[q];
-            Tl = __shfl_sync(0xFFFFFFFFu, Tl, ll);
-            s = __longlong_as_double((long long)(((u64)ef << 52) | ((u64)Tl & 0xFFFFFFFFFFFFFull)));
-        }
-        u0 += n_ok;
-        // ---- the operation that stopped the round, in real FP64 ----
-        if (fl < 32u && u0 < n_ops) {
-            double xe = 0.0;
-#pragma unroll
-            for (u32 q = 0; q < BK_CHAIN_E; q++) if (q == fq) xe = xs[q];
-            xe = __shfl_sync(0xFFFFFFFFu, xe, fl);
-            s = __dadd_rn(s, xe);
-            if (u0 % 6 == 5 && lane == 0) snap[u0 / 6] = s;
-            u0 += 1;
-        }
-    }
-    return s;
-}
-
 __device__ __forceinline__ bool noise_table_event(double old, double nw, double m_last) {
     // evict (src/call.rs:857-869) can only hit if some entry is within 1e-12 of `old`: impossible when the
     // table is full and its smallest entry exceeds `old` by more than 1e-9; insert (src/call.rs:872-890)
@@ -754,12 +634,13 @@ __device__ __forceinline__ bool noise_table_event(double old, double nw, double 
 }
 
 __global__ void __launch_bounds__(BK_NOISE_THREADS)
-k_noise(ScoreView sv, double* noise_max, double* vers_all) {
+k_noise(ScoreView sv, double* noise_max, double* vers_all, unsigned long long* dbg) {
     extern __shared__ __align__(16) u8 nsm[];
     double* maf = reinterpret_cast<double*>(nsm);                               // (T+100)*3
     double* snap_s = maf + (BK_NOISE_TILE + BK_NOISE_WINDOW) * 3;               // T
     double* snap_s2 = snap_s + BK_NOISE_TILE;                                   // T
     u32* pos_ver = reinterpret_cast<u32*>(snap_s2 + BK_NOISE_TILE);             // T: table version seen by iteration li
+    u32* npre = pos_ver + BK_NOISE_TILE;                                        // T+100: inclusive prefix of #positive fractions
     const i32 best = sv.ctr->best;
     if (best < 0) return;
     const u32 s = sv.genome_seq_off[best] + blockIdx.x;
@@ -772,7 +653,7 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
     }
     const u32 iters = len + BK_NOISE_HALF;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double sum = 0.0;                 // warp 0: s ; warp 1: s2 (uniform over the warp)
+    double sum = 0.0;                 // warp 0 lane 0: s ; warp 1 lane 0: s2
     double mt = 0.0;                  // warp 2: lane q < 10 owns table entry q
     double* vers = vers_all + (size_t)blockIdx.x * BK_NOISE_VERS * BK_NOISE_TABLE;
 
@@ -798,10 +679,36 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
         }
         __syncthreads();
         // ---- phase 2 ----
+        const long long t_p2 = clock64();
         if (wid == 0) {
-            sum = noise_chain_exact<false>(maf, snap_s, tn * 6, sum);            // src/call.rs:845-895: s
+            if (lane == 0) {                                                     // src/call.rs:845-895, s
+                const double* __restrict__ mf = maf;
+                double* __restrict__ out = snap_s;
+#pragma unroll 8
+                for (u32 li = 0; li < tn; li++) {
+                    const double* po = mf + li * 3;                              // position i - 100
+                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;          // position i
+#pragma unroll
+                    for (u32 j = 0; j < 3; j++) { sum = __dsub_rn(sum, po[j]); sum = __dadd_rn(sum, pn[j]); }
+                    out[li] = sum;
+                }
+            }
         } else if (wid == 1) {
-            sum = noise_chain_exact<true>(maf, snap_s2, tn * 6, sum);            // s2
+            if (lane == 0) {                                                     // s2
+                const double* __restrict__ mf = maf;
+                double* __restrict__ out = snap_s2;
+#pragma unroll 8
+                for (u32 li = 0; li < tn; li++) {
+                    const double* po = mf + li * 3;
+                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;
+#pragma unroll
+                    for (u32 j = 0; j < 3; j++) {
+                        const double o = po[j], w = pn[j];
+                        sum = __dsub_rn(sum, __dmul_rn(o, o)); sum = __dadd_rn(sum, __dmul_rn(w, w));
+                    }
+                    out[li] = sum;
+                }
+            }
         } else if (wid == 2) {
             // max table: lane q < 10 owns entry q (bit pattern; positive doubles order like their bits, so
             // the hot path is integer-only).  32 window updates are tested per step against the current
@@ -833,64 +740,106 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
                 const u32 u = u0 + lane;
                 const bool in_range = u < n_ops;
                 const u32 li = u / 3, j = u - li * 3;
-                const double old = in_range ? maf[li * 3 + j] : 0.0;
-                const u64 oldb = (u64)__double_as_longlong(old);
-                const u64 nwb = in_range ? (u64)__double_as_longlong(maf[(li + BK_NOISE_WINDOW) * 3 + j]) : 0ull;
-                u32 done = 0;                                                    // lanes below `done` are finished
-                for (;;) {
-                    const bool cand = lane >= done && ((oldb != 0 && oldb >= thrb) || nwb > m_lastb);
-                    const u32 mask = __ballot_sync(0xFFFFFFFFu, cand);
-                    const u32 first = mask ? (u32)__ffs(mask) - 1 : 32u;
-                    // ops [done, first) leave the table as it is
-                    if (in_range && lane >= done && lane < first && j == 2) pos_ver[li] = ver;
-                    if (first == 32u) break;
-                    const u64 e_oldb = __shfl_sync(0xFFFFFFFFu, oldb, first);
-                    const u64 e_newb = __shfl_sync(0xFFFFFFFFu, nwb, first);
-                    bool changed = false;
-                    if (e_oldb != 0 && e_oldb >= thrb) {                         // evict: src/call.rs:857-869
-                        const double e_old = __longlong_as_double((long long)e_oldb);
-                        const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0 &&
-                                                     fabs(__dsub_rn(__longlong_as_double((long long)mtb), e_old)) < 1e-12);
-                        if (hm) {                                                // first (= largest) entry within 1e-12
-                            const u32 pos = (u32)__ffs(hm) - 1;
-                            const u64 nxt = __shfl_down_sync(0xFFFFFFFFu, mtb, 1);
-                            if (lane >= pos && lane < BK_NOISE_TABLE) mtb = (lane == BK_NOISE_TABLE - 1) ? 0ull : nxt;
-                            changed = true;
-                            m_lastb = 0;                                         // the hole is never refilled
-                        }
+                const u64 oldb = in_range ? (u64)__double_as_longlong(maf[u]) : 0ull;               // leaving: maf[li*3+j]
+                const u64 nwb = in_range ? (u64)__double_as_longlong(maf[3 * BK_NOISE_WINDOW + u]) : 0ull;   // arriving
+                const u32 ver0 = ver;
+                u32 chg = 0;                         // lanes whose update changed the table (each made a version)
+                // Which leaving values can evict?  Exactly those within 1e-12 of an entry that is in the table
+                // when they leave: an entry of the table as it is now (tested here, all lanes at once), or one
+                // inserted earlier in this chunk (tested at insert time: the reference evicts BY VALUE, so a
+                // leaving value can remove an equal value that arrived a moment ago).
+                bool ematch = false;
+                const double old = __longlong_as_double((long long)oldb);
+                if (__any_sync(0xFFFFFFFFu, oldb != 0)) {
+#pragma unroll
+                    for (u32 q = 0; q < BK_NOISE_TABLE; q++) {
+                        const u64 tb = __shfl_sync(0xFFFFFFFFu, mtb, q);
+                        if (tb != 0 && oldb != 0 && fabs(__dsub_rn(__longlong_as_double((long long)tb), old)) < 1e-12) ematch = true;
                     }
-                    if (e_newb > m_lastb) {                                      // insert: src/call.rs:872-890
-                        const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_newb > mtb);
-                        const u32 pos = (u32)__ffs(gm) - 1;                      // non-increasing table: '>' holds on a suffix
-                        const u64 prv = __shfl_up_sync(0xFFFFFFFFu, mtb, 1);
-                        if (lane < BK_NOISE_TABLE && lane > pos) mtb = prv;
-                        if (lane == pos) mtb = e_newb;
-                        changed = true;
-                    }
-                    if (changed) {
-                        BK_TALLY();
-                        ver++;
-                        if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = __longlong_as_double((long long)mtb);
-                    }
-                    if (lane == first && j == 2) pos_ver[li] = ver;
-                    done = first + 1;
                 }
+                u32 from = 0;
+                for (;;) {
+                    // Candidates among lanes >= from against the CURRENT last entry.  Until an eviction makes a
+                    // hole an insert only raises the last entry, so the mask stays a superset of the updates that
+                    // can change the table and its bits are walked in order without re-voting.
+                    u32 cm = __ballot_sync(0xFFFFFFFFu, lane >= from && (ematch || nwb > m_lastb));
+                    bool restart = false;
+                    if (dbg && lane == 0) { atomicAdd(dbg + 5, 1ull); atomicAdd(dbg + 6, (unsigned long long)__popc(cm)); }
+                    while (cm) {
+                        const u32 src = (u32)__ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const u64 e_newb = __shfl_sync(0xFFFFFFFFu, nwb, src);
+                        const bool e_ev = __shfl_sync(0xFFFFFFFFu, ematch ? 1 : 0, src) != 0;
+                        bool changed = false;
+                        if (e_ev) {                                              // evict: src/call.rs:857-869
+                            if (dbg && lane == 0) atomicAdd(dbg + 7, 1ull);
+                            const double e_old = __shfl_sync(0xFFFFFFFFu, old, src);
+                            const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0 &&
+                                                         fabs(__dsub_rn(__longlong_as_double((long long)mtb), e_old)) < 1e-12);
+                            if (hm) {                                            // first (= largest) entry within 1e-12
+                                const u32 pos = (u32)__ffs(hm) - 1;
+                                const u64 nxt = __shfl_down_sync(0xFFFFFFFFu, mtb, 1);
+                                if (lane >= pos && lane < BK_NOISE_TABLE) mtb = (lane == BK_NOISE_TABLE - 1) ? 0ull : nxt;
+                                changed = true;
+                                restart = true;                                  // a hole: insert candidates must be re-derived
+                                if (dbg && lane == 0) atomicAdd(dbg + 8, 1ull);
+                            }
+                        }
+                        {                                                        // insert: src/call.rs:872-890
+                            const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_newb > mtb);
+                            const u64 prv = __shfl_up_sync(0xFFFFFFFFu, mtb, 1);
+                            if (gm) {                                            // beats the (current) last entry
+                                const u32 pos = (u32)__ffs(gm) - 1;              // non-increasing table: '>' holds on a suffix
+                                if (lane < BK_NOISE_TABLE && lane > pos) mtb = prv;
+                                if (lane == pos) mtb = e_newb;
+                                changed = true;
+                                if (dbg && lane == 0) atomicAdd(dbg + 9, 1ull);
+                                // later leaving values within 1e-12 of the new entry become eviction candidates
+                                const bool hit = lane > src && !ematch && oldb != 0 &&
+                                                 fabs(__dsub_rn(__longlong_as_double((long long)e_newb), old)) < 1e-12;
+                                if (hit) ematch = true;
+                                cm |= __ballot_sync(0xFFFFFFFFu, hit);
+                            }
+                        }
+                        if (changed) {
+                            chg |= 1u << src;
+                            ver = ver0 + __popc(chg);
+                            if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = __longlong_as_double((long long)mtb);
+                        }
+                        if (restart) { from = src + 1; break; }
+                    }
+                    BK_TALLY();
+                    if (!restart) break;
+                }
+                // the version every position of this chunk sees after its third update
+                if (in_range && j == 2) pos_ver[li] = ver0 + __popc(chg & (0xFFFFFFFFu >> (31 - lane)));
             }
 #undef BK_TALLY
             mt = __longlong_as_double((long long)mtb);
             __threadfence_block();
+        } else if (wid == 3) {
+            // n is order-free: prefix counts of positive fractions, so that phase 3 gets n with two loads
+            u32 carry = 0;
+            for (u32 x0 = 0; x0 < tn + BK_NOISE_WINDOW; x0 += 32) {
+                const u32 x = x0 + lane;
+                u32 c = 0;
+                if (x < tn + BK_NOISE_WINDOW) c = (maf[x * 3] > 0.0 ? 1u : 0u) + (maf[x * 3 + 1] > 0.0 ? 1u : 0u) + (maf[x * 3 + 2] > 0.0 ? 1u : 0u);
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, c, o); if (lane >= (u32)o) c += t; }
+                if (x < tn + BK_NOISE_WINDOW) npre[x] = carry + c;
+                carry += __shfl_sync(0xFFFFFFFFu, c, 31);
+            }
         }
+        if (dbg && lane == 0 && wid < 3) atomicAdd(dbg + wid, (unsigned long long)(clock64() - t_p2));   // BK_NOISE_DEBUG=1
         __syncthreads();
+        if (dbg && threadIdx.x == 0) atomicAdd(dbg + 3, (unsigned long long)(clock64() - t_p2));
+        const long long t_p3 = clock64();
         // ---- phase 3: n, then Thompson tau per output position w = i - 50 (src/call.rs:898-961) ----
         for (u32 li = threadIdx.x; li < tn; li += blockDim.x) {
             const u32 i = t0 + li;
             if (i < BK_NOISE_HALF) continue;
             // n after iteration i = number of positive fractions among positions [i-99, i]
-            u32 cn0 = 0;
-            for (u32 x = 0; x < BK_NOISE_WINDOW; x++) {
-                const double* pp = maf + (li + 1 + x) * 3;
-                cn0 += (pp[0] > 0.0 ? 1u : 0u) + (pp[1] > 0.0 ? 1u : 0u) + (pp[2] > 0.0 ? 1u : 0u);
-            }
+            const u32 cn0 = npre[li + BK_NOISE_WINDOW] - npre[li];
             const double s0 = snap_s[li], s20 = snap_s2[li];
             const double* mxp = vers + (size_t)pos_ver[li] * BK_NOISE_TABLE;   // written this tile by warp 2: read through L2
 
@@ -915,6 +864,7 @@ k_noise(ScoreView sv, double* noise_max, double* vers_all) {
             noise_max[r0 + i - BK_NOISE_HALF] = cand;
         }
         __syncthreads();
+        if (dbg && threadIdx.x == 0) atomicAdd(dbg + 4, (unsigned long long)(clock64() - t_p3));
     }
 }
 
