@@ -20,16 +20,27 @@
 #define BK_HD __device__ __forceinline__
 #define BK_CLZLL(x) __clzll((long long)(x))
 #define BK_POPCLL(x) __popcll((unsigned long long)(x))
+#define BK_POPC(x) __popc((unsigned)(x))
+#define BK_FFS0(x) ((u32)__ffs((int)(x)) - 1u)
 #define BK_ANY(p) __any_sync(0xFFFFFFFFu, (p))
 #define BK_SYNCWARP() __syncwarp()
 #define BK_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
+#define BK_PRMT(x, y, sel) __byte_perm((x), (y), (sel))
 #else
 #define BK_HD static inline
 #define BK_CLZLL(x) __builtin_clzll((unsigned long long)(x))
 #define BK_POPCLL(x) __builtin_popcountll((unsigned long long)(x))
+#define BK_POPC(x) __builtin_popcount((unsigned)(x))
+#define BK_FFS0(x) ((u32)__builtin_ctz((unsigned)(x)))
 #define BK_ANY(p) (p)
 #define BK_SYNCWARP() do {} while (0)
 #define BK_FUNNEL_R(lo, hi, sh) ((sh) ? (((lo) >> (sh)) | ((hi) << (32 - (sh)))) : (lo))
+static inline unsigned BK_PRMT(unsigned x, unsigned y, unsigned sel) {      // selector nibbles 0..7 only
+    const unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 struct uint2 { unsigned int x, y; };
 static inline uint2 make_uint2(unsigned int x, unsigned int y) { uint2 r; r.x = x; r.y = y; return r; }
 #endif
@@ -44,6 +55,7 @@ typedef uint8_t u8;
 static const u64 BK_EMPTY = ~0ull;
 
 struct GenSlot { u64 key; u32 cnt; u32 pad; };         // novel k-mer table slot, 16 B
+struct W4 { u32 x, y, z, w; };                         // one 16-byte chunk (32 bases) of the 4-bit reference
 struct ExactSlotD { u64 key; u32 gidx; u32 oseq; };    // reference k-mer table slot, 16 B
 
 BK_HD u32 hash_slot(u64 x, u32 shift) { return (u32)(((x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull) >> shift); }
@@ -130,25 +142,22 @@ BK_HD bool pack_kmer(const Ld& ld, u32 byte_off, u32 k, u64* out) {
     *out = v >> (64 - 2 * k);
     return bad == 0;
 }
-
-// 64 bits of the packed oriented reference starting at global base index g (may be out of range:
-// clamped; the caller masks those bases out).
-template <class LdRef>
-BK_HD u64 ref_word(const LdRef& ldr, i32 g, u32 n_words) {
-    i32 wi = g >> 5;
-    const u32 sh = 2 * (u32)(g & 31);
-    if (wi < 0) wi = 0;
-    if (wi > (i32)n_words - 2) wi = (i32)n_words - 2;
-    const u64 a = ldr((u32)wi);
-    if (sh == 0) return a;
-    const u64 b = ldr((u32)wi + 1);
-    return (a << sh) | (b >> (64 - sh));
+// Same when at least 32 bytes are readable from byte_off on (the branch-free packer; if any of the 32 bytes is
+// not ACGT fall back to the exact k-byte version, the offending byte may lie beyond the k-mer).
+template <class Ld>
+BK_HD bool pack_kmer32(const Ld& ld, u32 byte_off, u32 k, u64* out) {
+    u32 bad;
+    const u64 v = pack32_full(ld, byte_off, &bad);
+    if (bad) return pack_kmer(ld, byte_off, k, out);
+    *out = v >> (64 - 2 * k);
+    return true;
 }
 
 // Device-side view of everything the counting stage touches.
 struct CountView {
     u32 k;
-    const u64* refpk; u32 ref_words;
+    const u32* refnib; u32 ref_chunks;    // oriented reference, one 4-bit code per base index (A0 C1 G2 T3, padding 4),
+                                          // little-endian nibbles, in 16-byte chunks of 32 bases
     const u32* oseq_start; const u32* oseq_len;
     const ExactSlotD* exact; u32 exact_shift, exact_mask;
     u32* diff;                       // n_raw + 2
@@ -266,8 +275,8 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 // matching bases on the current diagonal.  A bad base at e (mismatch, non-ACGT byte, end of the
 // overlap with the oriented sequence, end of read) closes the stretch [ms, e): if it holds >= k bases
 // its k-mers [ms, e-k] become a run, everything pending before ms a leftover stretch.
-template <class Ld, class LdRef>
-BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, u32 len, u32 gofs, Pending& pend) {
+template <class Ld, class LdRef4>
+BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0, u32 len, u32 gofs, Pending& pend) {
     const u32 k = v.k;
     const bool has = len >= k;                   // shorter than k: contributes no k-mer
     const u32 nk = has ? len - k + 1 : 0;
@@ -285,7 +294,8 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, 
             if (!BK_ANY(need)) break;
             if (need) {
                 u64 km;
-                if (pack_kmer(ld, o0 + q, k, &km) && exact_lookup(v, km, &gidx, &oseq)) found = true;
+                const bool okk = (q + 32 <= len) ? pack_kmer32(ld, o0 + q, k, &km) : pack_kmer(ld, o0 + q, k, &km);
+                if (okk && exact_lookup(v, km, &gidx, &oseq)) found = true;
                 else q += k;
             }
             BK_SYNCWARP();
@@ -314,49 +324,88 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef& ldr, u32 o0, 
         }                                                                                   \
         ms = e__ + 1;                                                                       \
     } while (0)
+        // The oriented reference holds one 4-bit code per base: 32 bases are one aligned 16-byte chunk, and a
+        // byte-permute turns four codes into the four upper-case letters they stand for (padding → '#').  Every
+        // 32-base word of the read advances the reference by exactly one chunk, so the loop fetches ONE
+        // 16-byte chunk per lane per word (the lanes of a warp sit at unrelated reference positions: scattered
+        // requests are what bounds this kernel) and keeps the previous one.  Read bytes are case-folded
+        // (& 0xDF); byte equality with the expected letter proves "valid AND matching" in one xor.
+        const u32 wo = ((u32)g0 >> 3) & 3;                  // g0 mod 32 = nibble offset inside a chunk: word part ...
+        const u32 bs = ((u32)g0 & 7) * 4;                   // ... and bit part (the same for every word of the diagonal)
+        i32 c4 = (g0 + 32 * w) >> 5;                        // chunk holding the first base of word w
+        const i32 cmax = (i32)v.ref_chunks - 1;
+        W4 cur = {0, 0, 0, 0};
+        if (active) cur = ldr4((u32)(c4 < 0 ? 0 : (c4 > cmax ? cmax : c4)));
         for (;;) {
             const bool go = active && !bailed && w < w_end;
             if (!BK_ANY(go)) break;
             if (go) {
                 const i32 b0 = 32 * w;
-                const u32 nb = (u32)((i32)len - b0 < 32 ? (i32)len - b0 : 32);
-                u32 bad;
-                const u64 rd = pack32(ld, o0 + (u32)b0, nb, &bad);
-                const u64 rf = ref_word(ldr, g0 + b0, v.ref_words);
-                u64 x = rd ^ rf;
-                const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
-                const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
-                u64 mask = ~0ull;
-                if (lo > 0) mask &= ~0ull >> (2 * lo);
-                if (hi < 32) mask &= ~(~0ull >> (2 * hi));
-                x &= mask;
-                if ((x | bad) != 0) {                // the uncommon case: something in these 32 bases is off
-                    u64 t = (x | (x >> 1)) & 0x5555555555555555ull;
-                    if (bad) {                       // flag all 4 bases of a word holding a non-ACGT byte
-                        for (u32 i = 0; i < 8 && 4 * i < nb; i++) {
-                            u32 err;
-                            const u32 nbi = nb - 4 * i;
-                            const u32 wv = load_unaligned(ld, o0 + (u32)b0 + 4 * i);
-                            (void)pack4(wv, &err);
-                            if (nbi < 4) err &= (1u << (8 * nbi)) - 1u;
-                            if (err) t |= 0x55ull << (56 - 8 * i);
-                        }
-                        t &= mask;
+                const u32 rb = o0 + (u32)b0, rwi = rb >> 2, rsh = (rb & 3) * 8;
+                const i32 cn = c4 + 1;
+                const W4 nxt = ldr4((u32)(cn < 0 ? 0 : (cn > cmax ? cmax : cn)));
+                // the 160 reference bits of this word: words wo .. wo+4 of (cur, nxt), then shifted by bs
+                u32 d0 = cur.x, d1 = cur.y, d2 = cur.z, d3 = cur.w, d4 = nxt.x, d5 = nxt.y, d6 = nxt.z, d7 = nxt.w;
+                if (wo & 1) { d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = d5; d5 = d6; d6 = d7; }
+                if (wo & 2) { d0 = d2; d1 = d3; d2 = d4; d3 = d5; d4 = d6; }
+                const u32 e0 = BK_FUNNEL_R(d0, d1, bs), e1 = BK_FUNNEL_R(d1, d2, bs), e2 = BK_FUNNEL_R(d2, d3, bs), e3 = BK_FUNNEL_R(d3, d4, bs);
+                const u32 ee[4] = {e0, e1, e2, e3};
+                const bool inside = b0 >= i_lo && b0 + 32 <= i_hi;        // all 32 bases belong to the overlap
+                u32 xw[8];
+                u32 acc = 0;
+                u32 rp = ld(rwi);
+                if (inside) {
+#pragma unroll
+                    for (u32 i = 0; i < 8; i++) {
+                        const u32 rn = ld(rwi + i + 1);
+                        const u32 expect = BK_PRMT(0x54474341u, 0x23232323u, (i & 1) ? (ee[i >> 1] >> 16) : ee[i >> 1]);
+                        xw[i] = (BK_FUNNEL_R(rp, rn, rsh) & 0xDFDFDFDFu) ^ expect;
+                        acc |= xw[i];
+                        rp = rn;
                     }
-                    if (BK_POPCLL(t) >= BK_BAIL_MISMATCHES) {   // wrong diagonal from here on: close, re-seed
-                        const u32 p = 63 - (u32)BK_CLZLL(t);
-                        const i32 e = b0 + (i32)(31 - (p >> 1));
+                } else {                                                 // first / last word of the overlap
+                    const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
+                    const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
+#pragma unroll
+                    for (u32 i = 0; i < 8; i++) {
+                        const u32 rn = ld(rwi + i + 1);
+                        const u32 expect = BK_PRMT(0x54474341u, 0x23232323u, (i & 1) ? (ee[i >> 1] >> 16) : ee[i >> 1]);
+                        const i32 a0 = lo - 4 * (i32)i, a1 = hi - 4 * (i32)i;    // bytes of this sub-word inside [lo, hi)
+                        u32 bm = 0xFFFFFFFFu;
+                        if (a0 > 0) bm = a0 >= 4 ? 0u : bm << (8 * a0);
+                        if (a1 < 4) bm = a1 <= 0 ? 0u : bm & (0xFFFFFFFFu >> (8 * (4 - a1)));
+                        xw[i] = ((BK_FUNNEL_R(rp, rn, rsh) & 0xDFDFDFDFu) ^ expect) & bm;
+                        acc |= xw[i];
+                        rp = rn;
+                    }
+                }
+                if (acc != 0) {                                          // the uncommon case: some base is off
+                    u32 t = 0;                                           // bit j set: base b0+j is off
+#pragma unroll
+                    for (u32 i = 0; i < 8; i++) {
+                        if (xw[i]) {
+                            u32 f = xw[i] | (xw[i] >> 4);
+                            f |= f >> 2;
+                            f |= f >> 1;
+                            f &= 0x01010101u;                            // byte flags
+                            t |= ((f * 0x10204080u) >> 28) << (4 * i);   // 4 flags → 4 bits, first base lowest
+                        }
+                    }
+                    if (BK_POPC(t) >= BK_BAIL_MISMATCHES) {              // wrong diagonal from here on: close, re-seed
+                        const i32 e = b0 + (i32)BK_FFS0(t);
                         BK_EVENT(e);
                         seed_from = e + 1;
                         bailed = true;
                     } else {
                         while (t) {
-                            const u32 p = 63 - (u32)BK_CLZLL(t);
-                            t ^= 1ull << p;
-                            BK_EVENT(b0 + (i32)(31 - (p >> 1)));
+                            const u32 j = BK_FFS0(t);
+                            t &= t - 1;
+                            BK_EVENT(b0 + (i32)j);
                         }
                     }
                 }
+                cur = nxt;
+                c4 = cn;
                 w++;
             }
             BK_SYNCWARP();

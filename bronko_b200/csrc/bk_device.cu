@@ -71,7 +71,7 @@ struct bk_ctx {
     bool have_index = false;
     // device copies of the derived index
     DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
-    DevBuf<u64> d_refpk; DevBuf<u32> d_oseq_start, d_oseq_len;
+    DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
     DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
@@ -190,7 +190,7 @@ void bk_destroy(bk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    ctx->d_bucket_slots.release(); ctx->d_bucket_entries.release(); ctx->d_refpk.release(); ctx->d_oseq_start.release();
+    ctx->d_bucket_slots.release(); ctx->d_bucket_entries.release(); ctx->d_refnib.release(); ctx->d_oseq_start.release();
     ctx->d_oseq_len.release(); ctx->d_exact.release(); ctx->d_slot2id.release(); ctx->d_id_kmer.release();
     ctx->d_genome_row0.release(); ctx->d_genome_seq_off.release(); ctx->d_seq_row0.release(); ctx->d_genome_len.release();
     ctx->d_ref_code.release();
@@ -248,7 +248,7 @@ static int upload_index(bk_ctx* ctx) {
         BK_CUDA(cudaMemcpyAsync(ctx->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
     BK_CUDA(ctx->d_exact.reserve(d.exact_slots.size()));
     BK_CUDA(cudaMemcpyAsync(ctx->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
-    BK_CUDA(ctx->d_refpk.upload(d.refpk, st));
+    BK_CUDA(ctx->d_refnib.upload(d.refnib, st));
     BK_CUDA(ctx->d_oseq_start.upload(d.oseq_start, st));
     BK_CUDA(ctx->d_oseq_len.upload(d.oseq_len, st));
     BK_CUDA(ctx->d_slot2id.upload(d.slot2id, st));
@@ -384,7 +384,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
 static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     CountView v;
     v.k = ctx->ix.k;
-    v.refpk = ctx->d_refpk.p; v.ref_words = (u32)ctx->d.refpk.size();
+    v.refnib = ctx->d_refnib.p; v.ref_chunks = (u32)(ctx->d.refnib.size() / 4);
     v.oseq_start = ctx->d_oseq_start.p; v.oseq_len = ctx->d_oseq_len.p;
     v.exact = ctx->d_exact.p; v.exact_shift = 64 - ctx->d.exact_log2; v.exact_mask = (1u << ctx->d.exact_log2) - 1;
     v.diff = f.diff.p;

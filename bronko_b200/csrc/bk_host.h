@@ -74,6 +74,7 @@ struct DerivedIndex {
     // oriented reference store (forward and reverse-complement of every sequence), 2-bit packed,
     // MSB-first, 32 bases per u64; global base index space with REF_PAD_BASES of padding in front
     std::vector<u64> refpk;
+    std::vector<u32> refnib;                 // the same store, one 4-bit code per base index (padding = 4), 16-byte chunks
     std::vector<u32> oseq_start, oseq_len;   // per oriented sequence, in global base indices
     u32 n_raw = 0;                           // size of the global base index space (incl. padding)
     // exact (non-canonical) reference k-mer → one representative raw slot

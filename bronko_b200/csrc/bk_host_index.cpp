@@ -355,6 +355,15 @@ void derive_index(const HostIndex& ix, DerivedIndex& d) {
     d.n_raw = (u32)codes.size();
     d.refpk.assign((codes.size() + 31) / 32 + 2, 0);
     for (size_t i = 0; i < codes.size(); i++) d.refpk[i >> 5] |= (u64)codes[i] << (62 - 2 * (i & 31));
+    // 4-bit copy for the scan kernel (little-endian nibbles, base i in nibble i); padding nibbles are 4, which the
+    // kernel's byte-permute turns into '#', a byte no case-folded read byte can equal
+    const size_t n_chunks = (codes.size() + 31) / 32 + 2;
+    d.refnib.assign(n_chunks * 4, 0x44444444u);
+    for (size_t i = REF_PAD_BASES; i + REF_PAD_BASES < codes.size(); i++) {
+        u32& wd = d.refnib[i >> 3];
+        const u32 sh = 4 * (u32)(i & 7);
+        wd = (wd & ~(0xFu << sh)) | ((u32)codes[i] << sh);
+    }
 
     std::sort(occ.begin(), occ.end(), [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.gidx < b.gidx; });
     d.slot2id.assign(d.n_raw, 0xFFFFFFFFu);

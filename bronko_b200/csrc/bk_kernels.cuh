@@ -72,13 +72,13 @@ __device__ __forceinline__ u32 flush_pending(const CountView& v, const Ld& ld, c
     return created;
 }
 
-__global__ void __launch_bounds__(BK_SCAN_THREADS)
+__global__ void __launch_bounds__(BK_SCAN_THREADS, 4)
 k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u32 off_bias, u32 r_begin, u32 r_end,
        u32 tile_reads, u32 tile_bytes, u32* gen_new) {
     extern __shared__ __align__(16) u8 smem[];
     const u32 n_tiles = (r_end - r_begin + tile_reads - 1) / tile_reads;
-    const u64* refpk = v.refpk;
-    auto ldr = [refpk](u32 i) { return __ldg(refpk + i); };
+    const u32* refnib = v.refnib;
+    auto ldr4 = [refnib](u32 i4) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(refnib) + i4); W4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w; return r; };
     u32 created = 0;
     for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const u32 r0 = r_begin + tile * tile_reads;
@@ -104,12 +104,12 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
             __syncthreads();
             const u32* sw = reinterpret_cast<const u32*>(smem);
             auto ld = [sw](u32 i) { return sw[i]; };
-            created += scan_read(v, ld, ldr, r < r1 ? o0 - a : 0u, len, a, pend);
+            created += scan_read(v, ld, ldr4, r < r1 ? o0 - a : 0u, len, a, pend);
             created += flush_pending(v, ld, pend, a);
         } else {
             const u32* gw = reinterpret_cast<const u32*>(bases);
             auto ld = [gw](u32 i) { return __ldg(gw + i); };
-            created += scan_read(v, ld, ldr, o0, len, 0, pend);
+            created += scan_read(v, ld, ldr4, o0, len, 0, pend);
             created += flush_pending(v, ld, pend, 0);
         }
     }

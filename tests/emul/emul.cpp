@@ -69,7 +69,7 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     u32 n_desc = 0, gen_full = 0;
     CountView v;
     v.k = d.k;
-    v.refpk = d.refpk.data(); v.ref_words = (u32)d.refpk.size();
+    v.refnib = d.refnib.data(); v.ref_chunks = (u32)(d.refnib.size() / 4);
     v.oseq_start = d.oseq_start.data(); v.oseq_len = d.oseq_len.data();
     v.exact = (const ExactSlotD*)d.exact_slots.data(); v.exact_shift = 64 - d.exact_log2; v.exact_mask = (1u << d.exact_log2) - 1;
     v.diff = diff.data();
@@ -77,11 +77,11 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     v.gen_full = &gen_full;
     v.desc = desc.data(); v.desc_cap = desc_cap; v.n_desc = &n_desc;
     auto ld = [&](u32 i) { return words[i]; };
-    auto ldr = [&](u32 i) { return d.refpk[i]; };
+    auto ldr4 = [&](u32 i4) { W4 r; r.x = d.refnib[4 * i4]; r.y = d.refnib[4 * i4 + 1]; r.z = d.refnib[4 * i4 + 2]; r.w = d.refnib[4 * i4 + 3]; return r; };
     u64 novel = 0, left_kmers = 0;
     for (u64 r = 0; r < n_reads; r++) {
         Pending pend; pend.n = 0; pend.d0 = make_uint2(0, 0); pend.d1 = make_uint2(0, 0);
-        novel += scan_read(v, ld, ldr, off[r], off[r + 1] - off[r], 0, pend);
+        novel += scan_read(v, ld, ldr4, off[r], off[r + 1] - off[r], 0, pend);
         // same policy as flush_pending() on the device: a full queue means counting in place
         for (u32 q = 0; q < pend.n; q++) {
             const uint2 d = q == 0 ? pend.d0 : pend.d1;
