@@ -85,7 +85,10 @@ struct bk_ctx {
     Counters* h_ctr = nullptr;              // pinned
     DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
-    DevBuf<double> d_noise, d_noise_vers;
+    DevBuf<double> d_noise;                 // Noise.max per row
+    DevBuf<double> d_nz_maf, d_nz_s, d_nz_s2, d_nz_tab, d_nz_warm;   // noise scratch (bk_noise.cuh: NoiseView)
+    DevBuf<u8> d_nz_flag; DevBuf<u32> d_nz_stats;
+    u32 nz_max_chunks = 1;
     DevBuf<bk_variant> d_vars;
     // staging for host pushes (double buffered)
     DevBuf<u8> d_stage[2]; DevBuf<u32> d_stage_off;
@@ -94,7 +97,7 @@ struct bk_ctx {
     u32 shard_rank = 0, shard_n = 1;
     bk_kmc_stats shard_kmc[2];
     DevBuf<u32> d_part;
-    bool noise_debug = false; DevBuf<unsigned long long> d_dbg;
+    bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
 
     // results
@@ -174,14 +177,13 @@ int bk_create(bk_ctx** out, int device) {
     }
     if (ok) ok = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_map<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_noise, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NOISE_SMEM) == cudaSuccess;
+                 cudaFuncSetAttribute(k_noise_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NZ_SEQ_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
     memset(&ctx->result, 0, sizeof ctx->result);
     bk_params_default(&ctx->params);
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
-    if (ctx->noise_debug) ctx->d_dbg.reserve(16);
     *out = ctx;
     return BK_OK;
 }
@@ -197,7 +199,9 @@ void bk_destroy(bk_ctx* ctx) {
     for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
     ctx->d_part.release();
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
-    ctx->d_noise.release(); ctx->d_noise_vers.release(); ctx->d_dbg.release(); ctx->d_vars.release();
+    ctx->d_noise.release(); ctx->d_vars.release();
+    ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
+    ctx->d_nz_flag.release(); ctx->d_nz_stats.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < 2; i++) { if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]); if (ctx->stage_copied[i]) cudaEventDestroy(ctx->stage_copied[i]); }
@@ -263,7 +267,20 @@ static int upload_index(bk_ctx* ctx) {
     const size_t rows = std::max<u32>(d.max_genome_rows, 1);
     BK_CUDA(ctx->d_pile.reserve(rows * 16));
     BK_CUDA(ctx->d_noise.reserve(rows));
-    BK_CUDA(ctx->d_noise_vers.reserve((size_t)ctx->max_seqs_per_genome * BK_NOISE_VERS * BK_NOISE_TABLE));
+    {   // noise scratch: fractions with padding per sequence, per-iteration snapshots, chunk slots
+        const size_t seqs = ctx->max_seqs_per_genome;
+        const size_t it_slots = rows + BK_NOISE_HALF * seqs;
+        const size_t chunk_slots = it_slots / BK_NZ_CHUNK + seqs + 2;
+        u32 max_len = 0;
+        for (size_t q = 0; q + 1 < d.seq_row0.size(); q++) max_len = std::max(max_len, d.seq_row0[q + 1] - d.seq_row0[q]);
+        ctx->nz_max_chunks = (max_len + BK_NOISE_HALF + BK_NZ_CHUNK - 1) / BK_NZ_CHUNK;
+        BK_CUDA(ctx->d_nz_maf.reserve((rows + BK_NZ_PAD * seqs) * 3));
+        BK_CUDA(ctx->d_nz_s.reserve(it_slots)); BK_CUDA(ctx->d_nz_s2.reserve(it_slots));
+        BK_CUDA(ctx->d_nz_tab.reserve(it_slots * BK_NOISE_TABLE));
+        BK_CUDA(ctx->d_nz_warm.reserve(chunk_slots * BK_NOISE_TABLE));
+        BK_CUDA(ctx->d_nz_flag.reserve(chunk_slots));
+        BK_CUDA(ctx->d_nz_stats.reserve(8));
+    }
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
     BK_CUDA(ctx->d_bsum.reserve(((size_t)d.n_raw + 2 + BK_PS_BLOCK - 1) / BK_PS_BLOCK + 1));
@@ -636,14 +653,23 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
     sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
     const u32 row_blocks = (d.max_genome_rows + 255) / 256;
-    if (ctx->noise_debug) cudaMemsetAsync(ctx->d_dbg.p, 0, 128, st);
-    k_noise<<<ctx->max_seqs_per_genome, BK_NOISE_THREADS, BK_NOISE_SMEM, st>>>(sv, ctx->d_noise.p, ctx->d_noise_vers.p, ctx->noise_debug ? ctx->d_dbg.p : nullptr);
-    if (ctx->noise_debug) {        // BK_NOISE_DEBUG=1: cycles spent by the three phase-2 roles and by phases 2 / 3
-        unsigned long long h[16];
-        cudaMemcpyAsync(h, ctx->d_dbg.p, 128, cudaMemcpyDeviceToHost, st);
+    NoiseView nv;
+    nv.ctr = dc; nv.genome_row0 = ctx->d_genome_row0.p; nv.genome_seq_off = ctx->d_genome_seq_off.p; nv.seq_row0 = ctx->d_seq_row0.p;
+    nv.pile = ctx->d_pile.p; nv.pile_stride = pile_stride;
+    nv.maf = ctx->d_nz_maf.p; nv.snap_s = ctx->d_nz_s.p; nv.snap_s2 = ctx->d_nz_s2.p; nv.snap_tab = ctx->d_nz_tab.p;
+    nv.warm = ctx->d_nz_warm.p; nv.flag = ctx->d_nz_flag.p; nv.stats = ctx->noise_debug ? ctx->d_nz_stats.p : nullptr;
+    nv.noise_max = ctx->d_noise.p;
+    const u32 nseq = ctx->max_seqs_per_genome;
+    if (ctx->noise_debug) cudaMemsetAsync(ctx->d_nz_stats.p, 0, 32, st);
+    k_noise_fracs<<<dim3((d.max_genome_rows + BK_NZ_PAD + 255) / 256, nseq), 256, 0, st>>>(nv);
+    k_noise_seq<<<dim3(2 + (ctx->nz_max_chunks + 7) / 8, nseq), BK_NZ_SEQ_THREADS, BK_NZ_SEQ_SMEM, st>>>(nv);
+    k_noise_fix<<<dim3(1, nseq), 256, 0, st>>>(nv);
+    k_noise_tau<<<dim3((d.max_genome_rows + BK_NOISE_HALF + 255) / 256, nseq), 256, 0, st>>>(nv);
+    if (ctx->noise_debug) {        // BK_NOISE_DEBUG=1
+        u32 h[8];
+        cudaMemcpyAsync(h, ctx->d_nz_stats.p, 32, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
-        fprintf(stderr, "[k_noise cycles] s-chain %llu  s2-chain %llu  table %llu  phase2 %llu  phase3 %llu\n", h[0], h[1], h[2], h[3], h[4]);
-        fprintf(stderr, "[k_noise table] votes %llu  candidates %llu  evict tests %llu  evictions %llu  inserts %llu\n", h[5], h[6], h[7], h[8], h[9]);
+        fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u\n", h[0], h[1], h[2], h[3], h[4]);
     }
     CallParams cp;
     const bk_params& p = ctx->params;
@@ -653,7 +679,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     cp.strand_balance_ratio = p.strand_balance_ratio; cp.strand_odds_max = p.strand_odds_max; cp.variant_multiplier = p.variant_multiplier;
     k_call<<<row_blocks, 256, 0, st>>>(sv, cp, ctx->d_noise.p, ctx->d_vars.p, (u32)std::min<size_t>(ctx->d_vars.cap, 0xFFFFFFFFu), dc);
     ctx->span_end(sp);
-    ctx->launches += 2;
+    ctx->launches += 5;
     BK_CUDA(cudaGetLastError());
 
     BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,10 @@ struct Counters {
     u64 pos_covered; u64 total_cov;
 };
 
+}  // namespace bk
+#include "bk_noise.cuh"
+namespace bk {
+
 __device__ __forceinline__ u32 warp_sum_u32(u32 v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -588,285 +592,13 @@ __global__ void k_select(const u32* gstats0, const u32* gstats1, u32 n_files, u3
 }
 
 // ------------------------------------------------------------------------------------------------
-// Noise baseline, src/call.rs:799-967 (quirks: SURVEY.md Appendix C, Q12).  The reference is one
-// sequential loop; here it is split so that only what is inherently sequential runs on one thread:
-// (k_noise below: fractions in parallel, the two state chains on two threads out of shared memory,
-// the Thompson-tau loop in parallel).
+// Noise baseline, src/call.rs:799-967: bk_noise.cuh (k_noise_fracs / k_noise_seq / k_noise_fix / k_noise_tau).
 // ------------------------------------------------------------------------------------------------
 struct ScoreView {
     u32 n_genomes; const u32* genome_row0; const u32* genome_seq_off; const u32* seq_row0;
     const u8* ref_code; const Counters* ctr;
     const u32* pile; u32 pile_stride;
 };
-
-#define BK_NOISE_WINDOW 100
-#define BK_NOISE_HALF 50
-#define BK_NOISE_TABLE 10
-#define BK_NOISE_TILE 512
-#define BK_NOISE_THREADS 256
-// dynamic shared memory of k_noise, bytes
-#define BK_NOISE_SMEM ((BK_NOISE_TILE + BK_NOISE_WINDOW) * 3 * 8 + BK_NOISE_TILE * (8 + 8 + 4) + (BK_NOISE_TILE + BK_NOISE_WINDOW) * 4 + 16)
-// table versions a tile can create (one per window update at most) + the one it starts with
-#define BK_NOISE_VERS (BK_NOISE_TILE * 3 + 1)
-
-__constant__ double c_tau[301];
-
-// One CTA per sequence of the selected genome; the iteration space i in [0, len+50) of the reference
-// loop is walked in tiles of BK_NOISE_TILE:
-//   phase 1 (all threads)  sorted minor-allele fractions of positions [t0-100, t0+T) into shared memory
-//   phase 2 (three warps)  warp 0 / lane 0: s, warp 1 / lane 0: s2 — the reference's exact operation order
-//                          (FP64, no FMA; adding or subtracting an exact +0.0 where the reference skips the
-//                          update leaves every bit unchanged, so the chains are branch-free; measured
-//                          ~14 cycles per dependent DADD on B200);
-//                          warp 2 (all lanes): the 10-entry max table with its evict-by-value quirk — 32
-//                          window updates are tested per step against the current table, only the ones
-//                          that can change it are replayed serially (lane q owns entry q);
-//                          all snapshot their state after every iteration
-//   phase 3 (all threads)  n by counting (integer, order-free), then the Thompson-tau rejection loop per
-//                          output position from the snapshots
-__device__ __forceinline__ bool noise_table_event(double old, double nw, double m_last) {
-    // evict (src/call.rs:857-869) can only hit if some entry is within 1e-12 of `old`: impossible when the
-    // table is full and its smallest entry exceeds `old` by more than 1e-9; insert (src/call.rs:872-890)
-    // happens iff nw > last entry.
-    const bool ev = old > 0.0 && !(m_last > 0.0 && old < m_last - 1e-9);
-    const bool in = nw > 0.0 && nw > m_last;
-    return ev || in;
-}
-
-__global__ void __launch_bounds__(BK_NOISE_THREADS)
-k_noise(ScoreView sv, double* noise_max, double* vers_all, unsigned long long* dbg) {
-    extern __shared__ __align__(16) u8 nsm[];
-    double* maf = reinterpret_cast<double*>(nsm);                               // (T+100)*3
-    double* snap_s = maf + (BK_NOISE_TILE + BK_NOISE_WINDOW) * 3;               // T
-    double* snap_s2 = snap_s + BK_NOISE_TILE;                                   // T
-    u32* pos_ver = reinterpret_cast<u32*>(snap_s2 + BK_NOISE_TILE);             // T: table version seen by iteration li
-    u32* npre = pos_ver + BK_NOISE_TILE;                                        // T+100: inclusive prefix of #positive fractions
-    const i32 best = sv.ctr->best;
-    if (best < 0) return;
-    const u32 s = sv.genome_seq_off[best] + blockIdx.x;
-    if (s >= sv.genome_seq_off[best + 1]) return;
-    const u32 r0 = sv.seq_row0[s] - sv.genome_row0[best];
-    const u32 len = sv.seq_row0[s + 1] - sv.seq_row0[s];
-    if (len < BK_NOISE_WINDOW) {     // the reference indexes out of bounds (panics) here; report zero noise
-        for (u32 i = threadIdx.x; i < len; i += blockDim.x) noise_max[r0 + i] = 0.0;
-        return;
-    }
-    const u32 iters = len + BK_NOISE_HALF;
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double sum = 0.0;                 // warp 0 lane 0: s ; warp 1 lane 0: s2
-    double mt = 0.0;                  // warp 2: lane q < 10 owns table entry q
-    double* vers = vers_all + (size_t)blockIdx.x * BK_NOISE_VERS * BK_NOISE_TABLE;
-
-    for (u32 t0 = 0; t0 < iters; t0 += BK_NOISE_TILE) {
-        const u32 tn = min((u32)BK_NOISE_TILE, iters - t0);
-        // ---- phase 1: fractions of positions p = t0 - 100 + x, x in [0, tn + 100) ----
-        for (u32 x = threadIdx.x; x < tn + BK_NOISE_WINDOW; x += blockDim.x) {
-            const i32 p = (i32)t0 - BK_NOISE_WINDOW + (i32)x;
-            double m1 = 0.0, m2 = 0.0, m3 = 0.0;
-            if (p >= 0 && p < (i32)len) {
-                const u32 row = r0 + (u32)p;
-                const uint4 f = *reinterpret_cast<const uint4*>(sv.pile + row * 4);
-                const uint4 r = *reinterpret_cast<const uint4*>(sv.pile + sv.pile_stride + row * 4);
-                u64 c0 = (u64)f.x + r.x, c1 = (u64)f.y + r.y, c2 = (u64)f.z + r.z, c3 = (u64)f.w + r.w;
-                u64 t;
-#define BK_CSWAP(a, b) if (a < b) { t = a; a = b; b = t; }
-                BK_CSWAP(c0, c1) BK_CSWAP(c2, c3) BK_CSWAP(c0, c2) BK_CSWAP(c1, c3) BK_CSWAP(c1, c2)
-#undef BK_CSWAP
-                const u64 total = c0 + c1 + c2 + c3;
-                if (total != 0) { const double td = (double)total; m1 = (double)c1 / td; m2 = (double)c2 / td; m3 = (double)c3 / td; }
-            }
-            maf[x * 3 + 0] = m1; maf[x * 3 + 1] = m2; maf[x * 3 + 2] = m3;
-        }
-        __syncthreads();
-        // ---- phase 2 ----
-        const long long t_p2 = clock64();
-        if (wid == 0) {
-            if (lane == 0) {                                                     // src/call.rs:845-895, s
-                const double* __restrict__ mf = maf;
-                double* __restrict__ out = snap_s;
-#pragma unroll 8
-                for (u32 li = 0; li < tn; li++) {
-                    const double* po = mf + li * 3;                              // position i - 100
-                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;          // position i
-#pragma unroll
-                    for (u32 j = 0; j < 3; j++) { sum = __dsub_rn(sum, po[j]); sum = __dadd_rn(sum, pn[j]); }
-                    out[li] = sum;
-                }
-            }
-        } else if (wid == 1) {
-            if (lane == 0) {                                                     // s2
-                const double* __restrict__ mf = maf;
-                double* __restrict__ out = snap_s2;
-#pragma unroll 8
-                for (u32 li = 0; li < tn; li++) {
-                    const double* po = mf + li * 3;
-                    const double* pn = mf + (li + BK_NOISE_WINDOW) * 3;
-#pragma unroll
-                    for (u32 j = 0; j < 3; j++) {
-                        const double o = po[j], w = pn[j];
-                        sum = __dsub_rn(sum, __dmul_rn(o, o)); sum = __dadd_rn(sum, __dmul_rn(w, w));
-                    }
-                    out[li] = sum;
-                }
-            }
-        } else if (wid == 2) {
-            // max table: lane q < 10 owns entry q (bit pattern; positive doubles order like their bits, so
-            // the hot path is integer-only).  32 window updates are tested per step against the current
-            // table; only those that can change it are replayed (in order).  Every table state of the tile
-            // is kept as a "version" in a global scratch area; positions only record which version they see.
-            //   insert candidate: new > last entry (src/call.rs:872-890)
-            //   evict candidate : old >= thr, where thr is safely below (smallest positive entry - 1e-12):
-            //                     the entry's bit pattern minus 2^36 (>= 7.6e-6 relative) when the entry is
-            //                     >= 1e-6, else 0 — anything below thr cannot be within 1e-12 of an entry
-            u32 ver = 0;
-            u64 mtb = (u64)__double_as_longlong(mt);
-            if (lane < BK_NOISE_TABLE) vers[lane] = mt;
-#define BK_TALLY()                                                                                   \
-    do {                                                                                             \
-        m_lastb = __shfl_sync(0xFFFFFFFFu, mtb, BK_NOISE_TABLE - 1);                                 \
-        u64 pminb = m_lastb;                                                                         \
-        if (m_lastb == 0) {                                                                          \
-            const u32 nz = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0);            \
-            const u32 cnt = __popc(nz);                                                              \
-            pminb = __shfl_sync(0xFFFFFFFFu, mtb, cnt ? cnt - 1 : 0);                                \
-            if (!cnt) pminb = ~0ull;                                                                 \
-        }                                                                                            \
-        thrb = pminb == ~0ull ? ~0ull : (pminb >= 0x3EB0C6F7A0B5ED8Dull ? pminb - (1ull << 36) : 0ull); \
-    } while (0)
-            u64 m_lastb, thrb;
-            BK_TALLY();
-            const u32 n_ops = tn * 3;
-            for (u32 u0 = 0; u0 < n_ops; u0 += 32) {
-                const u32 u = u0 + lane;
-                const bool in_range = u < n_ops;
-                const u32 li = u / 3, j = u - li * 3;
-                const u64 oldb = in_range ? (u64)__double_as_longlong(maf[u]) : 0ull;               // leaving: maf[li*3+j]
-                const u64 nwb = in_range ? (u64)__double_as_longlong(maf[3 * BK_NOISE_WINDOW + u]) : 0ull;   // arriving
-                const u32 ver0 = ver;
-                u32 chg = 0;                         // lanes whose update changed the table (each made a version)
-                // Which leaving values can evict?  Exactly those within 1e-12 of an entry that is in the table
-                // when they leave: an entry of the table as it is now (tested here, all lanes at once), or one
-                // inserted earlier in this chunk (tested at insert time: the reference evicts BY VALUE, so a
-                // leaving value can remove an equal value that arrived a moment ago).
-                bool ematch = false;
-                const double old = __longlong_as_double((long long)oldb);
-                if (__any_sync(0xFFFFFFFFu, oldb != 0)) {
-#pragma unroll
-                    for (u32 q = 0; q < BK_NOISE_TABLE; q++) {
-                        const u64 tb = __shfl_sync(0xFFFFFFFFu, mtb, q);
-                        if (tb != 0 && oldb != 0 && fabs(__dsub_rn(__longlong_as_double((long long)tb), old)) < 1e-12) ematch = true;
-                    }
-                }
-                u32 from = 0;
-                for (;;) {
-                    // Candidates among lanes >= from against the CURRENT last entry.  Until an eviction makes a
-                    // hole an insert only raises the last entry, so the mask stays a superset of the updates that
-                    // can change the table and its bits are walked in order without re-voting.
-                    u32 cm = __ballot_sync(0xFFFFFFFFu, lane >= from && (ematch || nwb > m_lastb));
-                    bool restart = false;
-                    if (dbg && lane == 0) { atomicAdd(dbg + 5, 1ull); atomicAdd(dbg + 6, (unsigned long long)__popc(cm)); }
-                    while (cm) {
-                        const u32 src = (u32)__ffs(cm) - 1;
-                        cm &= cm - 1;
-                        const u64 e_newb = __shfl_sync(0xFFFFFFFFu, nwb, src);
-                        const bool e_ev = __shfl_sync(0xFFFFFFFFu, ematch ? 1 : 0, src) != 0;
-                        bool changed = false;
-                        if (e_ev) {                                              // evict: src/call.rs:857-869
-                            if (dbg && lane == 0) atomicAdd(dbg + 7, 1ull);
-                            const double e_old = __shfl_sync(0xFFFFFFFFu, old, src);
-                            const u32 hm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && mtb != 0 &&
-                                                         fabs(__dsub_rn(__longlong_as_double((long long)mtb), e_old)) < 1e-12);
-                            if (hm) {                                            // first (= largest) entry within 1e-12
-                                const u32 pos = (u32)__ffs(hm) - 1;
-                                const u64 nxt = __shfl_down_sync(0xFFFFFFFFu, mtb, 1);
-                                if (lane >= pos && lane < BK_NOISE_TABLE) mtb = (lane == BK_NOISE_TABLE - 1) ? 0ull : nxt;
-                                changed = true;
-                                restart = true;                                  // a hole: insert candidates must be re-derived
-                                if (dbg && lane == 0) atomicAdd(dbg + 8, 1ull);
-                            }
-                        }
-                        {                                                        // insert: src/call.rs:872-890
-                            const u32 gm = __ballot_sync(0xFFFFFFFFu, lane < BK_NOISE_TABLE && e_newb > mtb);
-                            const u64 prv = __shfl_up_sync(0xFFFFFFFFu, mtb, 1);
-                            if (gm) {                                            // beats the (current) last entry
-                                const u32 pos = (u32)__ffs(gm) - 1;              // non-increasing table: '>' holds on a suffix
-                                if (lane < BK_NOISE_TABLE && lane > pos) mtb = prv;
-                                if (lane == pos) mtb = e_newb;
-                                changed = true;
-                                if (dbg && lane == 0) atomicAdd(dbg + 9, 1ull);
-                                // later leaving values within 1e-12 of the new entry become eviction candidates
-                                const bool hit = lane > src && !ematch && oldb != 0 &&
-                                                 fabs(__dsub_rn(__longlong_as_double((long long)e_newb), old)) < 1e-12;
-                                if (hit) ematch = true;
-                                cm |= __ballot_sync(0xFFFFFFFFu, hit);
-                            }
-                        }
-                        if (changed) {
-                            chg |= 1u << src;
-                            ver = ver0 + __popc(chg);
-                            if (lane < BK_NOISE_TABLE) vers[ver * BK_NOISE_TABLE + lane] = __longlong_as_double((long long)mtb);
-                        }
-                        if (restart) { from = src + 1; break; }
-                    }
-                    BK_TALLY();
-                    if (!restart) break;
-                }
-                // the version every position of this chunk sees after its third update
-                if (in_range && j == 2) pos_ver[li] = ver0 + __popc(chg & (0xFFFFFFFFu >> (31 - lane)));
-            }
-#undef BK_TALLY
-            mt = __longlong_as_double((long long)mtb);
-            __threadfence_block();
-        } else if (wid == 3) {
-            // n is order-free: prefix counts of positive fractions, so that phase 3 gets n with two loads
-            u32 carry = 0;
-            for (u32 x0 = 0; x0 < tn + BK_NOISE_WINDOW; x0 += 32) {
-                const u32 x = x0 + lane;
-                u32 c = 0;
-                if (x < tn + BK_NOISE_WINDOW) c = (maf[x * 3] > 0.0 ? 1u : 0u) + (maf[x * 3 + 1] > 0.0 ? 1u : 0u) + (maf[x * 3 + 2] > 0.0 ? 1u : 0u);
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, c, o); if (lane >= (u32)o) c += t; }
-                if (x < tn + BK_NOISE_WINDOW) npre[x] = carry + c;
-                carry += __shfl_sync(0xFFFFFFFFu, c, 31);
-            }
-        }
-        if (dbg && lane == 0 && wid < 3) atomicAdd(dbg + wid, (unsigned long long)(clock64() - t_p2));   // BK_NOISE_DEBUG=1
-        __syncthreads();
-        if (dbg && threadIdx.x == 0) atomicAdd(dbg + 3, (unsigned long long)(clock64() - t_p2));
-        const long long t_p3 = clock64();
-        // ---- phase 3: n, then Thompson tau per output position w = i - 50 (src/call.rs:898-961) ----
-        for (u32 li = threadIdx.x; li < tn; li += blockDim.x) {
-            const u32 i = t0 + li;
-            if (i < BK_NOISE_HALF) continue;
-            // n after iteration i = number of positive fractions among positions [i-99, i]
-            const u32 cn0 = npre[li + BK_NOISE_WINDOW] - npre[li];
-            const double s0 = snap_s[li], s20 = snap_s2[li];
-            const double* mxp = vers + (size_t)pos_ver[li] * BK_NOISE_TABLE;   // written this tile by warp 2: read through L2
-
-            double mu = 0.0, var = 0.0;
-            if (cn0 != 0) { mu = __ddiv_rn(s0, (double)cn0); var = __dsub_rn(__ddiv_rn(s20, (double)cn0), __dmul_rn(mu, mu)); }
-            u32 idx = 0, cn = cn0;
-            double cs = s0, cs2 = s20, cmu = mu, cvar = var;
-            double cand = __ldcg(mxp);
-            while (cand != 0.0) {
-                const double sd = sqrt(cvar);
-                const double tau = (cn > 2) ? c_tau[cn <= 300 ? cn : 300] : __longlong_as_double(0x7FF0000000000000ll);
-                if (fabs(__dsub_rn(cand, cmu)) > __dmul_rn(tau, sd)) {
-                    cs = __dsub_rn(cs, cand);
-                    cs2 = __dsub_rn(cs2, cand);                       // sic: candidate, not its square (src/call.rs:936)
-                    cn -= 1;
-                    if (cn > 0) { cmu = __ddiv_rn(cs, (double)cn); cvar = __dsub_rn(__ddiv_rn(cs2, (double)cn), __dmul_rn(cmu, cmu)); }
-                    else { cmu = 0.0; cvar = 0.0; }
-                    idx += 1;
-                    cand = idx < BK_NOISE_TABLE ? __ldcg(mxp + idx) : 0.0;   // the reference would panic at idx == 10
-                } else break;
-            }
-            noise_max[r0 + i - BK_NOISE_HALF] = cand;
-        }
-        __syncthreads();
-        if (dbg && threadIdx.x == 0) atomicAdd(dbg + 4, (unsigned long long)(clock64() - t_p3));
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_call — call_variants, src/call.rs:969-1150 (one thread per position of the selected genome).

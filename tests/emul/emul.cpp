@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../bronko_b200/csrc/bk_core.cuh"
+#include "../../bronko_b200/csrc/bk_noise.cuh"
 #include "../../bronko_b200/csrc/bk_host.h"
 
 using namespace bk;
@@ -129,6 +130,110 @@ void emul_count_get(void* h, u64* kmers, u32* counts) {
     Emul* e = (Emul*)h;
     memcpy(kmers, e->out_kmers.data(), e->out_kmers.size() * 8);
     memcpy(counts, e->out_counts.data(), e->out_counts.size() * 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Noise baseline with the device logic (bk_noise.cuh), orchestrated like the kernels: fractions, the two exact
+// chains in block-wide rounds (threads stepped one after the other, the parity maps composed in thread order like
+// the scan does), speculative table chunks + boundary verification + replay, Thompson tau.
+//   fwd/rev: len*4 u32 depth arrays.  stats5: chunks replayed, iterations replayed, chain rounds, stops, serial its.
+// ---------------------------------------------------------------------------------------------------------
+}  // extern "C"
+template <bool SQUARE, class LdM>
+static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
+    double s = 0.0;
+    u32 i0 = 0, serial_left = 0;
+    while (i0 < iters) {
+        const u32 n_it = std::min<u32>(BK_NZ_ROUND, iters - i0);
+        const u64 sb = nz_b(s);
+        const u32 ef = (u32)(sb >> 52);
+        if (ef == 0 || ef >= 0x7FFu || serial_left) {
+            const u32 n_ser = std::min<u32>(n_it, BK_NZ_SERIAL);
+            for (u32 it = 0; it < n_ser; it++) {
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
+                snap[i0 + it] = s;
+            }
+            i0 += n_ser; stats[4] += n_ser; serial_left = 0;
+            continue;
+        }
+        stats[2]++;
+        const i32 e = (i32)ef - 1023;
+        const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
+        std::vector<i64> pre0(n_it * 6), pre1(n_it * 6), f0(n_it), f1(n_it);
+        std::vector<u32> bad(n_it, 6);
+        for (u32 t = 0; t < n_it; t++) {
+            i64 run0 = 0, run1 = 0;
+            for (u32 q = 0; q < 6; q++) {
+                const NzOp o = nz_classify(nz_operand<SQUARE>(M, (i32)(i0 + t), q), e);
+                run0 = nz_apply(o, run0, 0); run1 = nz_apply(o, run1, 1);
+                pre0[t * 6 + q] = run0; pre1[t * 6 + q] = run1;
+                if ((o.flags & 4u) && bad[t] == 6) bad[t] = q;
+            }
+            f0[t] = run0; f1[t] = run1;
+        }
+        // exclusive composition in thread order (what the warp scan + warp totals compute)
+        i64 g0 = 0, g1 = 0;
+        u32 n_ok = n_it * 6;
+        std::vector<i64> T(n_it * 6);
+        for (u32 t = 0; t < n_it; t++) {
+            i64 base = S0 + ((S0 & 1) ? g1 : g0);
+            const bool odd = (base & 1) != 0;
+            for (u32 q = 0; q < 6; q++) {
+                T[t * 6 + q] = base + (odd ? pre1[t * 6 + q] : pre0[t * 6 + q]);
+                if (!nz_inside(T[t * 6 + q]) && bad[t] > q) bad[t] = q;
+            }
+            if (bad[t] < 6) n_ok = std::min(n_ok, t * 6 + bad[t]);
+            i64 h0, h1; nz_compose(g0, g1, f0[t], f1[t], &h0, &h1); g0 = h0; g1 = h1;
+        }
+        for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz_value(ef, T[t * 6 + 5]);
+        if (n_ok > 0) s = nz_value(ef, T[n_ok - 1]);
+        if (n_ok == n_it * 6) { i0 += n_it; continue; }
+        stats[3]++;
+        const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
+        for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
+        snap[i0 + ib] = s;
+        i0 += ib + 1;
+        if (ib < 8) serial_left = 1;
+    }
+}
+
+extern "C" {
+int emul_noise(const u32* fwd, const u32* rev, u32 len, double* out_max, u32* stats5) {
+    for (int i = 0; i < 5; i++) stats5[i] = 0;
+    if (len < BK_NOISE_WINDOW) { for (u32 i = 0; i < len; i++) out_max[i] = 0.0; return 1; }
+    const u32 iters = len + BK_NOISE_HALF;
+    std::vector<double> maf((size_t)(len + BK_NZ_PAD) * 3, 0.0);
+    for (u32 p = 0; p < len; p++) nz_fractions(fwd + (size_t)p * 4, rev + (size_t)p * 4, &maf[(size_t)(p + BK_NZ_PAD_LO) * 3]);
+    const double* m0 = maf.data() + (size_t)BK_NZ_PAD_LO * 3;
+    auto M = [m0](i32 p, u32 j) { return m0[(long long)p * 3 + j]; };
+    std::vector<double> snap_s(iters), snap_s2(iters), snap_tab((size_t)iters * BK_NOISE_TABLE);
+    emul_chain<false>(M, iters, snap_s.data(), stats5);
+    emul_chain<true>(M, iters, snap_s2.data(), stats5);
+    const u32 n_chunks = (iters + BK_NZ_CHUNK - 1) / BK_NZ_CHUNK;
+    std::vector<double> warm((size_t)n_chunks * BK_NOISE_TABLE);
+    for (u32 c = n_chunks; c-- > 0;)          // any order: chunks are independent
+        nz_table_chunk(M, iters, c, snap_tab.data(), &warm[(size_t)c * BK_NOISE_TABLE]);
+    std::vector<u8> flag(n_chunks, 0);
+    for (u32 c = 1; c < n_chunks; c++)
+        for (int q = 0; q < BK_NOISE_TABLE; q++)
+            if (nz_b(snap_tab[(size_t)(c * BK_NZ_CHUNK - 1) * BK_NOISE_TABLE + q]) != nz_b(warm[(size_t)c * BK_NOISE_TABLE + q])) flag[c] = 1;
+    for (u32 c = 1; c < n_chunks;) {
+        if (!flag[c]) { c++; continue; }
+        const u32 i0 = c * BK_NZ_CHUNK;
+        const u32 met = nz_table_replay(M, iters, i0, snap_tab.data());
+        stats5[0]++; stats5[1] += std::min(met, iters - 1) - i0 + 1;
+        c = met / BK_NZ_CHUNK + 1;
+    }
+    double tau[301];
+    tau_table(tau);
+    auto tau_of = [&tau](u32 n) { return tau[n]; };
+    for (u32 i = BK_NOISE_HALF; i < iters; i++) {
+        u32 cn0 = 0;
+        for (i32 p = (i32)i - (BK_NOISE_WINDOW - 1); p <= (i32)i; p++)
+            if (p < (i32)len) cn0 += (M(p, 0) > 0.0) + (M(p, 1) > 0.0) + (M(p, 2) > 0.0);
+        out_max[i - BK_NOISE_HALF] = nz_tau_loop(cn0, snap_s[i], snap_s2[i], &snap_tab[(size_t)i * BK_NOISE_TABLE], tau_of);
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ def lib():
             "emul_revcomp": (u64, [u64, C.c_int]), "emul_tau_table": (None, [P]),
             "emul_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),
             "emul_count": (u64, [P, P, P, u64, u32, u32, u32, u32, P, P]), "emul_count_get": (None, [P, P, P]),
+            "emul_noise": (C.c_int, [P, P, u32, P, P]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -78,3 +79,14 @@ class Emul:
         km, ct = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
         lib().emul_count_get(self.h, ptr(km), ptr(ct))
         return km, ct, tuple(int(x) for x in st), tuple(int(x) for x in dbg)
+
+
+def noise(fwd, rev):
+    """Noise.max per position with the device logic of bk_noise.cuh stepped on the CPU.  fwd/rev: (len, 4) depths.
+    Returns (max, stats) with stats = (chunks replayed, iterations replayed, chain rounds, chain stops, serial its)."""
+    fwd = np.ascontiguousarray(fwd, dtype=np.uint32)
+    rev = np.ascontiguousarray(rev, dtype=np.uint32)
+    n = fwd.shape[0]
+    out, st = np.zeros(n, dtype=np.float64), np.zeros(5, dtype=np.uint32)
+    lib().emul_noise(ptr(fwd), ptr(rev), n, ptr(out), ptr(st))
+    return out, tuple(int(x) for x in st)
