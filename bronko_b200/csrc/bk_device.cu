@@ -176,7 +176,8 @@ int bk_create(bk_ctx** out, int device) {
         ok = cudaMemcpyToSymbol(c_tau, tau, sizeof tau) == cudaSuccess;
     }
     if (ok) ok = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_map<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_map<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_map<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_noise_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NZ_SEQ_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
@@ -239,7 +240,7 @@ static int upload_index(bk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->ix.k < 15 || ctx->ix.k > 31 || (ctx->ix.k & 1) == 0)
         return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
-    derive_index(ctx->ix, ctx->d);
+    derive_index(ctx->ix, ctx->d, getenv("BK_NO_REKEY") == nullptr);
     const DerivedIndex& d = ctx->d;
     if (d.n_genomes == 0 || d.n_genomes > 4096) return ctx->fail(BK_ERR_ARG, "index holds %u genomes (supported: 1..4096)", d.n_genomes);
     if ((u64)d.n_raw + 2 >= 0x7FFFFFFFull) return ctx->fail(BK_ERR_ARG, "reference set too large for 32-bit slot indices");
@@ -607,8 +608,8 @@ static int stage_map_stats(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db) k_map_small<0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else k_map<0><<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
     ctx->span_end(sp);
@@ -632,8 +633,8 @@ static int stage_select_pileup(bk_ctx* ctx) {
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db) k_map_small<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else k_map<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         ctx->launches++;
     }
     ctx->span_end(sp);
@@ -669,7 +670,8 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
         u32 h[8];
         cudaMemcpyAsync(h, ctx->d_nz_stats.p, 32, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
-        fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u\n", h[0], h[1], h[2], h[3], h[4]);
+        fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u; kcycles: s %u, s2 %u, slowest table lane %u\n",
+                h[0], h[1], h[2], h[3], h[4], h[5] / 64, h[6] / 64, h[7] / 64);
     }
     CallParams cp;
     const bk_params& p = ctx->params;

@@ -67,7 +67,10 @@ struct DerivedIndex {
     std::vector<u64> genome_len;       // n_genomes
     std::vector<u8> ref_code;          // per row: nt_to_bits(base)
     u32 max_genome_rows = 0;
-    // bucket-id → entries
+    // bucket-id → entries.  rekeyed: slots are keyed by (bucket index << 58) | (canonical k-mer with that digit
+    // zeroed) instead of the bucket id — the same map, because assign_buckets is a bijection (src/lcb.rs:1-45);
+    // only for k <= 29 (ids wrap for k = 31, src/lcb.rs:8-41) and only if every key of the index verifies.
+    bool rekeyed = false;
     u32 bucket_log2 = 0;
     std::vector<BucketSlot> bucket_slots;
     std::vector<BucketEntry> bucket_entries;
@@ -87,7 +90,7 @@ struct DerivedIndex {
 
 static const u32 REF_PAD_BASES = 64;
 
-void derive_index(const HostIndex& ix, DerivedIndex& d);
+void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey = true);
 
 // must match bk::hash_slot in bk_core.cuh (the device probes with the same function)
 inline u32 hash_slot_host(u64 x, u32 shift) { return (u32)(((x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull) >> shift); }

@@ -275,7 +275,7 @@ static u32 log2_cap(u64 n_items) {
     return l;
 }
 
-void derive_index(const HostIndex& ix, DerivedIndex& d) {
+void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
     d = DerivedIndex();
     d.k = ix.k;
     const u32 k = ix.k;
@@ -319,11 +319,37 @@ void derive_index(const HostIndex& ix, DerivedIndex& d) {
         be.row = r; be.file_id = e.file_id; be.idx = e.idx; be.canonical = e.canonical ? 1 : 0;
         d.bucket_entries[i] = be;
     }
+    // Re-key: bucket id j of a canonical k-mer is a perfect rank of (j, k-mer without digit j), so the device can probe
+    // with that pair directly and skip the id arithmetic.  Every key is verified against its first entry (the
+    // reference k-mer at `location`, canonicalised, digit idx zeroed must rank to exactly this key); one failure (an
+    // index not produced by `bronko build`) keeps the id-keyed table.
+    std::vector<u64> slot_key(ix.keys.begin(), ix.keys.end());
+    d.rekeyed = allow_rekey && k <= 29;
+    if (d.rekeyed) {
+        std::vector<u64> ids(k);
+        for (size_t i = 0; i < ix.keys.size() && d.rekeyed; i++) {
+            if (ix.entry_off[i + 1] == ix.entry_off[i]) { d.rekeyed = false; break; }
+            const bk_bucket_info& e = ix.entries[ix.entry_off[i]];
+            bool ok = e.file_id < d.n_genomes && e.idx < k;
+            const HostSeq* q = nullptr;
+            if (ok) { const HostGenome& g = ix.genomes[e.file_id]; ok = e.seq_id < g.seqs.size(); if (ok) q = &g.seqs[e.seq_id]; }
+            if (ok) ok = (u64)e.location + k <= q->bases.size();
+            if (!ok) { d.rekeyed = false; break; }
+            u64 fwd = 0;
+            for (u32 b = 0; b < k; b++) fwd = (fwd << 2) | nt_to_bits_host(q->bases[e.location + b]);
+            const u64 rev = revcomp_host(fwd, (int)k);
+            const u64 kb = fwd < rev ? fwd : rev;                       // src/lcb.rs:87-95
+            assign_buckets_host(kb, (int)k, ids.data());
+            if (ids[e.idx] != ix.keys[i]) { d.rekeyed = false; break; }
+            slot_key[i] = ((u64)e.idx << 58) | (kb & ~(3ull << (2 * (k - 1 - e.idx))));
+        }
+        if (!d.rekeyed) slot_key.assign(ix.keys.begin(), ix.keys.end());
+    }
     const u64 bmask = (1ull << d.bucket_log2) - 1;
     for (size_t i = 0; i < ix.keys.size(); i++) {
-        u64 h = hash_slot_host(ix.keys[i], 64 - d.bucket_log2);
+        u64 h = hash_slot_host(slot_key[i], 64 - d.bucket_log2);
         while (d.bucket_slots[h].key != ~0ull) h = (h + 1) & bmask;
-        d.bucket_slots[h] = BucketSlot{ix.keys[i], (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
+        d.bucket_slots[h] = BucketSlot{slot_key[i], (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
     }
 
     // oriented reference store

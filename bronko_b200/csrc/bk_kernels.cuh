@@ -374,7 +374,9 @@ __device__ __forceinline__ u64 revcomp_dev(u64 v, u32 k) {
     return x >> (64 - 2 * k);
 }
 
-template <int PILEUP>
+// REKEY: the table is keyed by (bucket index << 58) | (canonical k-mer with that digit zeroed) — the same map as the
+// bucket ids (bijection), without the id arithmetic; the host verifies every key before enabling it (derive_index).
+template <int PILEUP, int REKEY>
 __global__ void __launch_bounds__(256)
 k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
       u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
@@ -411,8 +413,9 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
         const u64 mu = valid ? (dgt ? w + (cur >> 2) * (u64)(k - 1 - lane) : val) : 0;
         const u32 zmask = __ballot_sync(0xFFFFFFFFu, valid && dgt == 0);
         const u64 num_a = __popc(zmask & ((1u << lane) - 1));
-        const u64 sum_mu = warp_sum_u64(mu);
-        const u64 bucket = sum_mu - mu + val - num_a * cur + 1 + num_a;
+        u64 bucket;
+        if (REKEY) bucket = ((u64)lane << 58) | (kb & ~(3ull << sh));
+        else { const u64 sum_mu = warp_sum_u64(mu); bucket = sum_mu - mu + val - num_a * cur + 1 + num_a; }
         if (lane >= m.b0 && lane < m.b1) {
             u32 h = hash_slot(bucket, m.shift);
             u32 off = 0, len = 0;
@@ -474,7 +477,7 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
 // bucket is probed as soon as its id is known.  ~25x fewer warp instructions per k-mer than the
 // warp-per-k-mer kernel; the counted list keeps reference k-mers and novel k-mers in separate runs,
 // so warps stay homogeneous.
-template <int PILEUP>
+template <int PILEUP, int REKEY>
 __global__ void __launch_bounds__(256)
 k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
             u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
@@ -505,22 +508,25 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
             // pass 1: sum of mu
             u64 mask = 3ull << (2 * (k - 1)), p = 1ull << (2 * (k - 1));
             u64 val = kb, sum_mu = 0;
-            for (u32 i = 0; i < k; i++) {
-                const u64 cur = kb & mask;
-                val -= cur;
-                sum_mu += cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val;
-                mask >>= 2; p >>= 2;
+            if (!REKEY) {
+                for (u32 i = 0; i < k; i++) {
+                    const u64 cur = kb & mask;
+                    val -= cur;
+                    sum_mu += cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val;
+                    mask >>= 2; p >>= 2;
+                }
             }
             // pass 2: ids of the queried buckets, probe, walk entries
             mask = 3ull << (2 * (k - 1)); p = 1ull << (2 * (k - 1));
             val = kb;
             u64 num_a = 0;
-            for (u32 i = 0; i < m.b1; i++) {
-                const u64 cur = kb & mask;
-                val -= cur;
+            for (u32 i = REKEY ? m.b0 : 0u; i < m.b1; i++) {
+                u64 cur = 0;
+                if (!REKEY) { cur = kb & mask; val -= cur; }
                 if (i >= m.b0) {
-                    const u64 mu = cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val;
-                    const u64 bucket = sum_mu - mu + val - num_a * cur + 1 + num_a;
+                    u64 bucket;
+                    if (REKEY) bucket = ((u64)i << 58) | (kb & ~(3ull << (2 * (k - 1 - i))));
+                    else { const u64 mu = cur ? p + (cur >> 2) * (u64)(k - 1 - i) : val; bucket = sum_mu - mu + val - num_a * cur + 1 + num_a; }
                     u32 h = hash_slot(bucket, m.shift);
                     u32 off = 0, len = 0;
                     for (;;) {

@@ -40,7 +40,7 @@ typedef long long i64;
 #define BK_NZ_WARM 256           // warm-up iterations in front of a chunk
 #define BK_NZ_ROUND 256          // iterations per chain round (= threads of the chain block)
 #define BK_NZ_TILE 1024          // iterations of fractions staged per shared-memory tile of a chain block
-#define BK_NZ_SERIAL 16          // iterations executed serially when a round cannot make progress
+#define BK_NZ_SERIAL 8           // iterations executed serially when a round cannot make progress
 #define BK_NZ_PAD_LO 100         // zero positions in front of every sequence in the fraction array
 #define BK_NZ_PAD (BK_NZ_PAD_LO + 150)   // total padding positions per sequence
 #define BK_NZ_MASK52 0xFFFFFFFFFFFFFull
@@ -136,30 +136,28 @@ BK_HD bool nz_table_equal(const NzTable& T, const double* snap) {
 }
 
 // ---- chains: one operand against the binade of the running sum ---------------------------------------------
-struct NzOp { u64 a; u32 flags; };      // |RN(X)| without the tie correction; flags: 1 = negative, 2 = tie, 4 = not fast-path-able
-BK_HD NzOp nz_classify(double x, i32 e) {
-    const u64 xb = nz_b(x);
-    const u32 xe = (u32)(xb >> 52) & 0x7FFu;
-    const u64 frac = xb & BK_NZ_MASK52;
-    NzOp o; o.a = 0; o.flags = (u32)(xb >> 63);
-    if (xe == 0) { if (frac != 0) o.flags |= 4u; return o; }          // zero: nothing; subnormal: slow way
-    if (xe == 0x7FFu) { o.flags |= 4u; return o; }
-    const i32 sh = e - ((i32)xe - 1023);
-    if (sh < 1) { o.flags |= 4u; return o; }                          // operand as large as the sum
-    if (sh > 53) return o;                                            // |X| < 1/2: rounds to nothing
-    const u64 m = frac | (1ull << 52);
-    const u64 half = 1ull << (sh - 1);
-    const u64 rem = m & ((half << 1) - 1);
-    o.a = m >> sh;
-    if (rem > half) o.a += 1;
-    else if (rem == half) o.flags |= 2u;
-    return o;
+// The increments (in ulps of the binade of s) that adding x produces for an even / an odd S come from real FP64
+// additions against two constants of the same binade: fl(C + x) - C with C = 1.5·2^e (even in ulps) and C + ulp
+// (odd).  The hardware rounds C + x exactly like s + x — to the binade's ulp, exact ties to even — so ties, tiny
+// and subnormal operands need no special case.  Valid while |x| < 2^(e-1) (then C + x cannot leave C's binade).
+struct NzBinade { double c_even, c_odd, scale, xmax; };
+BK_HD NzBinade nz_binade(u32 ef) {                                  // ef = exponent field of s, 64 <= ef <= 0x7FE
+    NzBinade b;
+    b.c_even = nz_d(((u64)ef << 52) | (1ull << 51));
+    b.c_odd = nz_d((((u64)ef << 52) | (1ull << 51)) + 1);
+    b.scale = nz_d((u64)(2098u - ef) << 52);                         // 2^(52-e): ulps → integers
+    b.xmax = nz_d((u64)(ef - 1) << 52);                              // 2^(e-1)
+    return b;
+}
+BK_HD bool nz_incs(const NzBinade& b, double x, i64* i_even, i64* i_odd) {
+    if (!(nz_abs(x) < b.xmax)) { *i_even = 0; *i_odd = 0; return false; }     // operand as large as the sum (or non-finite)
+    *i_even = (i64)nz_mul(nz_sub(nz_add(b.c_even, x), b.c_even), b.scale);
+    *i_odd = (i64)nz_mul(nz_sub(nz_add(b.c_odd, x), b.c_odd), b.scale);
+    return true;
 }
 // running integer offset after the operation, for a chain whose offset before it was `run` from a start of parity p
-BK_HD i64 nz_apply(const NzOp& o, i64 run, u32 p) {
-    u64 inc = o.a;
-    if (o.flags & 2u) inc += (((u64)run + p + o.a) & 1ull);           // tie: to even
-    return (o.flags & 1u) ? run - (i64)inc : run + (i64)inc;
+BK_HD i64 nz_apply(i64 i_even, i64 i_odd, i64 run, u32 p) {
+    return run + ((((u64)run + p) & 1ull) ? i_odd : i_even);
 }
 // (g then f): offsets for start parity 0 / 1
 BK_HD void nz_compose(i64 g0, i64 g1, i64 f0, i64 f1, i64* h0, i64* h1) {
@@ -260,7 +258,8 @@ struct NoiseView {
     double* snap_tab;     // (rows + 50 * seqs) * 10
     double* warm;         // chunk slots * 10
     u8* flag;             // chunk slots: boundary check failed
-    u32* stats;           // [0] chunks replayed, [1] iterations replayed, [2] chain rounds, [3] chain stops, [4] serial iterations
+    u32* stats;           // [0] chunks replayed, [1] iterations replayed, [2] chain rounds, [3] chain stops, [4] serial iterations,
+                          // [5] / [6] cycles/16 of the s / s2 chain, [7] cycles/16 of the slowest table lane
     double* noise_max;    // rows
 };
 
@@ -322,8 +321,9 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     const u32 pos_total = sq.len + BK_NZ_PAD;                                   // positions present in mafp
     double s = 0.0;
     u32 i0 = 0, tile_lo = 0, tile_hi = 0;                                       // tile covers iterations [tile_lo, tile_hi)
-    u32 round = 0, serial_left = 0;
+    u32 round = 0, serial_left = 0, width = BK_NZ_ROUND;                        // width: iterations tried per round
     u32 st_rounds = 0, st_stops = 0, st_serial = 0;
+    const long long t_begin = clock64();
     while (i0 < iters) {
         if (i0 + 1 > tile_hi || (i0 + BK_NZ_ROUND > tile_hi && tile_hi < iters)) {
             __syncthreads();
@@ -335,12 +335,12 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         }
         const u32 tl = tile_lo;
         auto M = [mt, tl](i32 p, u32 j) { return mt[(u32)(p + BK_NOISE_WINDOW - (i32)tl) * 3 + j]; };
-        const u32 n_it = min((u32)BK_NZ_ROUND, tile_hi - i0);
+        const u32 n_it = min(width, tile_hi - i0);
         const u64 sb = nz_b(s);
         const u32 ef = (u32)(sb >> 52);
-        if (ef == 0 || ef >= 0x7FFu || serial_left) {
+        if (ef < 64u || ef >= 0x7FFu || serial_left) {
             // s is zero / subnormal / negative / non-finite, or rounds stopped making progress: like the reference
-            const u32 n_ser = min(n_it, (u32)BK_NZ_SERIAL);
+            const u32 n_ser = min(tile_hi - i0, (u32)BK_NZ_SERIAL);
             for (u32 it = 0; it < n_ser; it++) {
 #pragma unroll
                 for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
@@ -352,30 +352,38 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         }
         const u32 buf = round & 1;
         round++; st_rounds++;
-        const i32 e = (i32)ef - 1023;
+        const NzBinade bin = nz_binade(ef);
         const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
         const bool active = tid < n_it;
         i64 pre0[6], pre1[6];
-        i64 run0 = 0, run1 = 0;
+        i64 x0 = 0, x1 = 0;                                                      // exclusive prefix inside the warp
         u32 bad = 6;
+        if (wid * 32 < n_it) {                                                   // warps without an iteration skip the work
+            i64 run0 = 0, run1 = 0;
 #pragma unroll
-        for (u32 q = 0; q < 6; q++) {
-            const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + tid), q) : 0.0;
-            const NzOp o = nz_classify(x, e);
-            run0 = nz_apply(o, run0, 0); run1 = nz_apply(o, run1, 1);
-            pre0[q] = run0; pre1[q] = run1;
-            if ((o.flags & 4u) && bad == 6) bad = q;
-        }
-        // inclusive scan of the parity maps over the warp
-        i64 f0 = run0, f1 = run1;
+            for (u32 q = 0; q < 6; q++) {
+                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + tid), q) : 0.0;
+                i64 ie, io;
+                const bool ok = nz_incs(bin, x, &ie, &io);
+                run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
+                pre0[q] = run0; pre1[q] = run1;
+                if (!ok && bad == 6) bad = q;
+            }
+            // inclusive scan of the parity maps over the warp
+            i64 f0 = run0, f1 = run1;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, f0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, f1, o);
-            if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, f0, f1, &h0, &h1); f0 = h0; f1 = h1; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, f0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, f1, o);
+                if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, f0, f1, &h0, &h1); f0 = h0; f1 = h1; }
+            }
+            if (lane == 31) { wt0[buf][wid] = f0; wt1[buf][wid] = f1; }
+            x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1); x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);
+            if (lane == 0) { x0 = 0; x1 = 0; }
+        } else {
+#pragma unroll
+            for (u32 q = 0; q < 6; q++) { pre0[q] = 0; pre1[q] = 0; }
+            if (lane == 31) { wt0[buf][wid] = 0; wt1[buf][wid] = 0; }
         }
-        if (lane == 31) { wt0[buf][wid] = f0; wt1[buf][wid] = f1; }
-        i64 x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1), x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);   // exclusive
-        if (lane == 0) { x0 = 0; x1 = 0; }
         __syncthreads();
         i64 base = S0;
         for (u32 w = 0; w < wid; w++) base += (base & 1) ? wt1[buf][w] : wt0[buf][w];
@@ -407,16 +415,20 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         }
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
-        if (n_ok == total_ops) { i0 += n_it; continue; }
+        if (n_ok == total_ops) { i0 += n_it; width = BK_NZ_ROUND; continue; }
         // the operation that ended the accepted prefix and the rest of its iteration, in real FP64
         st_stops++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
-        if (ib < 8) serial_left = 1;
+        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): one warp
+        if (ib < 4) serial_left = 1;
     }
-    if (tid == 0 && nv.stats) { atomicAdd(nv.stats + 2, st_rounds); atomicAdd(nv.stats + 3, st_stops); atomicAdd(nv.stats + 4, st_serial); }
+    if (tid == 0 && nv.stats) {
+        atomicAdd(nv.stats + 2, st_rounds); atomicAdd(nv.stats + 3, st_stops); atomicAdd(nv.stats + 4, st_serial);
+        nv.stats[SQUARE ? 6 : 5] = (u32)((clock64() - t_begin) >> 4);            // cycles / 16
+    }
 }
 
 // grid (2 + ceil(max_chunks / 8), max_seqs), 256 threads, BK_NZ_SEQ_SMEM dynamic shared memory
@@ -443,8 +455,10 @@ __global__ void __launch_bounds__(BK_NZ_SEQ_THREADS) k_noise_seq(NoiseView nv) {
     for (u32 x = lane; x < nx; x += 32) wm[x] = mafp[(i64)p_lo * 3 + (i64)x];
     __syncwarp();
     if (lane == 0) {
+        const long long t_begin = clock64();
         auto M = [wm, p_lo](i32 p, u32 j) { return wm[(u32)(p - p_lo) * 3 + j]; };
         nz_table_chunk(M, s.iters, c, nv.snap_tab + (size_t)s.ibase * BK_NOISE_TABLE, nv.warm + (size_t)(s.cbase + c) * BK_NOISE_TABLE);
+        if (nv.stats) atomicMax(nv.stats + 7, (u32)((clock64() - t_begin) >> 4));
     }
 }
 

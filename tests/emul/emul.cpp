@@ -142,13 +142,13 @@ void emul_count_get(void* h, u64* kmers, u32* counts) {
 template <bool SQUARE, class LdM>
 static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
     double s = 0.0;
-    u32 i0 = 0, serial_left = 0;
+    u32 i0 = 0, serial_left = 0, width = BK_NZ_ROUND;
     while (i0 < iters) {
-        const u32 n_it = std::min<u32>(BK_NZ_ROUND, iters - i0);
+        const u32 n_it = std::min<u32>(width, iters - i0);
         const u64 sb = nz_b(s);
         const u32 ef = (u32)(sb >> 52);
-        if (ef == 0 || ef >= 0x7FFu || serial_left) {
-            const u32 n_ser = std::min<u32>(n_it, BK_NZ_SERIAL);
+        if (ef < 64u || ef >= 0x7FFu || serial_left) {
+            const u32 n_ser = std::min<u32>(iters - i0, BK_NZ_SERIAL);
             for (u32 it = 0; it < n_ser; it++) {
                 for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
                 snap[i0 + it] = s;
@@ -157,17 +157,18 @@ static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
             continue;
         }
         stats[2]++;
-        const i32 e = (i32)ef - 1023;
+        const NzBinade bin = nz_binade(ef);
         const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
         std::vector<i64> pre0(n_it * 6), pre1(n_it * 6), f0(n_it), f1(n_it);
         std::vector<u32> bad(n_it, 6);
         for (u32 t = 0; t < n_it; t++) {
             i64 run0 = 0, run1 = 0;
             for (u32 q = 0; q < 6; q++) {
-                const NzOp o = nz_classify(nz_operand<SQUARE>(M, (i32)(i0 + t), q), e);
-                run0 = nz_apply(o, run0, 0); run1 = nz_apply(o, run1, 1);
+                i64 ie, io;
+                const bool ok = nz_incs(bin, nz_operand<SQUARE>(M, (i32)(i0 + t), q), &ie, &io);
+                run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
                 pre0[t * 6 + q] = run0; pre1[t * 6 + q] = run1;
-                if ((o.flags & 4u) && bad[t] == 6) bad[t] = q;
+                if (!ok && bad[t] == 6) bad[t] = q;
             }
             f0[t] = run0; f1[t] = run1;
         }
@@ -187,13 +188,14 @@ static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
         }
         for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz_value(ef, T[t * 6 + 5]);
         if (n_ok > 0) s = nz_value(ef, T[n_ok - 1]);
-        if (n_ok == n_it * 6) { i0 += n_it; continue; }
+        if (n_ok == n_it * 6) { i0 += n_it; width = BK_NZ_ROUND; continue; }
         stats[3]++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         snap[i0 + ib] = s;
         i0 += ib + 1;
-        if (ib < 8) serial_left = 1;
+        width = 32;
+        if (ib < 4) serial_left = 1;
     }
 }
 

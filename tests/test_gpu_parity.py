@@ -154,6 +154,39 @@ def test_many_genome_map_kernel_on_small_db(sars_paths, oracle, monkeypatch):
         c.close()
 
 
+@pytest.mark.parametrize("warp_map", [False, True])
+def test_id_keyed_map_tables(sars_paths, oracle, monkeypatch, warp_map):
+    """BK_NO_REKEY keeps the bucket table keyed by the reference's bucket ids (the path used for k = 31 and for
+    indexes whose keys do not verify): both map kernels must agree with the re-keyed default."""
+    import bronko_b200
+    monkeypatch.setenv("BK_NO_REKEY", "1")
+    if warp_map:
+        monkeypatch.setenv("BK_FORCE_WARP_MAP", "1")
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, sars_paths)
+        oi = oracle.Index.build(21, sars_paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[2]), 400, sim.SEED0 + 43)
+        run_both(c, oi, [(r1, o1), (r2, o2)])
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("k", [15, 19, 29, 31])
+def test_other_k(oracle, k):
+    """k = 15 .. 31 (odd): k <= 29 probes the re-keyed table, k = 31 the id-keyed one (bucket ids wrap there, Q20)."""
+    import bronko_b200
+    paths = [sim.genome_path(sim.HPV16)]
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(k, paths)
+        oi = oracle.Index.build(k, paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.HPV16), 300, sim.SEED0 + 50 + k)
+        run_both(c, oi, [(r1, o1), (r2, o2)], bronko_b200.CallArgs(kmer=k))
+    finally:
+        c.close()
+
+
 def test_edge_reads(ctx_hpv):
     """Ragged input: empty reads, reads shorter than k, N / lower-case / junk bytes, a read longer than a
     tile, reads hanging over both genome ends, foreign reads, an indel."""
