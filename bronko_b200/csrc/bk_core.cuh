@@ -163,6 +163,9 @@ struct CountView {
     u32* diff;                       // n_raw + 2
     GenSlot* gen; u32 gen_shift, gen_mask;
     u32* gen_full;                   // set to 1 if the novel table ran out of slots
+    u32 pass_shift, pass_id;         // count_one() handles a k-mer iff (novel-table home slot >> pass_shift) == pass_id:
+                                     // the leftover kernel runs once per slice of the table so that the slice it
+                                     // scatters into stays L2-resident (31 / 0 = every k-mer)
     uint2* desc; u32 desc_cap; u32* n_desc;
 };
 
@@ -196,12 +199,13 @@ BK_HD bool exact_lookup(const CountView& v, u64 kmer, u32* gidx, u32* oseq) {
 // Count one k-mer occurrence that did not extend a run.  Returns 1 if it created a new novel key.
 BK_HD u32 count_one(const CountView& v, u64 kmer) {
     u32 gidx, oseq;
+    u32 h = hash_slot(kmer, v.gen_shift);
+    if ((h >> v.pass_shift) != v.pass_id) return 0;      // another pass counts this one
     if (exact_lookup(v, kmer, &gidx, &oseq)) {
         add_u32(v.diff + gidx, 1u);
         add_u32(v.diff + gidx + 1, 0xFFFFFFFFu);
         return 0;
     }
-    u32 h = hash_slot(kmer, v.gen_shift);
     for (u32 probe = 0; probe <= v.gen_mask; probe++) {
         u64 cur = load_key(&v.gen[h].key);
         if (cur == BK_EMPTY) {
@@ -265,6 +269,87 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 #define BK_BAIL_MISMATCHES 8  // this many bad bases inside one 32-base word ends the diagonal
 #endif
 
+// Seed k-mer: k bytes at byte_off → k-mer value WITHOUT validation.  Bits 1..2 of an ASCII base are a 2-bit code
+// (A 00, C 01, T 10, G 11; the same for lower case), gathered four at a time by a multiply and turned into the
+// A0 C1 G2 T3 code by one xor.  Any other byte yields some code: a seed found through it is harmless, because the
+// extension below compares every byte of the read with the letter the reference expects.
+// Reads at most ceil(k/4) + 1 words (<= 15 bytes past the k-mer: inside the slack every buffer carries).
+template <class Ld>
+BK_HD u64 pack_seed(const Ld& ld, u32 byte_off, u32 k) {
+    const u32 wi = byte_off >> 2, sh = (byte_off & 3) * 8;
+    u32 hi32 = 0, lo32 = 0;
+    u32 prev = ld(wi);
+#pragma unroll
+    for (u32 i = 0; i < 8; i++) {
+        if (4 * i < k) {
+            const u32 nxt = ld(wi + i + 1);
+            const u32 y = (BK_FUNNEL_R(prev, nxt, sh) >> 1) & 0x03030303u;
+            const u32 pk = (y * 0x40100401u) >> 24;                // first base in the two high bits
+            if (i < 4) hi32 |= pk << (24 - 8 * i); else lo32 |= pk << (56 - 8 * i);
+            prev = nxt;
+        }
+    }
+    u64 v = (((u64)hi32 << 32) | lo32) >> (64 - 2 * k);
+    return v ^ ((v >> 1) & 0x5555555555555555ull);                 // T 10 <-> G 11
+}
+
+// The 32 reference letters expected at global base index g .. g+31, as eight words of four upper-case ASCII letters
+// ('#' in the padding): two 16-byte chunks of the 4-bit reference, aligned, byte-permuted.  cur / nxt are the chunks
+// holding base g and the one after it.
+BK_HD void ref_letters(const W4& cur, const W4& nxt, u32 g, u32* ex8) {
+    const u32 wo = (g >> 3) & 3, bs = (g & 7) * 4;
+    u32 d0 = cur.x, d1 = cur.y, d2 = cur.z, d3 = cur.w, d4 = nxt.x, d5 = nxt.y, d6 = nxt.z, d7 = nxt.w;
+    if (wo & 1) { d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = d5; d5 = d6; d6 = d7; }
+    if (wo & 2) { d0 = d2; d1 = d3; d2 = d4; d3 = d5; d4 = d6; }
+    const u32 e0 = BK_FUNNEL_R(d0, d1, bs), e1 = BK_FUNNEL_R(d1, d2, bs), e2 = BK_FUNNEL_R(d2, d3, bs), e3 = BK_FUNNEL_R(d3, d4, bs);
+    ex8[0] = BK_PRMT(0x54474341u, 0x23232323u, e0); ex8[1] = BK_PRMT(0x54474341u, 0x23232323u, e0 >> 16);
+    ex8[2] = BK_PRMT(0x54474341u, 0x23232323u, e1); ex8[3] = BK_PRMT(0x54474341u, 0x23232323u, e1 >> 16);
+    ex8[4] = BK_PRMT(0x54474341u, 0x23232323u, e2); ex8[5] = BK_PRMT(0x54474341u, 0x23232323u, e2 >> 16);
+    ex8[6] = BK_PRMT(0x54474341u, 0x23232323u, e3); ex8[7] = BK_PRMT(0x54474341u, 0x23232323u, e3 >> 16);
+}
+template <class LdRef4>
+BK_HD W4 ref_chunk(const LdRef4& ldr4, i32 c, i32 cmax) { return ldr4((u32)(c < 0 ? 0 : (c > cmax ? cmax : c))); }
+
+// Fast filter: are the 32 read bytes at byte offset rb exactly the upper-case letters ex8?  (No case folding: a
+// lower-case read only fails the filter and is then judged by word_mask().)
+template <class Ld>
+BK_HD u32 word_differs(const Ld& ld, u32 rb, const u32* ex8) {
+    const u32 rwi = rb >> 2, rsh = (rb & 3) * 8;
+    u32 acc = 0;
+    u32 rp = ld(rwi);
+#pragma unroll
+    for (u32 i = 0; i < 8; i++) {
+        const u32 rn = ld(rwi + i + 1);
+        acc |= BK_FUNNEL_R(rp, rn, rsh) ^ ex8[i];
+        rp = rn;
+    }
+    return acc;
+}
+
+// Exact judgement of one word: bit j set iff base j of the word (j in [lo, hi)) is NOT the expected letter in either
+// case — a mismatch, a non-ACGT byte, or reference padding.
+template <class Ld>
+BK_HD u32 word_mask(const Ld& ld, u32 rb, const u32* ex8, i32 lo, i32 hi) {
+    const u32 rwi = rb >> 2, rsh = (rb & 3) * 8;
+    u32 t = 0;
+    u32 rp = ld(rwi);
+#pragma unroll
+    for (u32 i = 0; i < 8; i++) {
+        const u32 rn = ld(rwi + i + 1);
+        const u32 x = (BK_FUNNEL_R(rp, rn, rsh) & 0xDFDFDFDFu) ^ ex8[i];
+        rp = rn;
+        u32 f = x | (x >> 4);
+        f |= f >> 2;
+        f |= f >> 1;
+        f &= 0x01010101u;                                    // byte flags
+        t |= ((f * 0x10204080u) >> 28) << (4 * i);           // 4 flags → 4 bits, first base lowest
+    }
+    u32 keep = 0xFFFFFFFFu;
+    if (lo > 0) keep = lo >= 32 ? 0u : keep << lo;
+    if (hi < 32) keep = hi <= 0 ? 0u : keep & (0xFFFFFFFFu >> (32 - hi));
+    return t & keep;
+}
+
 // One read: bytes [o0, o0+len) of the word source.  On the device EVERY lane of the warp must call
 // this (lanes without a read pass len = 0): the loops run a warp-uniform number of rounds and
 // reconverge after every round, so a mismatch in one lane's read does not split the warp for the
@@ -275,6 +360,12 @@ BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
 // matching bases on the current diagonal.  A bad base at e (mismatch, non-ACGT byte, end of the
 // overlap with the oriented sequence, end of read) closes the stretch [ms, e): if it holds >= k bases
 // its k-mers [ms, e-k] become a run, everything pending before ms a leftover stretch.
+//
+// Extension: the words of the read (32 bases on the read's own grid) that lie fully inside the overlap with the
+// oriented sequence go through word_differs(), a branch-free filter every lane executes; it only records WHICH words
+// are off.  The partial last word is filtered through the full word that ends with it.  Words that failed the filter
+// (and partial words that cannot be filtered) are then judged one by one with word_mask() and turned into events —
+// the only divergent part, a few rounds per warp.
 template <class Ld, class LdRef4>
 BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0, u32 len, u32 gofs, Pending& pend) {
     const u32 k = v.k;
@@ -284,6 +375,7 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
     i32 c = 0;
     i32 seed_from = 0;
     bool active = has;                           // still looking for / following a diagonal
+    const i32 cmax = (i32)v.ref_chunks - 1;
     for (u32 diag = 0; diag < BK_MAX_DIAGS; diag++) {
         if (!BK_ANY(active)) break;
         // ---- seed: first k-mer at or after seed_from that is an exact reference k-mer ----
@@ -293,15 +385,13 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
             const bool need = active && !found && q + k <= len;
             if (!BK_ANY(need)) break;
             if (need) {
-                u64 km;
-                const bool okk = (q + 32 <= len) ? pack_kmer32(ld, o0 + q, k, &km) : pack_kmer(ld, o0 + q, k, &km);
-                if (okk && exact_lookup(v, km, &gidx, &oseq)) found = true;
+                if (exact_lookup(v, pack_seed(ld, o0 + q, k), &gidx, &oseq)) found = true;
                 else q += k;
             }
             BK_SYNCWARP();
         }
         if (!found) active = false;              // no seed: what is left of the read is leftover
-        // ---- extend along the diagonal, 32 bases per round ----
+        // ---- extend along the diagonal ----
         i32 g0 = 0, i_lo = 0, i_hi = 0, ms = 0, w = 0, w_end = 0;
         if (active) {
             g0 = (i32)gidx - (i32)q;             // global base index of read base 0 on this diagonal
@@ -324,78 +414,59 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
         }                                                                                   \
         ms = e__ + 1;                                                                       \
     } while (0)
-        // The oriented reference holds one 4-bit code per base: 32 bases are one aligned 16-byte chunk, and a
-        // byte-permute turns four codes into the four upper-case letters they stand for (padding → '#').  Every
-        // 32-base word of the read advances the reference by exactly one chunk, so the loop fetches ONE
-        // 16-byte chunk per lane per word (the lanes of a warp sit at unrelated reference positions: scattered
-        // requests are what bounds this kernel) and keeps the previous one.  Read bytes are case-folded
-        // (& 0xDF); byte equality with the expected letter proves "valid AND matching" in one xor.
-        const u32 wo = ((u32)g0 >> 3) & 3;                  // g0 mod 32 = nibble offset inside a chunk: word part ...
-        const u32 bs = ((u32)g0 & 7) * 4;                   // ... and bit part (the same for every word of the diagonal)
-        i32 c4 = (g0 + 32 * w) >> 5;                        // chunk holding the first base of word w
-        const i32 cmax = (i32)v.ref_chunks - 1;
-        W4 cur = {0, 0, 0, 0};
-        if (active) cur = ldr4((u32)(c4 < 0 ? 0 : (c4 > cmax ? cmax : c4)));
-        for (;;) {
-            const bool go = active && !bailed && w < w_end;
-            if (!BK_ANY(go)) break;
-            if (go) {
-                const i32 b0 = 32 * w;
-                const u32 rb = o0 + (u32)b0, rwi = rb >> 2, rsh = (rb & 3) * 8;
-                const i32 cn = c4 + 1;
-                const W4 nxt = ldr4((u32)(cn < 0 ? 0 : (cn > cmax ? cmax : cn)));
-                // the 160 reference bits of this word: words wo .. wo+4 of (cur, nxt), then shifted by bs
-                u32 d0 = cur.x, d1 = cur.y, d2 = cur.z, d3 = cur.w, d4 = nxt.x, d5 = nxt.y, d6 = nxt.z, d7 = nxt.w;
-                if (wo & 1) { d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = d5; d5 = d6; d6 = d7; }
-                if (wo & 2) { d0 = d2; d1 = d3; d2 = d4; d3 = d5; d4 = d6; }
-                const u32 e0 = BK_FUNNEL_R(d0, d1, bs), e1 = BK_FUNNEL_R(d1, d2, bs), e2 = BK_FUNNEL_R(d2, d3, bs), e3 = BK_FUNNEL_R(d3, d4, bs);
-                const u32 ee[4] = {e0, e1, e2, e3};
-                const bool inside = b0 >= i_lo && b0 + 32 <= i_hi;        // all 32 bases belong to the overlap
-                u32 xw[8];
-                u32 acc = 0;
-                u32 rp = ld(rwi);
-                if (inside) {
-#pragma unroll
-                    for (u32 i = 0; i < 8; i++) {
-                        const u32 rn = ld(rwi + i + 1);
-                        const u32 expect = BK_PRMT(0x54474341u, 0x23232323u, (i & 1) ? (ee[i >> 1] >> 16) : ee[i >> 1]);
-                        xw[i] = (BK_FUNNEL_R(rp, rn, rsh) & 0xDFDFDFDFu) ^ expect;
-                        acc |= xw[i];
-                        rp = rn;
-                    }
-                } else {                                                 // first / last word of the overlap
-                    const i32 lo = i_lo - b0 > 0 ? i_lo - b0 : 0;
-                    const i32 hi = i_hi - b0 < 32 ? i_hi - b0 : 32;
-#pragma unroll
-                    for (u32 i = 0; i < 8; i++) {
-                        const u32 rn = ld(rwi + i + 1);
-                        const u32 expect = BK_PRMT(0x54474341u, 0x23232323u, (i & 1) ? (ee[i >> 1] >> 16) : ee[i >> 1]);
-                        const i32 a0 = lo - 4 * (i32)i, a1 = hi - 4 * (i32)i;    // bytes of this sub-word inside [lo, hi)
-                        u32 bm = 0xFFFFFFFFu;
-                        if (a0 > 0) bm = a0 >= 4 ? 0u : bm << (8 * a0);
-                        if (a1 < 4) bm = a1 <= 0 ? 0u : bm & (0xFFFFFFFFu >> (8 * (4 - a1)));
-                        xw[i] = ((BK_FUNNEL_R(rp, rn, rsh) & 0xDFDFDFDFu) ^ expect) & bm;
-                        acc |= xw[i];
-                        rp = rn;
-                    }
+        for (;;) {                               // segments of up to 32 words
+            const bool seg = active && !bailed && w < w_end;
+            if (!BK_ANY(seg)) break;
+            const i32 seg_w0 = w;
+            const i32 seg_end = seg ? (w_end < w + 32 ? w_end : w + 32) : w;
+            u32 wm = 0;                          // bit (ww - seg_w0): word ww must be judged by word_mask()
+            // -- filter pass: one reference chunk per word, the previous one is kept --
+            i32 c4 = (g0 + 32 * w) >> 5;
+            W4 cur = {0, 0, 0, 0};
+            if (seg) cur = ref_chunk(ldr4, c4, cmax);
+            for (;;) {
+                const bool go = seg && w < seg_end;
+                if (!BK_ANY(go)) break;
+                if (go) {
+                    const i32 b0 = 32 * w;
+                    const W4 nxt = ref_chunk(ldr4, c4 + 1, cmax);
+                    if (b0 >= i_lo && b0 + 32 <= i_hi) {               // all 32 bases belong to the overlap
+                        u32 ex8[8];
+                        ref_letters(cur, nxt, (u32)(g0 + b0), ex8);
+                        if (word_differs(ld, o0 + (u32)b0, ex8)) wm |= 1u << (w - seg_w0);
+                    } else if (b0 >= i_lo && i_hi - 32 >= i_lo) {      // partial last word: the full word ending with it
+                        const i32 bt = i_hi - 32;                      // (b0 - 32 < bt < b0: its bases lie in cur / nxt
+                        u32 ex8[8];                                    //  of the previous word and in this word's)
+                        const i32 ct = (g0 + bt) >> 5;
+                        const W4 ca = ref_chunk(ldr4, ct, cmax), cb = ref_chunk(ldr4, ct + 1, cmax);
+                        ref_letters(ca, cb, (u32)(g0 + bt), ex8);
+                        if (word_differs(ld, o0 + (u32)bt, ex8)) wm |= 1u << (w - seg_w0);
+                    } else wm |= 1u << (w - seg_w0);                   // partial and not filterable
+                    cur = nxt;
+                    c4++;
+                    w++;
                 }
-                if (acc != 0) {                                          // the uncommon case: some base is off
-                    u32 t = 0;                                           // bit j set: base b0+j is off
-#pragma unroll
-                    for (u32 i = 0; i < 8; i++) {
-                        if (xw[i]) {
-                            u32 f = xw[i] | (xw[i] >> 4);
-                            f |= f >> 2;
-                            f |= f >> 1;
-                            f &= 0x01010101u;                            // byte flags
-                            t |= ((f * 0x10204080u) >> 28) << (4 * i);   // 4 flags → 4 bits, first base lowest
-                        }
-                    }
-                    if (BK_POPC(t) >= BK_BAIL_MISMATCHES) {              // wrong diagonal from here on: close, re-seed
+                BK_SYNCWARP();
+            }
+            // -- judge the words that failed, in order --
+            for (;;) {
+                const bool go = wm != 0;
+                if (!BK_ANY(go)) break;
+                if (go) {
+                    const i32 ww = seg_w0 + (i32)BK_FFS0(wm);
+                    wm &= wm - 1;
+                    const i32 b0 = 32 * ww;
+                    const i32 cw = (g0 + b0) >> 5;
+                    const W4 ca = ref_chunk(ldr4, cw, cmax), cb = ref_chunk(ldr4, cw + 1, cmax);
+                    u32 ex8[8];
+                    ref_letters(ca, cb, (u32)(g0 + b0), ex8);
+                    u32 t = word_mask(ld, o0 + (u32)b0, ex8, i_lo - b0, i_hi - b0);
+                    if (BK_POPC(t) >= BK_BAIL_MISMATCHES) {            // wrong diagonal from here on: close, re-seed
                         const i32 e = b0 + (i32)BK_FFS0(t);
                         BK_EVENT(e);
                         seed_from = e + 1;
                         bailed = true;
+                        wm = 0;
                     } else {
                         while (t) {
                             const u32 j = BK_FFS0(t);
@@ -404,11 +475,8 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
                         }
                     }
                 }
-                cur = nxt;
-                c4 = cn;
-                w++;
+                BK_SYNCWARP();
             }
-            BK_SYNCWARP();
         }
         if (active && !bailed) { BK_EVENT(i_hi); active = false; }
 #undef BK_EVENT

@@ -581,6 +581,104 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
     }
 }
 
+// k_map_half — map_kmers for re-keyed tables of at most four genomes: a HALF-WARP per counted k-mer, one lane per
+// queried bucket (a whole warp when more than 16 buckets are queried).  The 16 probes of a k-mer are independent
+// L2 accesses; issuing them from 16 lanes at once instead of one after the other from one thread is what this kernel
+// is about (the thread-per-k-mer version spent two thirds of its time waiting for the probe it had just issued).
+// Per-genome hit counts are 32-bit fields of two registers, summed over the group with shuffles.
+template <int PILEUP>
+__global__ void __launch_bounds__(256)
+k_map_half(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
+           u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
+    const u32 n = min(*n_ptr, n_cap);
+    const u32 k = m.k;
+    const u32 lane = threadIdx.x & 31;
+    i32 best = -1; u32 g_row0 = 0;
+    if (PILEUP) {
+        best = *best_ptr;
+        if (best < 0) return;
+        g_row0 = m.genome_row0[best];
+    }
+    const u32 nb = m.b1 - m.b0;
+    const u32 G = nb <= 16 ? 16u : 32u;                 // lanes per k-mer
+    const u32 gl = lane & (G - 1), gid = lane / G, per_warp = 32 / G;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    u32 acc[12];                                        // group leaders: [g*3 + {perfect, variant, unique}]
+#pragma unroll
+    for (u32 i = 0; i < 12; i++) acc[i] = 0;
+    const u32 n_round = ((n + per_warp - 1) / per_warp) * per_warp;
+    for (u32 t0 = warp * per_warp; t0 < n_round; t0 += n_warps * per_warp) {
+        const u32 t = t0 + gid;
+        const bool live = t < n;
+        u64 h01 = 0, h23 = 0;                           // hits of genomes 0,1 / 2,3 (32 bits each)
+        if (live) {
+            const u64 fwd = __ldg(kmers + t);
+            const u32 cnt = __ldg(counts + t);
+            const u64 rev = revcomp_dev(fwd, k);
+            const bool rc = !(fwd < rev);               // src/lcb.rs:87-95
+            const u64 kb = rc ? rev : fwd;
+            for (u32 i = m.b0 + gl; i < m.b1; i += G) {
+                const u64 bucket = ((u64)i << 58) | (kb & ~(3ull << (2 * (k - 1 - i))));
+                u32 h = hash_slot(bucket, m.shift);
+                u32 off = 0, len = 0;
+                for (;;) {
+                    const uint4 sl = __ldg(reinterpret_cast<const uint4*>(m.slots) + h);
+                    const u64 key = ((u64)sl.y << 32) | sl.x;
+                    if (key == bucket) { off = sl.z; len = sl.w; break; }
+                    if (key == BK_EMPTY) break;
+                    h = (h + 1) & m.mask;
+                }
+                for (u32 j = 0; j < len; j++) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+                    const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
+                    if (row == 0xFFFFFFFFu) continue;
+                    if (!PILEUP) {                                                    // src/call.rs:1316-1318
+                        if (file_id < 2) h01 += 1ull << (32 * file_id); else h23 += 1ull << (32 * (file_id - 2));
+                    } else if ((i32)file_id == best) {
+                        u32 bit; bool to_fwd;
+                        if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
+                        else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
+                        const u32 cell = (row + idx - g_row0) * 4 + bit;
+                        atomicAdd(pile + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
+                        atomicMax(pile + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
+                    }
+                }
+            }
+        }
+        if (!PILEUP) {                                                               // src/call.rs:1389-1419
+            for (u32 o = G >> 1; o; o >>= 1) {
+                h01 += __shfl_xor_sync(0xFFFFFFFFu, h01, o);
+                h23 += __shfl_xor_sync(0xFFFFFFFFu, h23, o);
+            }
+            if (gl == 0 && live) {
+                const u32 hg[4] = {(u32)h01, (u32)(h01 >> 32), (u32)h23, (u32)(h23 >> 32)};
+                u32 n_perfect = 0;
+#pragma unroll
+                for (u32 g = 0; g < 4; g++) n_perfect += (hg[g] == nb && nb != 0) ? 1u : 0u;
+#pragma unroll
+                for (u32 g = 0; g < 4; g++) {
+                    const bool perfect = hg[g] != 0 && hg[g] == nb;
+                    acc[g * 3] += perfect ? 1u : 0u;
+                    acc[g * 3 + 1] += (hg[g] != 0 && !perfect) ? 1u : 0u;
+                    acc[g * 3 + 2] += (perfect && n_perfect == 1) ? 1u : 0u;
+                }
+            }
+        }
+    }
+    if (!PILEUP) {
+#pragma unroll
+        for (u32 i = 0; i < 12; i++) acc[i] = warp_sum_u32(acc[i]);
+        if (lane == 0) {
+            for (u32 g = 0; g < m.n_genomes && g < 4; g++) {
+                if (acc[g * 3]) atomicAdd(gstats + g * 4, acc[g * 3]);
+                if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
+                if (acc[g * 3 + 2]) atomicAdd(gstats + g * 4 + 2, acc[g * 3 + 2]);
+                if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
+            }
+        }
+    }
+}
+
 // k_select — pick_best_genome / pick_best_genome_paired (src/call.rs:422-502): argmax of
 // perfect / genome_len / 2.0 with strict '>' from 0.0; ties keep the lowest file index (the
 // reference's tie order is FxHashMap iteration order, unpinned).
