@@ -23,6 +23,7 @@
 #define BK_POPC(x) __popc((unsigned)(x))
 #define BK_FFS0(x) ((u32)__ffs((int)(x)) - 1u)
 #define BK_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#define BK_WARP_MAX(x) __reduce_max_sync(0xFFFFFFFFu, (unsigned)(x))
 #define BK_SYNCWARP() __syncwarp()
 #define BK_FUNNEL_R(lo, hi, sh) __funnelshift_r((lo), (hi), (sh))
 #define BK_PRMT(x, y, sel) __byte_perm((x), (y), (sel))
@@ -33,6 +34,7 @@
 #define BK_POPC(x) __builtin_popcount((unsigned)(x))
 #define BK_FFS0(x) ((u32)__builtin_ctz((unsigned)(x)))
 #define BK_ANY(p) (p)
+#define BK_WARP_MAX(x) ((unsigned)(x))
 #define BK_SYNCWARP() do {} while (0)
 #define BK_FUNNEL_R(lo, hi, sh) ((sh) ? (((lo) >> (sh)) | ((hi) << (32 - (sh)))) : (lo))
 static inline unsigned BK_PRMT(unsigned x, unsigned y, unsigned sel) {      // selector nibbles 0..7 only
@@ -163,9 +165,6 @@ struct CountView {
     u32* diff;                       // n_raw + 2
     GenSlot* gen; u32 gen_shift, gen_mask;
     u32* gen_full;                   // set to 1 if the novel table ran out of slots
-    u32 pass_shift, pass_id;         // count_one() handles a k-mer iff (novel-table home slot >> pass_shift) == pass_id:
-                                     // the leftover kernel runs once per slice of the table so that the slice it
-                                     // scatters into stays L2-resident (31 / 0 = every k-mer)
     uint2* desc; u32 desc_cap; u32* n_desc;
 };
 
@@ -199,13 +198,12 @@ BK_HD bool exact_lookup(const CountView& v, u64 kmer, u32* gidx, u32* oseq) {
 // Count one k-mer occurrence that did not extend a run.  Returns 1 if it created a new novel key.
 BK_HD u32 count_one(const CountView& v, u64 kmer) {
     u32 gidx, oseq;
-    u32 h = hash_slot(kmer, v.gen_shift);
-    if ((h >> v.pass_shift) != v.pass_id) return 0;      // another pass counts this one
     if (exact_lookup(v, kmer, &gidx, &oseq)) {
         add_u32(v.diff + gidx, 1u);
         add_u32(v.diff + gidx + 1, 0xFFFFFFFFu);
         return 0;
     }
+    u32 h = hash_slot(kmer, v.gen_shift);
     for (u32 probe = 0; probe <= v.gen_mask; probe++) {
         u64 cur = load_key(&v.gen[h].key);
         if (cur == BK_EMPTY) {
@@ -308,7 +306,7 @@ BK_HD void ref_letters(const W4& cur, const W4& nxt, u32 g, u32* ex8) {
     ex8[6] = BK_PRMT(0x54474341u, 0x23232323u, e3); ex8[7] = BK_PRMT(0x54474341u, 0x23232323u, e3 >> 16);
 }
 template <class LdRef4>
-BK_HD W4 ref_chunk(const LdRef4& ldr4, i32 c, i32 cmax) { return ldr4((u32)(c < 0 ? 0 : (c > cmax ? cmax : c))); }
+BK_HD W4 ref_chunk(const LdRef4& ldr4, i32 c, i32 cmax) { return ldr4((u32)c < (u32)cmax ? (u32)c : (u32)cmax); }   // (words inside the overlap never clamp)
 
 // Fast filter: are the 32 read bytes at byte offset rb exactly the upper-case letters ex8?  (No case folding: a
 // lower-case read only fails the filter and is then judged by word_mask().)
@@ -424,9 +422,9 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
             i32 c4 = (g0 + 32 * w) >> 5;
             W4 cur = {0, 0, 0, 0};
             if (seg) cur = ref_chunk(ldr4, c4, cmax);
-            for (;;) {
+            const u32 n_rounds = BK_WARP_MAX(seg_end - w);          // warp-uniform trip count, lanes with fewer words idle
+            for (u32 it = 0; it < n_rounds; it++) {
                 const bool go = seg && w < seg_end;
-                if (!BK_ANY(go)) break;
                 if (go) {
                     const i32 b0 = 32 * w;
                     const W4 nxt = ref_chunk(ldr4, c4 + 1, cmax);
@@ -446,7 +444,6 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
                     c4++;
                     w++;
                 }
-                BK_SYNCWARP();
             }
             // -- judge the words that failed, in order --
             for (;;) {

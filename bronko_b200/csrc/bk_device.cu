@@ -99,7 +99,6 @@ struct bk_ctx {
     DevBuf<u32> d_part;
     bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
-    u64 leftover_slice_bytes = ~0ull;      // experiment knob BK_LEFTOVER_SLICE_MB: walk the novel table in slices (measured slower: off)
 
     // results
     bk_sample_result result;
@@ -186,7 +185,6 @@ int bk_create(bk_ctx** out, int device) {
     bk_params_default(&ctx->params);
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
-    if (const char* e = getenv("BK_LEFTOVER_SLICE_MB")) { const long mb = atol(e); if (mb > 0) ctx->leftover_slice_bytes = (u64)mb << 20; }
     *out = ctx;
     return BK_OK;
 }
@@ -410,7 +408,6 @@ static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     v.diff = f.diff.p;
     v.gen = f.gen.p; v.gen_shift = 64 - f.gen_log2; v.gen_mask = (u32)((1ull << f.gen_log2) - 1);
     v.gen_full = &ctx->d_ctr.p->gen_full;
-    v.pass_shift = 31; v.pass_id = 0;
     v.desc = ctx->d_desc.p; v.desc_cap = (u32)std::min<size_t>(ctx->d_desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->n_desc;
     return v;
 }
@@ -454,17 +451,9 @@ static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_o
     ctx->span_end(sp);
     ctx->launches++; ctx->scan_launches++;
     BK_CUDA(cudaGetLastError());
-    // The leftover k-mers scatter into the novel table at random; a table larger than what stays L2-resident is
-    // walked in slices (one launch per slice, each re-rolling the queued stretches and keeping only the k-mers
-    // whose home slot lies in its slice).
-    u32 pass_log2 = 0;
-    while (pass_log2 < 4 && ((16ull << f.gen_log2) >> pass_log2) > ctx->leftover_slice_bytes) pass_log2++;
     sp = ctx->span_begin(ST_LEFTOVER);
-    for (u32 pass = 0; pass < (1u << pass_log2); pass++) {
-        v.pass_shift = pass_log2 ? f.gen_log2 - pass_log2 : 31; v.pass_id = pass_log2 ? pass : 0;
-        k_leftover<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
-        ctx->launches++;
-    }
+    k_leftover<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
     return BK_OK;
@@ -619,8 +608,7 @@ static int stage_map_stats(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && d.rekeyed) k_map_half<0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else if (small_db) k_map_small<0, 0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
@@ -645,8 +633,7 @@ static int stage_select_pileup(bk_ctx* ctx) {
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && d.rekeyed) k_map_half<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else if (small_db) k_map_small<1, 0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         ctx->launches++;
     }

@@ -76,13 +76,45 @@ __device__ __forceinline__ u32 flush_pending(const CountView& v, const Ld& ld, c
     return created;
 }
 
+// TMA bulk copy (cp.async.bulk, 1-D) of one tile global → shared, completion on an mbarrier: one thread issues it,
+// no thread spends instructions on moving bytes, and the same thread asks for the CTA's next tile to be pulled into L2.
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tile_load(void* dst, const void* src, u32 bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy reads of the old tile are done (barrier before)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tile_prefetch_l2(const void* src, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BK_DONE_%=;\n"
+        "bra BK_WAIT_%=;\n"
+        "BK_DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
 __global__ void __launch_bounds__(BK_SCAN_THREADS, 4)
 k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u32 off_bias, u32 r_begin, u32 r_end,
        u32 tile_reads, u32 tile_bytes, u32* gen_new) {
-    extern __shared__ __align__(16) u8 smem[];
+    extern __shared__ __align__(128) u8 smem[];
+    __shared__ __align__(8) unsigned long long tile_bar;
     const u32 n_tiles = (r_end - r_begin + tile_reads - 1) / tile_reads;
     const u32* refnib = v.refnib;
     auto ldr4 = [refnib](u32 i4) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(refnib) + i4); W4 r; r.x = q.x; r.y = q.y; r.z = q.z; r.w = q.w; return r; };
+    if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
+    __syncthreads();
+    u32 parity = 0;
     u32 created = 0;
     for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const u32 r0 = r_begin + tile * tile_reads;
@@ -96,16 +128,16 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
         Pending pend; pend.n = 0; pend.d0 = make_uint2(0, 0); pend.d1 = make_uint2(0, 0);
         if (staged) {
             __syncthreads();                                 // previous tile fully consumed
-            const uint4* src = reinterpret_cast<const uint4*>(bases + a);
-            uint4* dst = reinterpret_cast<uint4*>(smem);
-            const u32 n16 = (e - a) >> 4;
-            for (u32 i = threadIdx.x; i < n16; i += BK_SCAN_THREADS) {
-                uint4 q;
-                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src + i));
-                dst[i] = q;
+            if (threadIdx.x == 0) {
+                if (e > a) tile_load(smem, bases + a, e - a, &tile_bar);
+                const u32 nt = tile + gridDim.x;             // this CTA's next tile: into L2 while this one is scanned
+                if (nt < n_tiles) {
+                    const u32 na = (__ldg(off + r_begin + nt * tile_reads) - off_bias) & ~15u;
+                    const u32 ne = (__ldg(off + min(r_begin + (nt + 1) * tile_reads, r_end)) - off_bias + 15u) & ~15u;
+                    if (ne > na && ne - na <= tile_bytes) tile_prefetch_l2(bases + na, ne - na);
+                }
             }
-            __syncthreads();
+            if (e > a) { mbar_wait(&tile_bar, parity); parity ^= 1; }
             const u32* sw = reinterpret_cast<const u32*>(smem);
             auto ld = [sw](u32 i) { return sw[i]; };
             created += scan_read(v, ld, ldr4, r < r1 ? o0 - a : 0u, len, a, pend);
@@ -577,104 +609,6 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
             if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
             if (acc[g * 3 + 2]) atomicAdd(gstats + g * 4 + 2, acc[g * 3 + 2]);
             if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
-        }
-    }
-}
-
-// k_map_half — map_kmers for re-keyed tables of at most four genomes: a HALF-WARP per counted k-mer, one lane per
-// queried bucket (a whole warp when more than 16 buckets are queried).  The 16 probes of a k-mer are independent
-// L2 accesses; issuing them from 16 lanes at once instead of one after the other from one thread is what this kernel
-// is about (the thread-per-k-mer version spent two thirds of its time waiting for the probe it had just issued).
-// Per-genome hit counts are 32-bit fields of two registers, summed over the group with shuffles.
-template <int PILEUP>
-__global__ void __launch_bounds__(256)
-k_map_half(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
-           u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
-    const u32 n = min(*n_ptr, n_cap);
-    const u32 k = m.k;
-    const u32 lane = threadIdx.x & 31;
-    i32 best = -1; u32 g_row0 = 0;
-    if (PILEUP) {
-        best = *best_ptr;
-        if (best < 0) return;
-        g_row0 = m.genome_row0[best];
-    }
-    const u32 nb = m.b1 - m.b0;
-    const u32 G = nb <= 16 ? 16u : 32u;                 // lanes per k-mer
-    const u32 gl = lane & (G - 1), gid = lane / G, per_warp = 32 / G;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    u32 acc[12];                                        // group leaders: [g*3 + {perfect, variant, unique}]
-#pragma unroll
-    for (u32 i = 0; i < 12; i++) acc[i] = 0;
-    const u32 n_round = ((n + per_warp - 1) / per_warp) * per_warp;
-    for (u32 t0 = warp * per_warp; t0 < n_round; t0 += n_warps * per_warp) {
-        const u32 t = t0 + gid;
-        const bool live = t < n;
-        u64 h01 = 0, h23 = 0;                           // hits of genomes 0,1 / 2,3 (32 bits each)
-        if (live) {
-            const u64 fwd = __ldg(kmers + t);
-            const u32 cnt = __ldg(counts + t);
-            const u64 rev = revcomp_dev(fwd, k);
-            const bool rc = !(fwd < rev);               // src/lcb.rs:87-95
-            const u64 kb = rc ? rev : fwd;
-            for (u32 i = m.b0 + gl; i < m.b1; i += G) {
-                const u64 bucket = ((u64)i << 58) | (kb & ~(3ull << (2 * (k - 1 - i))));
-                u32 h = hash_slot(bucket, m.shift);
-                u32 off = 0, len = 0;
-                for (;;) {
-                    const uint4 sl = __ldg(reinterpret_cast<const uint4*>(m.slots) + h);
-                    const u64 key = ((u64)sl.y << 32) | sl.x;
-                    if (key == bucket) { off = sl.z; len = sl.w; break; }
-                    if (key == BK_EMPTY) break;
-                    h = (h + 1) & m.mask;
-                }
-                for (u32 j = 0; j < len; j++) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
-                    const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
-                    if (row == 0xFFFFFFFFu) continue;
-                    if (!PILEUP) {                                                    // src/call.rs:1316-1318
-                        if (file_id < 2) h01 += 1ull << (32 * file_id); else h23 += 1ull << (32 * (file_id - 2));
-                    } else if ((i32)file_id == best) {
-                        u32 bit; bool to_fwd;
-                        if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
-                        else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
-                        const u32 cell = (row + idx - g_row0) * 4 + bit;
-                        atomicAdd(pile + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
-                        atomicMax(pile + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
-                    }
-                }
-            }
-        }
-        if (!PILEUP) {                                                               // src/call.rs:1389-1419
-            for (u32 o = G >> 1; o; o >>= 1) {
-                h01 += __shfl_xor_sync(0xFFFFFFFFu, h01, o);
-                h23 += __shfl_xor_sync(0xFFFFFFFFu, h23, o);
-            }
-            if (gl == 0 && live) {
-                const u32 hg[4] = {(u32)h01, (u32)(h01 >> 32), (u32)h23, (u32)(h23 >> 32)};
-                u32 n_perfect = 0;
-#pragma unroll
-                for (u32 g = 0; g < 4; g++) n_perfect += (hg[g] == nb && nb != 0) ? 1u : 0u;
-#pragma unroll
-                for (u32 g = 0; g < 4; g++) {
-                    const bool perfect = hg[g] != 0 && hg[g] == nb;
-                    acc[g * 3] += perfect ? 1u : 0u;
-                    acc[g * 3 + 1] += (hg[g] != 0 && !perfect) ? 1u : 0u;
-                    acc[g * 3 + 2] += (perfect && n_perfect == 1) ? 1u : 0u;
-                }
-            }
-        }
-    }
-    if (!PILEUP) {
-#pragma unroll
-        for (u32 i = 0; i < 12; i++) acc[i] = warp_sum_u32(acc[i]);
-        if (lane == 0) {
-            for (u32 g = 0; g < m.n_genomes && g < 4; g++) {
-                if (acc[g * 3]) atomicAdd(gstats + g * 4, acc[g * 3]);
-                if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
-                if (acc[g * 3 + 2]) atomicAdd(gstats + g * 4 + 2, acc[g * 3 + 2]);
-                if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
-            }
         }
     }
 }
