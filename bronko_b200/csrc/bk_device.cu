@@ -85,6 +85,7 @@ struct bk_ctx {
     Counters* h_ctr = nullptr;              // pinned
     DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
+    DevBuf<u32> d_pile_all;                 // one such block per genome (databases of at most four genomes: one-pass map)
     DevBuf<double> d_noise;                 // Noise.max per row
     DevBuf<double> d_nz_maf, d_nz_s, d_nz_s2, d_nz_tab, d_nz_warm;   // noise scratch (bk_noise.cuh: NoiseView)
     DevBuf<u8> d_nz_flag; DevBuf<u32> d_nz_stats;
@@ -99,6 +100,7 @@ struct bk_ctx {
     DevBuf<u32> d_part;
     bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
+    bool no_fused_map = false;              // tests: BK_NO_FUSED_MAP keeps the two-pass map on small databases
 
     // results
     bk_sample_result result;
@@ -185,6 +187,7 @@ int bk_create(bk_ctx** out, int device) {
     bk_params_default(&ctx->params);
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
+    ctx->no_fused_map = getenv("BK_NO_FUSED_MAP") != nullptr;
     *out = ctx;
     return BK_OK;
 }
@@ -199,7 +202,7 @@ void bk_destroy(bk_ctx* ctx) {
     ctx->d_ref_code.release();
     for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
     ctx->d_part.release();
-    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release();
+    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();
     ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
     ctx->d_nz_flag.release(); ctx->d_nz_stats.release();
@@ -267,6 +270,7 @@ static int upload_index(bk_ctx* ctx) {
     for (u32 g = 0; g < d.n_genomes; g++) ctx->max_seqs_per_genome = std::max(ctx->max_seqs_per_genome, d.genome_seq_off[g + 1] - d.genome_seq_off[g]);
     const size_t rows = std::max<u32>(d.max_genome_rows, 1);
     BK_CUDA(ctx->d_pile.reserve(rows * 16));
+    if (d.n_genomes <= 4) BK_CUDA(ctx->d_pile_all.reserve(rows * 16 * d.n_genomes));
     BK_CUDA(ctx->d_noise.reserve(rows));
     {   // noise scratch: fractions with padding per sequence, per-iteration snapshots, chunk slots
         const size_t seqs = ctx->max_seqs_per_genome;
@@ -595,6 +599,36 @@ static MapView make_map_view(bk_ctx* ctx) {
 
 static int n_files_used(bk_ctx* ctx) { return ctx->file[1].used ? 2 : 1; }
 
+// stages 3 + 4 in one pass per file for databases of at most four genomes (re-keyed table, not sharded): tallies and
+// the pileups of all genomes together, selection, then the selected genome's arrays are moved to d_pile
+static bool can_fuse_map(const bk_ctx* ctx) {
+    return ctx->d.n_genomes <= 4 && ctx->d.rekeyed && !ctx->force_warp_map && ctx->shard_n == 1 && !ctx->no_fused_map;
+}
+static int stage_map_fused(bk_ctx* ctx) {
+    const DerivedIndex& d = ctx->d;
+    const MapView m = make_map_view(ctx);
+    const u32 pile_stride = d.max_genome_rows * 4;
+    const int n_files = n_files_used(ctx);
+    Counters* dc = ctx->d_ctr.p;
+    cudaStream_t st = ctx->stream;
+    int sp = ctx->span_begin(ST_MAP);
+    BK_CUDA(cudaMemsetAsync(ctx->d_pile_all.p, 0, (size_t)pile_stride * 4 * 4 * d.n_genomes, st));
+    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
+    for (int f = 0; f < n_files; f++) {
+        FileState& fs = ctx->file[f];
+        BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
+        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+        k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        ctx->launches++;
+    }
+    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
+    k_pile_pick<<<ctx->sm_count, 256, 0, st>>>(ctx->d_pile_all.p, ctx->d_pile.p, pile_stride, &dc->best);
+    ctx->launches += 2;
+    ctx->span_end(sp);
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
 // stage 3: map_kmers tallies of every file (src/call.rs:1389-1430)
 static int stage_map_stats(bk_ctx* ctx) {
     const DerivedIndex& d = ctx->d;
@@ -773,8 +807,11 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
         if ((rc = stage_fold(ctx, f))) return rc;
         if ((rc = stage_compact(ctx, f))) return rc;
     }
-    if ((rc = stage_map_stats(ctx))) return rc;
-    if ((rc = stage_select_pileup(ctx))) return rc;
+    if (can_fuse_map(ctx)) { if ((rc = stage_map_fused(ctx))) return rc; }
+    else {
+        if ((rc = stage_map_stats(ctx))) return rc;
+        if ((rc = stage_select_pileup(ctx))) return rc;
+    }
     return stage_score(ctx, out);
 }
 

@@ -509,7 +509,11 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
 // bucket is probed as soon as its id is known.  ~25x fewer warp instructions per k-mer than the
 // warp-per-k-mer kernel; the counted list keeps reference k-mers and novel k-mers in separate runs,
 // so warps stay homogeneous.
-template <int PILEUP, int REKEY>
+// MODE 0: tallies only; MODE 1: pileup of the selected genome only; MODE 2 (databases of at most four genomes, one
+// pass): tallies AND the pileup of EVERY genome — genome g's four arrays start at pile + g * 4 * pile_stride, rows
+// relative to the genome; k_pile_pick copies the selected genome's slice afterwards.  Same results as the reference,
+// which also updates every genome (src/call.rs:1324-1385) and reads only the selected one.
+template <int MODE, int REKEY>
 __global__ void __launch_bounds__(256)
 k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
             u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
@@ -517,7 +521,7 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
     const u32 k = m.k;
     const u32 lane = threadIdx.x & 31;
     i32 best = -1; u32 g_row0 = 0;
-    if (PILEUP) {
+    if (MODE == 1) {
         best = *best_ptr;
         if (best < 0) return;
         g_row0 = m.genome_row0[best];
@@ -572,15 +576,17 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
                         const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
                         const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
                         if (row == 0xFFFFFFFFu) continue;
-                        if (!PILEUP) {
-                            hits4 += 1ull << (16 * file_id);                  // src/call.rs:1316-1318
-                        } else if ((i32)file_id == best) {
+                        if (MODE != 1) hits4 += 1ull << (16 * file_id);       // src/call.rs:1316-1318
+                        if (MODE == 2 || (MODE == 1 && (i32)file_id == best)) {
                             u32 bit; bool to_fwd;
                             if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
                             else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
-                            const u32 cell = (row + idx - g_row0) * 4 + bit;
-                            atomicAdd(pile + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
-                            atomicMax(pile + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
+                            u32* gp = pile;
+                            u32 r0 = g_row0;
+                            if (MODE == 2) { gp = pile + (size_t)file_id * 4 * pile_stride; r0 = __ldg(m.genome_row0 + file_id); }
+                            const u32 cell = (row + idx - r0) * 4 + bit;
+                            atomicAdd(gp + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
+                            atomicMax(gp + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
                         }
                     }
                 }
@@ -588,7 +594,7 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
                 mask >>= 2; p >>= 2;
             }
         }
-        if (!PILEUP) {                                                       // src/call.rs:1389-1419
+        if (MODE != 1) {                                                     // src/call.rs:1389-1419
             u32 n_perfect = 0;
 #pragma unroll
             for (u32 g = 0; g < 4; g++) n_perfect += (((hits4 >> (16 * g)) & 0xFFFFu) == nb && nb != 0) ? 1u : 0u;
@@ -603,7 +609,7 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
             }
         }
     }
-    if (!PILEUP && lane == 0) {
+    if (MODE != 1 && lane == 0) {
         for (u32 g = 0; g < m.n_genomes && g < 4; g++) {
             if (acc[g * 3]) atomicAdd(gstats + g * 4, acc[g * 3]);
             if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
@@ -611,6 +617,16 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
             if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
         }
     }
+}
+
+// after a MODE 2 map: the selected genome's four arrays → the front of the buffer every later stage reads
+__global__ void __launch_bounds__(256) k_pile_pick(const u32* __restrict__ pile_all, u32* __restrict__ pile, u32 pile_stride, const i32* best_ptr) {
+    const i32 best = *best_ptr;
+    if (best < 0) return;
+    const uint4* src = reinterpret_cast<const uint4*>(pile_all + (size_t)best * 4 * pile_stride);
+    uint4* dst = reinterpret_cast<uint4*>(pile);
+    const u32 n4 = pile_stride;                       // 4 arrays * pile_stride u32 = pile_stride uint4
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // k_select — pick_best_genome / pick_best_genome_paired (src/call.rs:422-502): argmax of

@@ -86,18 +86,22 @@ BK_HD void nz_fractions(const u32* f4, const u32* r4, double* m3) {
 
 // ---- the max table: src/call.rs:857-890 --------------------------------------------------------------------
 // Entries are bit patterns of non-negative doubles (they order like their bit patterns), non-increasing, 0 = empty.
-struct NzTable { u64 t[BK_NOISE_TABLE]; u64 lo; };   // lo: smallest non-zero entry (bits), ~0 if none
+struct NzTable { u64 t[BK_NOISE_TABLE]; u64 skip_below; };
+// skip_below: a leaving value whose bit pattern is below this (and above NZ_TINY) cannot be within 1e-12 of any entry —
+// the smallest non-zero entry minus 4e-12 (everything if the table is empty, nothing if that entry is tiny itself)
+#define BK_NZ_TINY_BITS 0x3D919799812DEA11ull      /* 4e-12 */
 
-BK_HD void nz_table_clear(NzTable& T) {
-#pragma unroll
-    for (int q = 0; q < BK_NOISE_TABLE; q++) T.t[q] = 0;
-    T.lo = ~0ull;
-}
 BK_HD void nz_table_relo(NzTable& T) {
     u64 lo = ~0ull;
 #pragma unroll
     for (int q = 0; q < BK_NOISE_TABLE; q++) if (T.t[q] != 0) lo = T.t[q];     // non-increasing: the last non-zero
-    T.lo = lo;
+    if (lo == ~0ull) T.skip_below = ~0ull;
+    else { const double d = nz_sub(nz_d(lo), 4e-12); T.skip_below = d > 4e-12 ? nz_b(d) : 0ull; }
+}
+BK_HD void nz_table_clear(NzTable& T) {
+#pragma unroll
+    for (int q = 0; q < BK_NOISE_TABLE; q++) T.t[q] = 0;
+    T.skip_below = ~0ull;
 }
 // insert (src/call.rs:872-890): bubbles up while strictly greater → lands behind every entry >= nw
 BK_HD void nz_table_insert(NzTable& T, u64 nwb) {
@@ -111,10 +115,10 @@ BK_HD void nz_table_insert(NzTable& T, u64 nwb) {
     nz_table_relo(T);
 }
 // evict (src/call.rs:857-869): the FIRST entry within 1e-12 of the leaving value is removed, nothing refills
-BK_HD void nz_table_evict(NzTable& T, double old) {
-    if (!(old > 0.0)) return;
-    // no entry can be within 1e-12 of `old` if old is clear of zero and clearly below the smallest non-zero entry
-    if (old > 4e-12 && (T.lo == ~0ull || nz_add(old, 4e-12) < nz_d(T.lo))) return;
+BK_HD void nz_table_evict(NzTable& T, u64 oldb) {
+    if (oldb == 0) return;                                  // fractions are never negative: old > 0.0 <=> bits != 0
+    if (oldb > BK_NZ_TINY_BITS && oldb < T.skip_below) return;
+    const double old = nz_d(oldb);
     u32 pos = BK_NOISE_TABLE;
 #pragma unroll
     for (int q = BK_NOISE_TABLE - 1; q >= 0; q--) if (nz_abs(nz_sub(nz_d(T.t[q]), old)) < 1e-12) pos = (u32)q;
@@ -125,8 +129,8 @@ BK_HD void nz_table_evict(NzTable& T, double old) {
     nz_table_relo(T);
 }
 BK_HD void nz_table_update(NzTable& T, double old, double nw) {
-    nz_table_evict(T, old);
-    if (nw > 0.0) nz_table_insert(T, nz_b(nw));
+    nz_table_evict(T, nz_b(old));
+    nz_table_insert(T, nz_b(nw));
 }
 BK_HD bool nz_table_equal(const NzTable& T, const double* snap) {
     bool eq = true;
@@ -302,17 +306,19 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
     o[0] = m3[0]; o[1] = m3[1]; o[2] = m3[2];
 }
 
-// ---- chain block: 256 threads, one iteration per thread and round ---------------------------------------------
-#define BK_NZ_SEQ_THREADS 256
+// ---- chain block: 512 threads, half an iteration (three operations) per thread and round ----------------------
+#define BK_NZ_SEQ_THREADS 512
+#define BK_NZ_SEQ_WARPS (BK_NZ_SEQ_THREADS / 32)
 #define BK_NZ_CHAIN_SMEM ((BK_NZ_TILE + BK_NOISE_WINDOW) * 3 * 8)
 #define BK_NZ_TABLE_POS (BK_NOISE_WINDOW + BK_NZ_WARM + BK_NZ_CHUNK)          // positions a chunk lane touches
-#define BK_NZ_TABLE_SMEM (8 * BK_NZ_TABLE_POS * 3 * 8)
+#define BK_NZ_TABLE_WARPS 8                                                   // chunk lanes per table block
+#define BK_NZ_TABLE_SMEM (BK_NZ_TABLE_WARPS * BK_NZ_TABLE_POS * 3 * 8)
 #define BK_NZ_SEQ_SMEM (BK_NZ_TABLE_SMEM > BK_NZ_CHAIN_SMEM ? BK_NZ_TABLE_SMEM : BK_NZ_CHAIN_SMEM)
 
 template <bool SQUARE>
 __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* mt) {
-    __shared__ i64 wt0[2][8], wt1[2][8];
-    __shared__ u32 wbad[2][8];
+    __shared__ i64 wt0[2][BK_NZ_SEQ_WARPS], wt1[2][BK_NZ_SEQ_WARPS];
+    __shared__ u32 wbad[2][BK_NZ_SEQ_WARPS];
     __shared__ double sstate[2];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* mafp = nv.maf + (size_t)(sq.mbase - BK_NZ_PAD_LO) * 3;       // position -100
@@ -324,6 +330,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     u32 round = 0, serial_left = 0, width = BK_NZ_ROUND;                        // width: iterations tried per round
     u32 st_rounds = 0, st_stops = 0, st_serial = 0;
     const long long t_begin = clock64();
+    const u32 my_it = tid >> 1, my_q0 = (tid & 1) * 3;                          // this thread: operations my_q0 .. my_q0+2 of iteration i0 + my_it
     while (i0 < iters) {
         if (i0 + 1 > tile_hi || (i0 + BK_NZ_ROUND > tile_hi && tile_hi < iters)) {
             __syncthreads();
@@ -354,64 +361,68 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         round++; st_rounds++;
         const NzBinade bin = nz_binade(ef);
         const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
-        const bool active = tid < n_it;
-        i64 pre0[6], pre1[6];
-        i64 x0 = 0, x1 = 0;                                                      // exclusive prefix inside the warp
-        u32 bad = 6;
-        if (wid * 32 < n_it) {                                                   // warps without an iteration skip the work
+        const bool active = my_it < n_it;
+        const u32 n_warps_used = (2 * n_it + 31) >> 5;
+        i64 pre0[3], pre1[3];
+        i64 f0 = 0, f1 = 0;                                                      // inclusive scan of the parity maps in the warp
+        u32 bad = 3;
+        if (wid < n_warps_used) {                                                // warps without an operation skip the work
             i64 run0 = 0, run1 = 0;
 #pragma unroll
-            for (u32 q = 0; q < 6; q++) {
-                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + tid), q) : 0.0;
+            for (u32 q = 0; q < 3; q++) {
+                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + my_it), my_q0 + q) : 0.0;
                 i64 ie, io;
                 const bool ok = nz_incs(bin, x, &ie, &io);
                 run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
                 pre0[q] = run0; pre1[q] = run1;
-                if (!ok && bad == 6) bad = q;
+                if (!ok && bad == 3) bad = q;
             }
-            // inclusive scan of the parity maps over the warp
-            i64 f0 = run0, f1 = run1;
+            f0 = run0; f1 = run1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, f0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, f1, o);
                 if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, f0, f1, &h0, &h1); f0 = h0; f1 = h1; }
             }
             if (lane == 31) { wt0[buf][wid] = f0; wt1[buf][wid] = f1; }
-            x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1); x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);
-            if (lane == 0) { x0 = 0; x1 = 0; }
         } else {
 #pragma unroll
-            for (u32 q = 0; q < 6; q++) { pre0[q] = 0; pre1[q] = 0; }
+            for (u32 q = 0; q < 3; q++) { pre0[q] = 0; pre1[q] = 0; }
             if (lane == 31) { wt0[buf][wid] = 0; wt1[buf][wid] = 0; }
         }
+        i64 x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1), x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);     // exclusive inside the warp
+        if (lane == 0) { x0 = 0; x1 = 0; }
         __syncthreads();
-        i64 base = S0;
-        for (u32 w = 0; w < wid; w++) base += (base & 1) ? wt1[buf][w] : wt0[buf][w];
+        // the maps of the warps in front of this one: every warp scans the (at most 16) warp totals itself
+        i64 w0 = 0, w1 = 0;
+        if (lane < BK_NZ_SEQ_WARPS) { w0 = wt0[buf][lane]; w1 = wt1[buf][lane]; }
+#pragma unroll
+        for (int o = 1; o < BK_NZ_SEQ_WARPS; o <<= 1) {
+            const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, w0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, w1, o);
+            if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, w0, w1, &h0, &h1); w0 = h0; w1 = h1; }
+        }
+        const u32 src = wid ? wid - 1 : 0;
+        i64 b0 = __shfl_sync(0xFFFFFFFFu, w0, src), b1 = __shfl_sync(0xFFFFFFFFu, w1, src);        // inclusive up to warp wid-1
+        if (wid == 0) { b0 = 0; b1 = 0; }
+        i64 base = S0 + ((S0 & 1) ? b1 : b0);
         base += (base & 1) ? x1 : x0;
         const bool odd = (base & 1) != 0;
-        i64 T[6];
+        i64 T[3];
 #pragma unroll
-        for (u32 q = 0; q < 6; q++) {
+        for (u32 q = 0; q < 3; q++) {
             T[q] = base + (odd ? pre1[q] : pre0[q]);
             if (!nz_inside(T[q]) && bad > q) bad = q;
         }
         const u32 total_ops = n_it * 6;
-        u32 mine = (active && bad < 6) ? tid * 6 + bad : total_ops;
+        u32 mine = (active && bad < 3) ? tid * 3 + bad : total_ops;
         mine = __reduce_min_sync(0xFFFFFFFFu, mine);
         if (lane == 0) wbad[buf][wid] = mine;
         __syncthreads();
-        u32 n_ok = total_ops;
-#pragma unroll
-        for (u32 w = 0; w < 8; w++) n_ok = min(n_ok, wbad[buf][w]);
-        if (active && tid * 6 + 5 < n_ok) snap[i0 + tid] = nz_value(ef, T[5]);
+        u32 n_ok = lane < BK_NZ_SEQ_WARPS ? wbad[buf][lane] : total_ops;
+        n_ok = __reduce_min_sync(0xFFFFFFFFu, n_ok);
+        if (active && (tid & 1) && tid * 3 + 2 < n_ok) snap[i0 + my_it] = nz_value(ef, T[2]);
         if (n_ok > 0) {
-            const u32 owner = (n_ok - 1) / 6, oq = (n_ok - 1) - owner * 6;
-            if (tid == owner) {
-                i64 Tl = T[0];
-#pragma unroll
-                for (u32 q = 1; q < 6; q++) if (q == oq) Tl = T[q];
-                sstate[buf] = nz_value(ef, Tl);
-            }
+            const u32 owner = (n_ok - 1) / 3, oq = (n_ok - 1) - owner * 3;
+            if (tid == owner) sstate[buf] = nz_value(ef, oq == 0 ? T[0] : (oq == 1 ? T[1] : T[2]));
         }
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
@@ -422,7 +433,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
-        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): one warp
+        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): two warps
         if (ib < 4) serial_left = 1;
     }
     if (tid == 0 && nv.stats) {
@@ -431,7 +442,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     }
 }
 
-// grid (2 + ceil(max_chunks / 8), max_seqs), 256 threads, BK_NZ_SEQ_SMEM dynamic shared memory
+// grid (2 + ceil(max_chunks / 8), max_seqs), 512 threads, BK_NZ_SEQ_SMEM dynamic shared memory
 __global__ void __launch_bounds__(BK_NZ_SEQ_THREADS) k_noise_seq(NoiseView nv) {
     extern __shared__ __align__(16) u8 nz_sm[];
     const NzSeq s = nz_seq(nv, blockIdx.y);
@@ -442,7 +453,8 @@ __global__ void __launch_bounds__(BK_NZ_SEQ_THREADS) k_noise_seq(NoiseView nv) {
     // table chunks: warp w of this block owns chunk (blockIdx.x - 2) * 8 + w; its lanes stage the fractions the chunk
     // touches into shared memory, lane 0 walks them
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const u32 c = (blockIdx.x - 2) * 8 + wid;
+    if (wid >= BK_NZ_TABLE_WARPS) return;
+    const u32 c = (blockIdx.x - 2) * BK_NZ_TABLE_WARPS + wid;
     const u32 n_chunks = (s.iters + BK_NZ_CHUNK - 1) / BK_NZ_CHUNK;
     if (c >= n_chunks) return;
     double* wm = mt + (size_t)wid * BK_NZ_TABLE_POS * 3;

@@ -172,6 +172,21 @@ def test_id_keyed_map_tables(sars_paths, oracle, monkeypatch, warp_map):
         c.close()
 
 
+def test_two_pass_map_on_small_db(sars_paths, oracle, monkeypatch):
+    """BK_NO_FUSED_MAP: tallies, selection, then a second pass for the selected genome's pileup (what databases of
+    more than four genomes and the read-sharded mode use) instead of the one-pass map of small databases."""
+    import bronko_b200
+    monkeypatch.setenv("BK_NO_FUSED_MAP", "1")
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, sars_paths)
+        oi = oracle.Index.build(21, sars_paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[1]), 400, sim.SEED0 + 44)
+        run_both(c, oi, [(r1, o1), (r2, o2)])
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("k", [15, 19, 29, 31])
 def test_other_k(oracle, k):
     """k = 15 .. 31 (odd): k <= 29 probes the re-keyed table, k = 31 the id-keyed one (bucket ids wrap there, Q20)."""
