@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--ref-depth", type=int, default=2000, help="bounded sample depth for the CPU arm")
     ap.add_argument("--cpu-depth", type=int, default=2000, help="bounded sample depth for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=3,
+    ap.add_argument("--in-flight", type=int, default=4,
                     help="samples in flight per GPU (one bk_ctx + stream each); 1 = strictly one sample at a time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -167,9 +167,12 @@ def main():
     # three warps) overlaps the next samples' streaming kernels.  Every step is still one whole sample.
     S = max(1, args.in_flight)
     ctxs = []
-    for _ in range(S):
+    for i in range(S):
         c = bronko_b200.Bronko(local_rank)    # raises without the CUDA library / a B200: no fallback
-        c.build_index(21, [sim.genome_path(n) for n in sim.SARS4])
+        if i == 0:
+            c.build_index(21, [sim.genome_path(n) for n in sim.SARS4])
+        else:
+            c.share_index(ctxs[0])            # one copy of the db per GPU
         ctxs.append(c)
     ctx = ctxs[0]
     files = make_workload(rank, args.depth)

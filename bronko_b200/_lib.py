@@ -63,6 +63,7 @@ SIGNATURES = {
     "bk_index_load_file": (C.c_int, [P, C.c_char_p]),
     "bk_index_build": (C.c_int, [P, u32, u32, P]),
     "bk_index_save": (C.c_int, [P, C.c_char_p]),
+    "bk_index_share": (C.c_int, [P, P]),
     "bk_index_info": (C.c_int, [P, P, P, P, P]),
     "bk_genome_name": (C.c_char_p, [P, u32]),
     "bk_genome_n_seqs": (u32, [P, u32]),

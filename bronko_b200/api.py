@@ -101,6 +101,11 @@ class Bronko:
     def save_index(self, path):
         self._check(self._lib.bk_index_save(self.h, path.encode()))
 
+    def share_index(self, owner):
+        """Read the index of another context on the same GPU instead of loading a copy (one context per sample in
+        flight, one set of tables)."""
+        self._check(self._lib.bk_index_share(self.h, owner.h))
+
     def load_index_arrays(self, k, keys, entry_off, entries, genome_seq_off, seq_len, seq_base_off, ref_bases):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         entry_off = np.ascontiguousarray(entry_off, dtype=np.uint64)

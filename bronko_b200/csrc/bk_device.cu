@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -58,6 +59,27 @@ struct FileState {
     u64 total_reads = 0, total_bases = 0;
 };
 
+// The index on one device: host form, derived tables and their device copies.  Read-only once uploaded, so the
+// contexts of one GPU (one per sample in flight) share a single copy (bk_index_share): the bucket table stays
+// L2-resident for all of them instead of once per context.
+struct IndexDev {
+    int device = 0;
+    HostIndex ix;
+    DerivedIndex d;
+    DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
+    DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
+    DevBuf<ExactSlotD> d_exact;
+    DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
+    DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
+    u32 max_seqs_per_genome = 1;
+    ~IndexDev() {
+        cudaSetDevice(device);
+        d_bucket_slots.release(); d_bucket_entries.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
+        d_exact.release(); d_slot2id.release(); d_id_kmer.release(); d_genome_row0.release(); d_genome_seq_off.release();
+        d_seq_row0.release(); d_genome_len.release(); d_ref_code.release();
+    }
+};
+
 }  // namespace
 
 struct bk_ctx {
@@ -66,16 +88,7 @@ struct bk_ctx {
     std::string err;
     int sm_count = 148;
 
-    HostIndex ix;
-    DerivedIndex d;
-    bool have_index = false;
-    // device copies of the derived index
-    DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
-    DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
-    DevBuf<ExactSlotD> d_exact;
-    DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
-    DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
-    u32 max_seqs_per_genome = 1;
+    std::shared_ptr<IndexDev> I;            // null until an index is loaded / built / shared
 
     // per-sample state
     bk_params params;
@@ -196,10 +209,7 @@ void bk_destroy(bk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    ctx->d_bucket_slots.release(); ctx->d_bucket_entries.release(); ctx->d_refnib.release(); ctx->d_oseq_start.release();
-    ctx->d_oseq_len.release(); ctx->d_exact.release(); ctx->d_slot2id.release(); ctx->d_id_kmer.release();
-    ctx->d_genome_row0.release(); ctx->d_genome_seq_off.release(); ctx->d_seq_row0.release(); ctx->d_genome_len.release();
-    ctx->d_ref_code.release();
+    ctx->I.reset();                         // the last context sharing an index frees its device copies
     for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
     ctx->d_part.release();
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
@@ -239,41 +249,54 @@ uint64_t bk_clean_sample_id(const char* path, char* buf, uint64_t cap) {
 // ---------------------------------------------------------------------------------------------
 // index
 // ---------------------------------------------------------------------------------------------
-static int upload_index(bk_ctx* ctx) {
+static int size_for_index(bk_ctx* ctx);
+
+// device copies of a freshly filled IndexDev (I->ix); on success it becomes the context's index
+static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
     cudaSetDevice(ctx->device);
-    if (ctx->ix.k < 15 || ctx->ix.k > 31 || (ctx->ix.k & 1) == 0)
+    fresh->device = ctx->device;
+    if (fresh->ix.k < 15 || fresh->ix.k > 31 || (fresh->ix.k & 1) == 0)
         return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
-    derive_index(ctx->ix, ctx->d, getenv("BK_NO_REKEY") == nullptr);
-    const DerivedIndex& d = ctx->d;
+    derive_index(fresh->ix, fresh->d, getenv("BK_NO_REKEY") == nullptr);
+    ctx->I = fresh;
+    const DerivedIndex& d = ctx->I->d;
     if (d.n_genomes == 0 || d.n_genomes > 4096) return ctx->fail(BK_ERR_ARG, "index holds %u genomes (supported: 1..4096)", d.n_genomes);
     if ((u64)d.n_raw + 2 >= 0x7FFFFFFFull) return ctx->fail(BK_ERR_ARG, "reference set too large for 32-bit slot indices");
     cudaStream_t st = ctx->stream;
     static_assert(sizeof(BucketSlot) == sizeof(BucketSlotD) && sizeof(BucketEntry) == sizeof(BucketEntryD) && sizeof(ExactSlot) == sizeof(ExactSlotD), "layout");
-    BK_CUDA(ctx->d_bucket_slots.reserve(d.bucket_slots.size()));
-    BK_CUDA(cudaMemcpyAsync(ctx->d_bucket_slots.p, d.bucket_slots.data(), d.bucket_slots.size() * 16, cudaMemcpyHostToDevice, st));
-    BK_CUDA(ctx->d_bucket_entries.reserve(d.bucket_entries.size()));
+    BK_CUDA(ctx->I->d_bucket_slots.reserve(d.bucket_slots.size()));
+    BK_CUDA(cudaMemcpyAsync(ctx->I->d_bucket_slots.p, d.bucket_slots.data(), d.bucket_slots.size() * 16, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->I->d_bucket_entries.reserve(d.bucket_entries.size()));
     if (!d.bucket_entries.empty())
-        BK_CUDA(cudaMemcpyAsync(ctx->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
-    BK_CUDA(ctx->d_exact.reserve(d.exact_slots.size()));
-    BK_CUDA(cudaMemcpyAsync(ctx->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
-    BK_CUDA(ctx->d_refnib.upload(d.refnib, st));
-    BK_CUDA(ctx->d_oseq_start.upload(d.oseq_start, st));
-    BK_CUDA(ctx->d_oseq_len.upload(d.oseq_len, st));
-    BK_CUDA(ctx->d_slot2id.upload(d.slot2id, st));
-    BK_CUDA(ctx->d_id_kmer.upload(d.id_kmer, st));
-    BK_CUDA(ctx->d_genome_row0.upload(d.genome_row0, st));
-    BK_CUDA(ctx->d_genome_seq_off.upload(d.genome_seq_off, st));
-    BK_CUDA(ctx->d_seq_row0.upload(d.seq_row0, st));
-    BK_CUDA(ctx->d_genome_len.upload(d.genome_len, st));
-    BK_CUDA(ctx->d_ref_code.upload(d.ref_code, st));
-    ctx->max_seqs_per_genome = 1;
-    for (u32 g = 0; g < d.n_genomes; g++) ctx->max_seqs_per_genome = std::max(ctx->max_seqs_per_genome, d.genome_seq_off[g + 1] - d.genome_seq_off[g]);
+        BK_CUDA(cudaMemcpyAsync(ctx->I->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->I->d_exact.reserve(d.exact_slots.size()));
+    BK_CUDA(cudaMemcpyAsync(ctx->I->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
+    BK_CUDA(ctx->I->d_refnib.upload(d.refnib, st));
+    BK_CUDA(ctx->I->d_oseq_start.upload(d.oseq_start, st));
+    BK_CUDA(ctx->I->d_oseq_len.upload(d.oseq_len, st));
+    BK_CUDA(ctx->I->d_slot2id.upload(d.slot2id, st));
+    BK_CUDA(ctx->I->d_id_kmer.upload(d.id_kmer, st));
+    BK_CUDA(ctx->I->d_genome_row0.upload(d.genome_row0, st));
+    BK_CUDA(ctx->I->d_genome_seq_off.upload(d.genome_seq_off, st));
+    BK_CUDA(ctx->I->d_seq_row0.upload(d.seq_row0, st));
+    BK_CUDA(ctx->I->d_genome_len.upload(d.genome_len, st));
+    BK_CUDA(ctx->I->d_ref_code.upload(d.ref_code, st));
+    ctx->I->max_seqs_per_genome = 1;
+    for (u32 g = 0; g < d.n_genomes; g++) ctx->I->max_seqs_per_genome = std::max(ctx->I->max_seqs_per_genome, d.genome_seq_off[g + 1] - d.genome_seq_off[g]);
+    BK_CUDA(cudaStreamSynchronize(st));
+    return size_for_index(ctx);
+}
+
+// per-context buffers whose size follows the index (pileups, noise scratch, per-file counters)
+static int size_for_index(bk_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    const DerivedIndex& d = ctx->I->d;
     const size_t rows = std::max<u32>(d.max_genome_rows, 1);
     BK_CUDA(ctx->d_pile.reserve(rows * 16));
     if (d.n_genomes <= 4) BK_CUDA(ctx->d_pile_all.reserve(rows * 16 * d.n_genomes));
     BK_CUDA(ctx->d_noise.reserve(rows));
     {   // noise scratch: fractions with padding per sequence, per-iteration snapshots, chunk slots
-        const size_t seqs = ctx->max_seqs_per_genome;
+        const size_t seqs = ctx->I->max_seqs_per_genome;
         const size_t it_slots = rows + BK_NOISE_HALF * seqs;
         const size_t chunk_slots = it_slots / BK_NZ_CHUNK + seqs + 2;
         u32 max_len = 0;
@@ -284,7 +307,7 @@ static int upload_index(bk_ctx* ctx) {
         BK_CUDA(ctx->d_nz_tab.reserve(it_slots * BK_NOISE_TABLE));
         BK_CUDA(ctx->d_nz_warm.reserve(chunk_slots * BK_NOISE_TABLE));
         BK_CUDA(ctx->d_nz_flag.reserve(chunk_slots));
-        BK_CUDA(ctx->d_nz_stats.reserve(8));
+        BK_CUDA(ctx->d_nz_stats.reserve(16));
     }
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
@@ -294,10 +317,17 @@ static int upload_index(bk_ctx* ctx) {
         BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
         BK_CUDA(f.gstats.reserve((size_t)d.n_genomes * 4));
     }
-    BK_CUDA(cudaStreamSynchronize(st));
-    ctx->have_index = true;
     ctx->in_sample = false; ctx->finished = false;
     return BK_OK;
+}
+
+int bk_index_share(bk_ctx* ctx, bk_ctx* owner) {
+    if (!ctx || !owner) return BK_ERR_ARG;
+    if (!owner->I) return ctx->fail(BK_ERR_ARG, "bk_index_share: the other context holds no index");
+    if (owner->device != ctx->device) return ctx->fail(BK_ERR_ARG, "bk_index_share: contexts live on different devices");
+    if (ctx->in_sample && !ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_index_share: call between samples");
+    ctx->I = owner->I;
+    return size_for_index(ctx);
 }
 
 int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys, const uint64_t* entry_off,
@@ -306,8 +336,8 @@ int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys
     if (!ctx) return BK_ERR_ARG;
     if (!keys || !entry_off || !entries || !genome_seq_off || !seq_len || !seq_base_off || !ref_bases)
         return ctx->fail(BK_ERR_ARG, "bk_index_load: null argument");
-    HostIndex& ix = ctx->ix;
-    ix = HostIndex();
+    auto fresh = std::make_shared<IndexDev>();
+    HostIndex& ix = fresh->ix;
     ix.k = k; ix.meta_k = k;
     std::vector<KeyedEntry> pairs;
     pairs.reserve(entry_off[n_keys]);
@@ -326,14 +356,15 @@ int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys
         }
         ix.genomes.push_back(std::move(hg));
     }
-    return upload_index(ctx);
+    return upload_index(ctx, fresh);
 }
 
 int bk_index_load_file(bk_ctx* ctx, const char* path) {
     if (!ctx || !path) return BK_ERR_ARG;
     std::string err;
-    if (!bkdb_read(path, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
-    return upload_index(ctx);
+    auto fresh = std::make_shared<IndexDev>();
+    if (!bkdb_read(path, fresh->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    return upload_index(ctx, fresh);
 }
 
 int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const* fasta_paths) {
@@ -341,41 +372,42 @@ int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const*
     if (k < 15 || k > 31 || (k & 1) == 0) return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
     std::vector<std::string> paths(fasta_paths, fasta_paths + n_files);
     std::string err;
-    if (!index_build_from_fasta(k, paths, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
-    return upload_index(ctx);
+    auto fresh = std::make_shared<IndexDev>();
+    if (!index_build_from_fasta(k, paths, fresh->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    return upload_index(ctx, fresh);
 }
 
 int bk_index_save(bk_ctx* ctx, const char* path) {
-    if (!ctx || !path || !ctx->have_index) return BK_ERR_ARG;
+    if (!ctx || !path || !(ctx->I != nullptr)) return BK_ERR_ARG;
     std::string err;
-    if (!bkdb_write(path, ctx->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
+    if (!bkdb_write(path, ctx->I->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
     return BK_OK;
 }
 
 int bk_index_info(bk_ctx* ctx, uint32_t* k, uint64_t* n_keys, uint64_t* n_entries, uint32_t* n_genomes) {
-    if (!ctx || !ctx->have_index) return BK_ERR_ARG;
-    if (k) *k = ctx->ix.k;
-    if (n_keys) *n_keys = ctx->ix.keys.size();
-    if (n_entries) *n_entries = ctx->ix.entries.size();
-    if (n_genomes) *n_genomes = (u32)ctx->ix.genomes.size();
+    if (!ctx || !(ctx->I != nullptr)) return BK_ERR_ARG;
+    if (k) *k = ctx->I->ix.k;
+    if (n_keys) *n_keys = ctx->I->ix.keys.size();
+    if (n_entries) *n_entries = ctx->I->ix.entries.size();
+    if (n_genomes) *n_genomes = (u32)ctx->I->ix.genomes.size();
     return BK_OK;
 }
-const char* bk_genome_name(bk_ctx* ctx, uint32_t g) { return (ctx && g < ctx->ix.genomes.size()) ? ctx->ix.genomes[g].name.c_str() : nullptr; }
-uint32_t bk_genome_n_seqs(bk_ctx* ctx, uint32_t g) { return (ctx && g < ctx->ix.genomes.size()) ? (u32)ctx->ix.genomes[g].seqs.size() : 0; }
+const char* bk_genome_name(bk_ctx* ctx, uint32_t g) { return (ctx && ctx->I && g < ctx->I->ix.genomes.size()) ? ctx->I->ix.genomes[g].name.c_str() : nullptr; }
+uint32_t bk_genome_n_seqs(bk_ctx* ctx, uint32_t g) { return (ctx && ctx->I && g < ctx->I->ix.genomes.size()) ? (u32)ctx->I->ix.genomes[g].seqs.size() : 0; }
 const char* bk_seq_name(bk_ctx* ctx, uint32_t g, uint32_t s) {
-    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].name.c_str() : nullptr;
+    return (ctx && ctx->I && g < ctx->I->ix.genomes.size() && s < ctx->I->ix.genomes[g].seqs.size()) ? ctx->I->ix.genomes[g].seqs[s].name.c_str() : nullptr;
 }
 uint64_t bk_seq_len(bk_ctx* ctx, uint32_t g, uint32_t s) {
-    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].len : 0;
+    return (ctx && ctx->I && g < ctx->I->ix.genomes.size() && s < ctx->I->ix.genomes[g].seqs.size()) ? ctx->I->ix.genomes[g].seqs[s].len : 0;
 }
 const uint8_t* bk_seq_bases(bk_ctx* ctx, uint32_t g, uint32_t s) {
-    return (ctx && g < ctx->ix.genomes.size() && s < ctx->ix.genomes[g].seqs.size()) ? ctx->ix.genomes[g].seqs[s].bases.data() : nullptr;
+    return (ctx && ctx->I && g < ctx->I->ix.genomes.size() && s < ctx->I->ix.genomes[g].seqs.size()) ? ctx->I->ix.genomes[g].seqs[s].bases.data() : nullptr;
 }
 int bk_index_export(bk_ctx* ctx, uint64_t* keys, uint64_t* entry_off, bk_bucket_info* entries) {
-    if (!ctx || !ctx->have_index || !keys || !entry_off || !entries) return BK_ERR_ARG;
-    memcpy(keys, ctx->ix.keys.data(), ctx->ix.keys.size() * 8);
-    memcpy(entry_off, ctx->ix.entry_off.data(), ctx->ix.entry_off.size() * 8);
-    memcpy(entries, ctx->ix.entries.data(), ctx->ix.entries.size() * sizeof(bk_bucket_info));
+    if (!ctx || !(ctx->I != nullptr) || !keys || !entry_off || !entries) return BK_ERR_ARG;
+    memcpy(keys, ctx->I->ix.keys.data(), ctx->I->ix.keys.size() * 8);
+    memcpy(entry_off, ctx->I->ix.entry_off.data(), ctx->I->ix.entry_off.size() * 8);
+    memcpy(entries, ctx->I->ix.entries.data(), ctx->I->ix.entries.size() * sizeof(bk_bucket_info));
     return BK_OK;
 }
 
@@ -384,10 +416,10 @@ int bk_index_export(bk_ctx* ctx, uint64_t* keys, uint64_t* entry_off, bk_bucket_
 // ---------------------------------------------------------------------------------------------
 int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     if (!ctx) return BK_ERR_ARG;
-    if (!ctx->have_index) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: no index loaded");
+    if (!(ctx->I != nullptr)) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: no index loaded");
     if (!params) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: null params");
-    if (params->k != ctx->ix.k)
-        return ctx->fail(BK_ERR_ARG, "Database k is not the same as provided, please set -k to %u or build a new index", ctx->ix.k);
+    if (params->k != ctx->I->ix.k)
+        return ctx->fail(BK_ERR_ARG, "Database k is not the same as provided, please set -k to %u or build a new index", ctx->I->ix.k);
     if (params->table_log2 != 0 && (params->table_log2 < 10 || params->table_log2 > 31))
         return ctx->fail(BK_ERR_ARG, "table_log2 must be 0 (auto) or in [10, 31]");
     cudaSetDevice(ctx->device);
@@ -405,10 +437,10 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
 
 static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     CountView v;
-    v.k = ctx->ix.k;
-    v.refnib = ctx->d_refnib.p; v.ref_chunks = (u32)(ctx->d.refnib.size() / 4);
-    v.oseq_start = ctx->d_oseq_start.p; v.oseq_len = ctx->d_oseq_len.p;
-    v.exact = ctx->d_exact.p; v.exact_shift = 64 - ctx->d.exact_log2; v.exact_mask = (1u << ctx->d.exact_log2) - 1;
+    v.k = ctx->I->ix.k;
+    v.refnib = ctx->I->d_refnib.p; v.ref_chunks = (u32)(ctx->I->d.refnib.size() / 4);
+    v.oseq_start = ctx->I->d_oseq_start.p; v.oseq_len = ctx->I->d_oseq_len.p;
+    v.exact = ctx->I->d_exact.p; v.exact_shift = 64 - ctx->I->d.exact_log2; v.exact_mask = (1u << ctx->I->d.exact_log2) - 1;
     v.diff = f.diff.p;
     v.gen = f.gen.p; v.gen_shift = 64 - f.gen_log2; v.gen_mask = (u32)((1ull << f.gen_log2) - 1);
     v.gen_full = &ctx->d_ctr.p->gen_full;
@@ -427,8 +459,8 @@ static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
     }
     f.gen_log2 = lg;
     BK_CUDA(f.gen.reserve(1ull << lg));
-    BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->d.n_raw + 2) * 4, ctx->stream));
-    BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->d.id_kmer.size(), 1) * 4, ctx->stream));
+    BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->I->d.n_raw + 2) * 4, ctx->stream));
+    BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->I->d.id_kmer.size(), 1) * 4, ctx->stream));
     k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
     ctx->launches++;
     BK_CUDA(cudaGetLastError());
@@ -547,13 +579,13 @@ int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
 static int stage_fold(bk_ctx* ctx, int slot) {
     FileState& f = ctx->file[slot];
     if (f.folded) return BK_OK;
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const u32 n = d.n_raw;
     const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
     int sp = ctx->span_begin(ST_FINALIZE);
     k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p);
     k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
-    k_diff_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p, ctx->d_slot2id.p, f.idcnt.p);
+    k_diff_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p, ctx->I->d_slot2id.p, f.idcnt.p);
     ctx->span_end(sp);
     ctx->launches += 3;
     BK_CUDA(cudaGetLastError());
@@ -565,7 +597,7 @@ static int stage_fold(bk_ctx* ctx, int slot) {
 static int stage_compact(bk_ctx* ctx, int slot) {
     FileState& f = ctx->file[slot];
     if (f.finalized) return BK_OK;
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const u32 n_ids = (u32)d.id_kmer.size();
     const size_t out_cap = (size_t)n_ids + (1ull << f.gen_log2);
     BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
@@ -574,7 +606,7 @@ static int stage_compact(bk_ctx* ctx, int slot) {
     a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n;
     a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
     a.fc = &ctx->d_ctr.p->f[slot];
-    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->d_id_kmer.p, n_ids);
+    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
     k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
     ctx->span_end(sp);
     ctx->launches += 2;
@@ -585,15 +617,15 @@ static int stage_compact(bk_ctx* ctx, int slot) {
 
 static MapView make_map_view(bk_ctx* ctx) {
     MapView m;
-    const u32 k = ctx->ix.k;
+    const u32 k = ctx->I->ix.k;
     m.k = k;
     // src/call.rs:1291-1300: buckets[n_fixed .. k - n_fixed - 1) unless --use-full-kmer
     if (ctx->params.use_full_kmer) { m.b0 = 0; m.b1 = k; }
     else if ((u64)ctx->params.n_fixed * 2 + 1 >= k) { m.b0 = 0; m.b1 = 0; }
     else { m.b0 = ctx->params.n_fixed; m.b1 = k - ctx->params.n_fixed - 1; }
-    m.slots = ctx->d_bucket_slots.p; m.shift = 64 - ctx->d.bucket_log2; m.mask = (1u << ctx->d.bucket_log2) - 1;
-    m.entries = ctx->d_bucket_entries.p;
-    m.n_genomes = ctx->d.n_genomes; m.genome_row0 = ctx->d_genome_row0.p;
+    m.slots = ctx->I->d_bucket_slots.p; m.shift = 64 - ctx->I->d.bucket_log2; m.mask = (1u << ctx->I->d.bucket_log2) - 1;
+    m.entries = ctx->I->d_bucket_entries.p;
+    m.n_genomes = ctx->I->d.n_genomes; m.genome_row0 = ctx->I->d_genome_row0.p;
     return m;
 }
 
@@ -602,10 +634,10 @@ static int n_files_used(bk_ctx* ctx) { return ctx->file[1].used ? 2 : 1; }
 // stages 3 + 4 in one pass per file for databases of at most four genomes (re-keyed table, not sharded): tallies and
 // the pileups of all genomes together, selection, then the selected genome's arrays are moved to d_pile
 static bool can_fuse_map(const bk_ctx* ctx) {
-    return ctx->d.n_genomes <= 4 && ctx->d.rekeyed && !ctx->force_warp_map && ctx->shard_n == 1 && !ctx->no_fused_map;
+    return ctx->I->d.n_genomes <= 4 && ctx->I->d.rekeyed && !ctx->force_warp_map && ctx->shard_n == 1 && !ctx->no_fused_map;
 }
 static int stage_map_fused(bk_ctx* ctx) {
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
     const int n_files = n_files_used(ctx);
@@ -621,7 +653,7 @@ static int stage_map_fused(bk_ctx* ctx) {
         k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
         ctx->launches++;
     }
-    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
+    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
     k_pile_pick<<<ctx->sm_count, 256, 0, st>>>(ctx->d_pile_all.p, ctx->d_pile.p, pile_stride, &dc->best);
     ctx->launches += 2;
     ctx->span_end(sp);
@@ -631,7 +663,7 @@ static int stage_map_fused(bk_ctx* ctx) {
 
 // stage 3: map_kmers tallies of every file (src/call.rs:1389-1430)
 static int stage_map_stats(bk_ctx* ctx) {
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
     const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
@@ -653,7 +685,7 @@ static int stage_map_stats(bk_ctx* ctx) {
 
 // stage 4: pick_best_genome(_paired) + the selected genome's pileup (src/call.rs:1324-1385)
 static int stage_select_pileup(bk_ctx* ctx) {
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
     const u32 pile_stride = d.max_genome_rows * 4;
@@ -662,7 +694,7 @@ static int stage_select_pileup(bk_ctx* ctx) {
     cudaStream_t st = ctx->stream;
     int sp = ctx->span_begin(ST_MAP);
     BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
-    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->d_genome_len.p, dc);
+    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
     ctx->launches++;
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
@@ -678,31 +710,31 @@ static int stage_select_pileup(bk_ctx* ctx) {
 
 // stage 5: noise baseline + call_variants, read everything back, fill bk_sample_result
 static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
-    const DerivedIndex& d = ctx->d;
+    const DerivedIndex& d = ctx->I->d;
     const int n_files = n_files_used(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
     Counters* dc = ctx->d_ctr.p;
     cudaStream_t st = ctx->stream;
     int sp = ctx->span_begin(ST_SCORE);
     ScoreView sv;
-    sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->d_genome_row0.p; sv.genome_seq_off = ctx->d_genome_seq_off.p;
-    sv.seq_row0 = ctx->d_seq_row0.p; sv.ref_code = ctx->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
+    sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->I->d_genome_row0.p; sv.genome_seq_off = ctx->I->d_genome_seq_off.p;
+    sv.seq_row0 = ctx->I->d_seq_row0.p; sv.ref_code = ctx->I->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
     const u32 row_blocks = (d.max_genome_rows + 255) / 256;
     NoiseView nv;
-    nv.ctr = dc; nv.genome_row0 = ctx->d_genome_row0.p; nv.genome_seq_off = ctx->d_genome_seq_off.p; nv.seq_row0 = ctx->d_seq_row0.p;
+    nv.ctr = dc; nv.genome_row0 = ctx->I->d_genome_row0.p; nv.genome_seq_off = ctx->I->d_genome_seq_off.p; nv.seq_row0 = ctx->I->d_seq_row0.p;
     nv.pile = ctx->d_pile.p; nv.pile_stride = pile_stride;
     nv.maf = ctx->d_nz_maf.p; nv.snap_s = ctx->d_nz_s.p; nv.snap_s2 = ctx->d_nz_s2.p; nv.snap_tab = ctx->d_nz_tab.p;
     nv.warm = ctx->d_nz_warm.p; nv.flag = ctx->d_nz_flag.p; nv.stats = ctx->noise_debug ? ctx->d_nz_stats.p : nullptr;
     nv.noise_max = ctx->d_noise.p;
-    const u32 nseq = ctx->max_seqs_per_genome;
-    if (ctx->noise_debug) cudaMemsetAsync(ctx->d_nz_stats.p, 0, 32, st);
+    const u32 nseq = ctx->I->max_seqs_per_genome;
+    if (ctx->noise_debug) cudaMemsetAsync(ctx->d_nz_stats.p, 0, 64, st);
     k_noise_fracs<<<dim3((d.max_genome_rows + BK_NZ_PAD + 255) / 256, nseq), 256, 0, st>>>(nv);
     k_noise_seq<<<dim3(2 + (ctx->nz_max_chunks + 7) / 8, nseq), BK_NZ_SEQ_THREADS, BK_NZ_SEQ_SMEM, st>>>(nv);
     k_noise_fix<<<dim3(1, nseq), 256, 0, st>>>(nv);
     k_noise_tau<<<dim3((d.max_genome_rows + BK_NOISE_HALF + 255) / 256, nseq), 256, 0, st>>>(nv);
     if (ctx->noise_debug) {        // BK_NOISE_DEBUG=1
-        u32 h[8];
-        cudaMemcpyAsync(h, ctx->d_nz_stats.p, 32, cudaMemcpyDeviceToHost, st);
+        u32 h[16];
+        cudaMemcpyAsync(h, ctx->d_nz_stats.p, 64, cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u; kcycles: s %u, s2 %u, slowest table lane %u\n",
                 h[0], h[1], h[2], h[3], h[4], h[5] / 64, h[6] / 64, h[7] / 64);
@@ -755,7 +787,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     }
     r.n_variants = c.n_var; r.num_major_variants = c.n_major; r.num_minor_variants = c.n_minor;
     u64 total_positions = 0;
-    for (const HostSeq& q : ctx->ix.genomes[c.best].seqs) total_positions += q.bases.size();
+    for (const HostSeq& q : ctx->I->ix.genomes[c.best].seqs) total_positions += q.bases.size();
     r.breadth_coverage = (double)c.pos_covered / (double)total_positions;      // src/call.rs:1144-1145
     r.depth_coverage = (double)c.total_cov / (double)c.pos_covered;
     u64 uc = 0, pv = 0;
@@ -865,7 +897,7 @@ int bk_shard_begin(bk_ctx* ctx, int file_slot, void** d_ref_counts, uint64_t* n_
     ctx->launches += 2;
     BK_CUDA(cudaGetLastError());
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    *d_ref_counts = f.idcnt.p; *n_ref_counts = ctx->d.id_kmer.size();
+    *d_ref_counts = f.idcnt.p; *n_ref_counts = ctx->I->d.id_kmer.size();
     *d_novel_kmers = f.xk.p; *d_novel_counts = f.xc.p;
     return BK_OK;
 }
@@ -911,7 +943,7 @@ int bk_shard_map_stats(bk_ctx* ctx, void** d_tallies0, void** d_tallies1, uint64
     }
     if (d_tallies0) *d_tallies0 = ctx->file[0].gstats.p;
     if (d_tallies1) *d_tallies1 = n_files > 1 ? ctx->file[1].gstats.p : nullptr;
-    if (n_tallies) *n_tallies = (u64)ctx->d.n_genomes * 4;
+    if (n_tallies) *n_tallies = (u64)ctx->I->d.n_genomes * 4;
     return BK_OK;
 }
 
@@ -922,7 +954,7 @@ int bk_shard_select_pileup(bk_ctx* ctx, const bk_kmc_stats* global_kmc, void** d
     if ((rc = stage_select_pileup(ctx))) return rc;
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (d_pile) *d_pile = ctx->d_pile.p;
-    if (n_per_array) *n_per_array = (u64)ctx->d.max_genome_rows * 4;
+    if (n_per_array) *n_per_array = (u64)ctx->I->d.max_genome_rows * 4;
     return BK_OK;
 }
 
@@ -947,7 +979,7 @@ int bk_sample_variants(bk_ctx* ctx, bk_variant* out, uint64_t cap) {
 
 int bk_sample_genome_stats(bk_ctx* ctx, int slot, bk_genome_stats* out) {
     if (!ctx || !ctx->finished || slot < 0 || slot > 1 || !out) return BK_ERR_ARG;
-    if (ctx->gstats[slot].size() != ctx->d.n_genomes) return ctx->fail(BK_ERR_ARG, "no stats for file slot %d", slot);
+    if (ctx->gstats[slot].size() != ctx->I->d.n_genomes) return ctx->fail(BK_ERR_ARG, "no stats for file slot %d", slot);
     memcpy(out, ctx->gstats[slot].data(), ctx->gstats[slot].size() * sizeof(bk_genome_stats));
     return BK_OK;
 }
@@ -957,10 +989,10 @@ int bk_sample_pileup(bk_ctx* ctx, int arr, uint64_t* out, uint64_t cap_rows) {
     const int best = ctx->result.best_genome;
     if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
     cudaSetDevice(ctx->device);
-    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    const u32 rows = ctx->I->d.genome_row0[best + 1] - ctx->I->d.genome_row0[best];
     if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_pileup: buffer too small (%u rows)", rows);
     std::vector<u32> tmp((size_t)rows * 4);
-    BK_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_pile.p + (size_t)arr * ctx->d.max_genome_rows * 4, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_pile.p + (size_t)arr * ctx->I->d.max_genome_rows * 4, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < tmp.size(); i++) out[i] = tmp[i];
     return BK_OK;
@@ -971,7 +1003,7 @@ int bk_sample_noise_max(bk_ctx* ctx, double* out, uint64_t cap_rows) {
     const int best = ctx->result.best_genome;
     if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
     cudaSetDevice(ctx->device);
-    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    const u32 rows = ctx->I->d.genome_row0[best + 1] - ctx->I->d.genome_row0[best];
     if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_noise_max: buffer too small");
     BK_CUDA(cudaMemcpyAsync(out, ctx->d_noise.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
     BK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1013,7 +1045,7 @@ int bk_write_vcf(bk_ctx* ctx, const char* reads_path, const char* out_path) {
     if (!ctx || !ctx->finished || !reads_path || !out_path) return BK_ERR_ARG;
     const int best = ctx->result.best_genome;
     if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
-    const HostGenome& g = ctx->ix.genomes[best];
+    const HostGenome& g = ctx->I->ix.genomes[best];
     std::string o;
     o += "##fileformat=VCFv4.5\n##source=bronko-v0.1.0\n";
     o += std::string("##reference=file://") + reads_path + "\n";
@@ -1037,8 +1069,8 @@ int bk_write_pileup(bk_ctx* ctx, const char* out_path) {
     if (!ctx || !ctx->finished || !out_path) return BK_ERR_ARG;
     const int best = ctx->result.best_genome;
     if (best < 0) return ctx->fail(BK_ERR_NO_GENOME, "no genome selected");
-    const HostGenome& g = ctx->ix.genomes[best];
-    const u32 rows = ctx->d.genome_row0[best + 1] - ctx->d.genome_row0[best];
+    const HostGenome& g = ctx->I->ix.genomes[best];
+    const u32 rows = ctx->I->d.genome_row0[best + 1] - ctx->I->d.genome_row0[best];
     std::vector<u64> fw((size_t)rows * 4), rv((size_t)rows * 4);
     int rc;
     if ((rc = bk_sample_pileup(ctx, 0, fw.data(), rows)) || (rc = bk_sample_pileup(ctx, 1, rv.data(), rows))) return rc;

@@ -133,6 +133,9 @@ int bk_index_load_file(bk_ctx* ctx, const char* bkdb_path);
 int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const* fasta_paths);
 /* save_index (src/build.rs:122-143); keys are written in ascending order. */
 int bk_index_save(bk_ctx* ctx, const char* bkdb_path);
+/* Use the index already loaded into `owner` (same device) without copying it: the contexts of one GPU — one per
+ * sample in flight — read one set of tables.  The reference holds one index per process (src/call.rs:170-200). */
+int bk_index_share(bk_ctx* ctx, bk_ctx* owner);
 int bk_index_info(bk_ctx* ctx, uint32_t* k, uint64_t* n_keys, uint64_t* n_entries, uint32_t* n_genomes);
 const char* bk_genome_name(bk_ctx* ctx, uint32_t genome);
 uint32_t bk_genome_n_seqs(bk_ctx* ctx, uint32_t genome);

@@ -172,6 +172,29 @@ def test_id_keyed_map_tables(sars_paths, oracle, monkeypatch, warp_map):
         c.close()
 
 
+def test_shared_index_between_contexts(ctx_sars):
+    """bk_index_share: a second context on the same GPU reads the first one's tables; results identical, and the
+    index outlives the context that loaded it."""
+    import bronko_b200
+    c0, oi = ctx_sars
+    c1 = bronko_b200.Bronko(0)
+    try:
+        c1.share_index(c0)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[3]), 300, sim.SEED0 + 45)
+        run_both(c1, oi, [(r1, o1), (r2, o2)])
+        c2 = bronko_b200.Bronko(0)
+        c2.build_index(21, [sim.genome_path(sim.HPV16)])
+        c3 = bronko_b200.Bronko(0)
+        c3.share_index(c2)
+        c2.close()                                   # c3 keeps the HPV16 index alive
+        import oracle.oracle as O
+        h1, ho1, h2, ho2, _ = sim.simulate_pairs(sim.load_genome(sim.HPV16), 200, sim.SEED0 + 46)
+        run_both(c3, O.Index.build(21, [sim.genome_path(sim.HPV16)]), [(h1, ho1), (h2, ho2)])
+        c3.close()
+    finally:
+        c1.close()
+
+
 def test_two_pass_map_on_small_db(sars_paths, oracle, monkeypatch):
     """BK_NO_FUSED_MAP: tallies, selection, then a second pass for the selected genome's pileup (what databases of
     more than four genomes and the read-sharded mode use) instead of the one-pass map of small databases."""
