@@ -284,10 +284,18 @@ def main():
     scan_ms = alone["scan_ms"] / scan_launches
     alg_bytes = (n_bases + 4 * (n_reads + 2)) / 2.0            # per launch: one file's bases + u32 offsets
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch at this workload, from the committed
+    # `ncu --set full` capture (profiles/r01_ncu_full_summary.csv: 158.04 MB + 5.32 MB); other depths: not captured
+    traffic = 163.35e6 if args.depth == 10000 else None
+    alone_total = max(alone.get("total_ms", 0.0), 1e-9)
     roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": scan_ms,
-                "timed": "CUDA events around each k_scan launch, one sample in flight (kernel timed alone), %d samples" % n_alone}
+                "share_of_step": alone["scan_ms"] / alone_total,
+                "timed": "CUDA events around each k_scan launch, one sample in flight (kernel timed alone), %d samples" % n_alone,
+                "note": "k_scan is the kernel that streams the reads (the HBM-bound stage of SURVEY.md 8d); the other "
+                        "stages are latency-bound random access (leftover / map) or a sequential FP64 chain (noise): "
+                        "see stage_ms_single_sample and profiles/r01_kernel_share.txt"}
     stages = {k_: (v_ / args.steps) for k_, v_ in stage_acc.items()}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample ----------
@@ -321,7 +329,11 @@ def main():
             "latency_ms_single_sample": latency_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(stage_acc["launches"]),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "roofline": roofline,
+            "roofline_path": {"alg_bytes_per_step": 1.03 * n_bases, "achieved_gbs": 1.03 * n_bases * world / (ms_step * 1e-3) / 1e9,
+                              "frac_of_hbm": 1.03 * n_bases / (ms_step * 1e-3) / 1e9 / peak,
+                              "note": "whole path, SURVEY.md 8d: 1.03 algorithmic bytes per read base"},
+            "cpu_baseline": cpu, "clocks": clk,
             "stage_ms_per_step_in_flight": stages, "stage_ms_single_sample": alone,
             "result_check": {"best_genome": int(res.best_genome), "n_variants": int(len(res.variants))},
         }

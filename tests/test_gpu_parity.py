@@ -172,6 +172,58 @@ def test_id_keyed_map_tables(sars_paths, oracle, monkeypatch, warp_map):
         c.close()
 
 
+def _segmented_db(tmp_path, n_genomes=7, seed=5):
+    """Synthetic db of n_genomes related 'segmented' genomes (1-3 contigs of 1.2-3 kb each, 2 % apart), with
+    lower-case stretches and a few non-ACGT reference bases (encoded as A: Q11).  Returns (paths, contigs per genome)."""
+    rng = np.random.default_rng(seed)
+    base = [rng.integers(0, 4, size=int(n)).astype(np.uint8) for n in (3000, 1800, 1200)]
+    paths, genomes = [], []
+    for g in range(n_genomes):
+        contigs = [sim.mutate_genome(b, 0.02, 1000 + 17 * g + i) for i, b in enumerate(base[:1 + g % 3])]
+        p = tmp_path / ("strain%d.fa" % g)
+        with open(p, "w") as f:
+            for i, cod in enumerate(contigs):
+                seq = "".join("ACGT"[x] for x in cod)
+                if g % 2:
+                    seq = seq[:200] + seq[200:260].lower() + seq[260:]          # soft-masked stretch
+                if g == 3 and i == 0:
+                    seq = seq[:500] + "N" + seq[501:900] + "R" + seq[901:]      # non-ACGT reference bases
+                f.write(">seg%d strain%d\n" % (i + 1, g))
+                for j in range(0, len(seq), 70):
+                    f.write(seq[j:j + 70] + "\n")
+        paths.append(str(p))
+        genomes.append(contigs)
+    return paths, genomes
+
+
+@pytest.mark.parametrize("source", [2, 3, 5])
+def test_many_genomes_multi_contig_db(tmp_path, oracle, source):
+    """More than four genomes (warp-per-k-mer map, two passes) with several contigs each: per-contig noise,
+    contig lookup in the variant kernel, selection among close strains, REF of non-ACGT bases."""
+    import bronko_b200
+    paths, genomes = _segmented_db(tmp_path)
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, paths)
+        oi = oracle.Index.build(21, paths)
+        parts = []
+        for i, cod in enumerate(genomes[source]):
+            ascii_ = np.frombuffer("".join("ACGT"[x] for x in cod).encode(), dtype=np.uint8)
+            parts.append(sim.simulate_pairs(ascii_, 400, sim.SEED0 + 70 + 3 * source + i, n_snv=3, n_isnv=5))
+        def cat(idx_b, idx_o):
+            bases = np.concatenate([p[idx_b] for p in parts])
+            offs, shift = [np.zeros(1, np.uint32)], 0
+            for p in parts:
+                offs.append(p[idx_o][1:] + np.uint32(shift))
+                shift += int(p[idx_o][-1])
+            return bases, np.concatenate(offs)
+        files = [cat(0, 1), cat(2, 3)]
+        g, osample = run_both(c, oi, files, bronko_b200.CallArgs(min_depth=50))
+        assert g.best_genome == source
+    finally:
+        c.close()
+
+
 def test_shared_index_between_contexts(ctx_sars):
     """bk_index_share: a second context on the same GPU reads the first one's tables; results identical, and the
     index outlives the context that loaded it."""
