@@ -164,7 +164,9 @@ struct CountView {
     const ExactSlotD* exact; u32 exact_shift, exact_mask;
     u32* diff;                       // n_raw + 2
     GenSlot* gen; u32 gen_shift, gen_mask;
-    u32* gen_full;                   // set to 1 if the novel table ran out of slots
+    u32* gen_full;                   // set to 1 if the novel table / list ran out of room
+    u64* nov; u32 nov_cap; u32* nov_n;   // list mode (nov != null): novel k-mer occurrences are appended here instead of
+                                         // being counted in `gen`; bk_bins.cuh counts the list afterwards
     uint2* desc; u32 desc_cap; u32* n_desc;
 };
 
@@ -201,6 +203,11 @@ BK_HD u32 count_one(const CountView& v, u64 kmer) {
     if (exact_lookup(v, kmer, &gidx, &oseq)) {
         add_u32(v.diff + gidx, 1u);
         add_u32(v.diff + gidx + 1, 0xFFFFFFFFu);
+        return 0;
+    }
+    if (v.nov) {                                         // list mode, rare paths only (one atomic per k-mer)
+        const u32 pos = fetch_add_u32(v.nov_n, 1u);
+        if (pos < v.nov_cap) v.nov[pos] = kmer; else *v.gen_full = 1;
         return 0;
     }
     u32 h = hash_slot(kmer, v.gen_shift);

@@ -55,6 +55,12 @@ struct FileState {
     DevBuf<u32> gstats;
     u32 gen_log2 = 0;
     DevBuf<u64> xk; DevBuf<u32> xc;          // sharded mode: novel (k-mer, count) pairs grouped by owner rank
+    DevBuf<u64> nov, nov_sorted;             // list mode (bk_bins.cuh): novel k-mer occurrences, then grouped by bin
+    DevBuf<u32> bin_cnt;
+    bool list_mode = false;                  // novel k-mers through the list + bins instead of the gen table
+    u64 nov_ub = 0;                          // upper bound of list entries the pushes so far were given room for
+    u64 nov_limit = 0;                       // entries the kernels may use (the allocation can be larger: it is reused)
+    u32 bin_log2p = 8;
     bool used = false, folded = false, finalized = false;
     u64 total_reads = 0, total_bases = 0;
 };
@@ -97,6 +103,7 @@ struct bk_ctx {
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;              // pinned
     DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
+    DevBuf<u64> d_nov_sorted;               // list mode: one file's novel k-mers grouped by bin (files are finalized one after the other)
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
     DevBuf<u32> d_pile_all;                 // one such block per genome (databases of at most four genomes: one-pass map)
     DevBuf<double> d_noise;                 // Noise.max per row
@@ -114,6 +121,7 @@ struct bk_ctx {
     bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
     bool no_fused_map = false;              // tests: BK_NO_FUSED_MAP keeps the two-pass map on small databases
+    bool novel_table = false;               // tests: BK_NOVEL_TABLE counts novel k-mers in the global hash table (what the sharded mode uses)
 
     // results
     bk_sample_result result;
@@ -193,7 +201,10 @@ int bk_create(bk_ctx** out, int device) {
     if (ok) ok = cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_map<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_map<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_noise_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NZ_SEQ_SMEM) == cudaSuccess;
+                 cudaFuncSetAttribute(k_noise_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NZ_SEQ_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
     memset(&ctx->result, 0, sizeof ctx->result);
@@ -201,6 +212,7 @@ int bk_create(bk_ctx** out, int device) {
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
     ctx->no_fused_map = getenv("BK_NO_FUSED_MAP") != nullptr;
+    ctx->novel_table = getenv("BK_NOVEL_TABLE") != nullptr;
     *out = ctx;
     return BK_OK;
 }
@@ -210,9 +222,9 @@ void bk_destroy(bk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->I.reset();                         // the last context sharing an index frees its device copies
-    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); }
+    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); f.nov.release(); f.nov_sorted.release(); f.bin_cnt.release(); }
     ctx->d_part.release();
-    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
+    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_nov_sorted.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();
     ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
     ctx->d_nz_flag.release(); ctx->d_nz_stats.release();
@@ -311,7 +323,7 @@ static int size_for_index(bk_ctx* ctx) {
     }
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
-    BK_CUDA(ctx->d_bsum.reserve(((size_t)d.n_raw + 2 + BK_PS_BLOCK - 1) / BK_PS_BLOCK + 1));
+    BK_CUDA(ctx->d_bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count) / BK_PS_BLOCK + 2));
     for (FileState& f : ctx->file) {
         BK_CUDA(f.diff.reserve((size_t)d.n_raw + 2));
         BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
@@ -425,7 +437,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     cudaSetDevice(ctx->device);
     ctx->params = *params;
     ctx->in_sample = true; ctx->finished = false;
-    for (FileState& f : ctx->file) { f.used = false; f.folded = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; }
+    for (FileState& f : ctx->file) { f.used = false; f.folded = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; f.nov_ub = 0; }
     ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0;
     ctx->variants.clear();
     memset(&ctx->result, 0, sizeof ctx->result);
@@ -444,6 +456,8 @@ static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     v.diff = f.diff.p;
     v.gen = f.gen.p; v.gen_shift = 64 - f.gen_log2; v.gen_mask = (u32)((1ull << f.gen_log2) - 1);
     v.gen_full = &ctx->d_ctr.p->gen_full;
+    v.nov = f.list_mode ? f.nov.p : nullptr; v.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
+    v.nov_n = &ctx->d_ctr.p->f[&f - ctx->file].nov_n;
     v.desc = ctx->d_desc.p; v.desc_cap = (u32)std::min<size_t>(ctx->d_desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->n_desc;
     return v;
 }
@@ -452,19 +466,45 @@ static CountView make_count_view(bk_ctx* ctx, FileState& f) {
 static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
     FileState& f = ctx->file[slot];
     if (f.used) return BK_OK;
-    u32 lg = ctx->params.table_log2;
-    if (lg == 0) {            // auto: ~1 slot per 32 read bases of this first push, clamped to [2^22, 2^27]
-        lg = 22;
-        while (lg < 27 && (1ull << lg) < bases_hint / 32) lg++;
-    }
-    f.gen_log2 = lg;
-    BK_CUDA(f.gen.reserve(1ull << lg));
+    f.list_mode = ctx->shard_n == 1 && !ctx->novel_table;
     BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->I->d.n_raw + 2) * 4, ctx->stream));
     BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->I->d.id_kmer.size(), 1) * 4, ctx->stream));
-    k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
-    ctx->launches++;
-    BK_CUDA(cudaGetLastError());
+    if (!f.list_mode) {
+        u32 lg = ctx->params.table_log2;
+        if (lg == 0) {            // auto: ~1 slot per 32 read bases of this first push, clamped to [2^22, 2^27]
+            lg = 22;
+            while (lg < 27 && (1ull << lg) < bases_hint / 32) lg++;
+        }
+        f.gen_log2 = lg;
+        BK_CUDA(f.gen.reserve(1ull << lg));
+        k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
+        ctx->launches++;
+        BK_CUDA(cudaGetLastError());
+    }
     f.used = true;
+    return BK_OK;
+}
+
+// list mode: room for the novel k-mer occurrences of a push of n_bases bases (they cannot outnumber the bases);
+// what earlier pushes of the file wrote is kept.  bk_params.table_log2 != 0 fixes the capacity instead.
+static int novel_room(bk_ctx* ctx, int slot, u64 n_bases) {
+    FileState& f = ctx->file[slot];
+    if (!f.list_mode) return BK_OK;
+    u64 need;
+    const u64 before = f.nov_ub;
+    if (ctx->params.table_log2) { need = 1ull << ctx->params.table_log2; f.nov_ub = need; }
+    else { f.nov_ub += n_bases + 64; need = f.nov_ub; }
+    need = std::min<u64>(need, 0xFFFFFFF0ull);
+    f.nov_limit = need;
+    if (need <= f.nov.cap) return BK_OK;
+    if (before != 0 && f.nov.p) {                      // not the first push of the file: keep the entries
+        DevBuf<u64> bigger;
+        BK_CUDA(bigger.reserve(need + need / 2));
+        BK_CUDA(cudaMemcpyAsync(bigger.p, f.nov.p, f.nov.cap * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));
+        f.nov.release();
+        f.nov = bigger;
+    } else BK_CUDA(f.nov.reserve(need));
     return BK_OK;
 }
 
@@ -488,7 +528,8 @@ static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_o
     ctx->launches++; ctx->scan_launches++;
     BK_CUDA(cudaGetLastError());
     sp = ctx->span_begin(ST_LEFTOVER);
-    k_leftover<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    if (f.list_mode) k_leftover<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    else k_leftover<0><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
@@ -513,6 +554,7 @@ int bk_reads_push_device(bk_ctx* ctx, int slot, const uint8_t* d_bases, const ui
     if (((uintptr_t)d_bases & 15) != 0) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: bases must be 16-byte aligned");
     if (n_reads >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFF0ull) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: push at most 2^32-16 bases / reads at a time");
     if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
+    if ((rc = novel_room(ctx, slot, n_bases))) return rc;
     ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
     return launch_count(ctx, slot, d_bases, d_off, 0, 0, (u32)n_reads, max_read_len);
 }
@@ -525,6 +567,7 @@ int bk_reads_push(bk_ctx* ctx, int slot, const uint8_t* bases, const uint32_t* r
     if (n_reads >= 0xFFFFFFFFull) return ctx->fail(BK_ERR_ARG, "bk_reads_push: too many reads in one push");
     const u64 n_bases = read_off[n_reads];
     if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
+    if ((rc = novel_room(ctx, slot, n_bases))) return rc;
     ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
     // offsets once, bases in chunks through two staging buffers so H2D overlaps the kernels
     BK_CUDA(ctx->d_stage_off.reserve(n_reads + 1));
@@ -599,17 +642,44 @@ static int stage_compact(bk_ctx* ctx, int slot) {
     if (f.finalized) return BK_OK;
     const DerivedIndex& d = ctx->I->d;
     const u32 n_ids = (u32)d.id_kmer.size();
-    const size_t out_cap = (size_t)n_ids + (1ull << f.gen_log2);
+    // the novel part of the list: a kept k-mer stands for >= ci occurrences (list mode) / occupies a table slot
+    const size_t novel_cap = f.list_mode ? std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)) / std::max<u32>(ctx->params.min_kmers, 1) + 1
+                                         : (size_t)(1ull << f.gen_log2);
+    const size_t out_cap = (size_t)n_ids + novel_cap;
     BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
     int sp = ctx->span_begin(ST_FINALIZE);
     CompactArgs a;
     a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n;
     a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
     a.fc = &ctx->d_ctr.p->f[slot];
-    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
-    k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
+    if (!f.list_mode) {
+        k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
+        k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
+        ctx->launches += 2;
+    } else {
+        // bins sized for the room the pushes were given (≈ 5 % of it is used at 0.2 % error: a few hundred k-mers per bin)
+        BinView b;
+        u32 lp = 6;                          // a round of a bin is sized for 1/32 of the room: 3 % of the bases novel
+        while (lp < 14 && ((u64)BK_BIN_ROUND << lp) < f.nov_ub / 32) lp++;
+        f.bin_log2p = lp;
+        const u32 P = 1u << lp, G = (u32)ctx->sm_count, PG = P * G;
+        const u32 nb = (PG + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
+        BK_CUDA(f.bin_cnt.reserve((size_t)PG + 1));
+        BK_CUDA(ctx->d_nov_sorted.reserve(std::max<size_t>(f.nov.cap, 1)));
+        b.nov = f.nov.p; b.nov_n = &ctx->d_ctr.p->f[slot].nov_n; b.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
+        b.sorted = ctx->d_nov_sorted.p; b.cnt = f.bin_cnt.p; b.log2p = lp; b.G = G;
+        b.exact = ctx->I->d_exact.p; b.exact_shift = 64 - d.exact_log2; b.exact_mask = (1u << d.exact_log2) - 1;
+        b.slot2id = ctx->I->d_slot2id.p; b.idcnt = f.idcnt.p;
+        k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
+        k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
+        k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
+        k_excl_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
+        k_bin_scatter<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
+        k_bin_count<<<P, 256, BK_BIN_SMEM, ctx->stream>>>(b, a, &ctx->d_ctr.p->gen_full);
+        k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);   // after the bins: they add to idcnt
+        ctx->launches += 7;
+    }
     ctx->span_end(sp);
-    ctx->launches += 2;
     BK_CUDA(cudaGetLastError());
     f.finalized = true;
     return BK_OK;
@@ -759,7 +829,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     BK_CUDA(cudaStreamSynchronize(st));
     const Counters& c = *ctx->h_ctr;
     ctx->finished = true;
-    if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "novel k-mer table (2^%u slots) is full; set bk_params.table_log2 higher", ctx->file[0].gen_log2);
+    if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "no room left for novel k-mers (table / list / bin table); set bk_params.table_log2 higher");
     if (c.var_overflow) return ctx->fail(BK_ERR_OVERFLOW, "variant buffer overflow");
     for (int f = 0; f < n_files; f++) {
         if ((size_t)c.f[f].n_counted > ctx->file[f].ckmers.cap) return ctx->fail(BK_ERR_OVERFLOW, "counted k-mer list overflow");

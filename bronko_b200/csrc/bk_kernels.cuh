@@ -15,7 +15,7 @@ namespace bk {
 struct BucketSlotD { u64 key; u32 off; u32 len; };
 struct BucketEntryD { u32 row; unsigned short file_id; u8 idx; u8 canonical; };
 
-struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 pad; u64 total_kmers; };
+struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 nov_n; u64 total_kmers; };
 struct Counters {
     u32 n_desc; u32 gen_full; u32 var_overflow; u32 pad0;
     FileCounters f[2];
@@ -157,7 +157,12 @@ k_scan(CountView v, const u8* __restrict__ bases, const u32* __restrict__ off, u
 // k-mer, non-ACGT bytes reset the roll: KMC splits reads there) and counts each with count_one().
 // Stretches longer than BK_LEFT_LONG k-mers (foreign reads, wrong diagonals) are handled by the whole
 // warp afterwards, lane j taking k-mers j, j+32, ...
+// LIST: the k-mers are not counted here but written to the list v.nov (one slot per k-mer of the stretch, BK_HOLE
+// where the k-mer contained a non-ACGT byte); a warp reserves the slots of its 32 stretches with one atomic, and the
+// kernel touches no table at all.  bk_bins.cuh counts the list.
 #define BK_LEFT_LONG 96
+#define BK_HOLE (~0ull)
+template <int LIST>
 __global__ void __launch_bounds__(256)
 k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
     const u32 n = min(*v.n_desc, v.desc_cap);
@@ -173,7 +178,18 @@ k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
         uint2 d = make_uint2(0, 0);
         if (i < n) d = v.desc[i];
         const bool is_long = d.y > BK_LEFT_LONG;
-        if (d.y != 0 && !is_long) {
+        const bool mine = d.y != 0 && !is_long;
+        u32 base = 0;
+        if (LIST) {                                          // slots of this warp's stretches: one atomic
+            const u32 want = mine ? d.y : 0u;
+            u32 incl = want;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += t; }
+            const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (lane == 31 && total) base = atomicAdd(v.nov_n, total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - want;
+        }
+        if (mine) {
             const u32 n_bytes = d.y + k - 1;
             u64 km = 0; u32 run = 0;
             u32 word = 0;
@@ -186,7 +202,13 @@ k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
                 const u32 code = ((up >> 1) ^ (up >> 2)) & 3u;
                 km = ((km << 2) | code) & kmask;
                 run = ok ? run + 1 : 0;
-                if (run >= k) created += count_one(v, km);
+                if (LIST) {
+                    if (b + 1 >= k) {                        // k-mer number b + 1 - k of the stretch ends at this byte
+                        const u32 pos = base + (b + 1 - k);                // reference k-mers among them are
+                        if (pos < v.nov_cap) v.nov[pos] = run >= k ? km : BK_HOLE;   // recognised when the bins are counted
+                        else *v.gen_full = 1;
+                    }
+                } else if (run >= k) created += count_one(v, km);
             }
         }
         u32 lm = __ballot_sync(0xFFFFFFFFu, is_long);
@@ -741,3 +763,5 @@ k_call(ScoreView sv, CallParams p, const double* __restrict__ noise_max, bk_vari
 }
 
 }  // namespace bk
+
+#include "bk_bins.cuh"

@@ -306,9 +306,8 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
     o[0] = m3[0]; o[1] = m3[1]; o[2] = m3[2];
 }
 
-// ---- chain block: 512 threads, half an iteration (three operations) per thread and round ----------------------
-#define BK_NZ_SEQ_THREADS 512
-#define BK_NZ_SEQ_WARPS (BK_NZ_SEQ_THREADS / 32)
+// ---- chain block: 256 threads, one iteration per thread and round ---------------------------------------------
+#define BK_NZ_SEQ_THREADS 256
 #define BK_NZ_CHAIN_SMEM ((BK_NZ_TILE + BK_NOISE_WINDOW) * 3 * 8)
 #define BK_NZ_TABLE_POS (BK_NOISE_WINDOW + BK_NZ_WARM + BK_NZ_CHUNK)          // positions a chunk lane touches
 #define BK_NZ_TABLE_WARPS 8                                                   // chunk lanes per table block
@@ -317,8 +316,8 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
 
 template <bool SQUARE>
 __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* mt) {
-    __shared__ i64 wt0[2][BK_NZ_SEQ_WARPS], wt1[2][BK_NZ_SEQ_WARPS];
-    __shared__ u32 wbad[2][BK_NZ_SEQ_WARPS];
+    __shared__ i64 wt0[2][8], wt1[2][8];
+    __shared__ u32 wbad[2][8];
     __shared__ double sstate[2];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* mafp = nv.maf + (size_t)(sq.mbase - BK_NZ_PAD_LO) * 3;       // position -100
@@ -330,7 +329,6 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     u32 round = 0, serial_left = 0, width = BK_NZ_ROUND;                        // width: iterations tried per round
     u32 st_rounds = 0, st_stops = 0, st_serial = 0;
     const long long t_begin = clock64();
-    const u32 my_it = tid >> 1, my_q0 = (tid & 1) * 3;                          // this thread: operations my_q0 .. my_q0+2 of iteration i0 + my_it
     while (i0 < iters) {
         if (i0 + 1 > tile_hi || (i0 + BK_NZ_ROUND > tile_hi && tile_hi < iters)) {
             __syncthreads();
@@ -361,68 +359,64 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         round++; st_rounds++;
         const NzBinade bin = nz_binade(ef);
         const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
-        const bool active = my_it < n_it;
-        const u32 n_warps_used = (2 * n_it + 31) >> 5;
-        i64 pre0[3], pre1[3];
-        i64 f0 = 0, f1 = 0;                                                      // inclusive scan of the parity maps in the warp
-        u32 bad = 3;
-        if (wid < n_warps_used) {                                                // warps without an operation skip the work
+        const bool active = tid < n_it;
+        i64 pre0[6], pre1[6];
+        i64 x0 = 0, x1 = 0;                                                      // exclusive prefix inside the warp
+        u32 bad = 6;
+        if (wid * 32 < n_it) {                                                   // warps without an iteration skip the work
             i64 run0 = 0, run1 = 0;
 #pragma unroll
-            for (u32 q = 0; q < 3; q++) {
-                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + my_it), my_q0 + q) : 0.0;
+            for (u32 q = 0; q < 6; q++) {
+                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + tid), q) : 0.0;
                 i64 ie, io;
                 const bool ok = nz_incs(bin, x, &ie, &io);
                 run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
                 pre0[q] = run0; pre1[q] = run1;
-                if (!ok && bad == 3) bad = q;
+                if (!ok && bad == 6) bad = q;
             }
-            f0 = run0; f1 = run1;
+            // inclusive scan of the parity maps over the warp
+            i64 f0 = run0, f1 = run1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, f0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, f1, o);
                 if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, f0, f1, &h0, &h1); f0 = h0; f1 = h1; }
             }
             if (lane == 31) { wt0[buf][wid] = f0; wt1[buf][wid] = f1; }
+            x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1); x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);
+            if (lane == 0) { x0 = 0; x1 = 0; }
         } else {
 #pragma unroll
-            for (u32 q = 0; q < 3; q++) { pre0[q] = 0; pre1[q] = 0; }
+            for (u32 q = 0; q < 6; q++) { pre0[q] = 0; pre1[q] = 0; }
             if (lane == 31) { wt0[buf][wid] = 0; wt1[buf][wid] = 0; }
         }
-        i64 x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1), x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);     // exclusive inside the warp
-        if (lane == 0) { x0 = 0; x1 = 0; }
         __syncthreads();
-        // the maps of the warps in front of this one: every warp scans the (at most 16) warp totals itself
-        i64 w0 = 0, w1 = 0;
-        if (lane < BK_NZ_SEQ_WARPS) { w0 = wt0[buf][lane]; w1 = wt1[buf][lane]; }
-#pragma unroll
-        for (int o = 1; o < BK_NZ_SEQ_WARPS; o <<= 1) {
-            const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, w0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, w1, o);
-            if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, w0, w1, &h0, &h1); w0 = h0; w1 = h1; }
-        }
-        const u32 src = wid ? wid - 1 : 0;
-        i64 b0 = __shfl_sync(0xFFFFFFFFu, w0, src), b1 = __shfl_sync(0xFFFFFFFFu, w1, src);        // inclusive up to warp wid-1
-        if (wid == 0) { b0 = 0; b1 = 0; }
-        i64 base = S0 + ((S0 & 1) ? b1 : b0);
+        i64 base = S0;
+        for (u32 w = 0; w < wid; w++) base += (base & 1) ? wt1[buf][w] : wt0[buf][w];
         base += (base & 1) ? x1 : x0;
         const bool odd = (base & 1) != 0;
-        i64 T[3];
+        i64 T[6];
 #pragma unroll
-        for (u32 q = 0; q < 3; q++) {
+        for (u32 q = 0; q < 6; q++) {
             T[q] = base + (odd ? pre1[q] : pre0[q]);
             if (!nz_inside(T[q]) && bad > q) bad = q;
         }
         const u32 total_ops = n_it * 6;
-        u32 mine = (active && bad < 3) ? tid * 3 + bad : total_ops;
+        u32 mine = (active && bad < 6) ? tid * 6 + bad : total_ops;
         mine = __reduce_min_sync(0xFFFFFFFFu, mine);
         if (lane == 0) wbad[buf][wid] = mine;
         __syncthreads();
-        u32 n_ok = lane < BK_NZ_SEQ_WARPS ? wbad[buf][lane] : total_ops;
-        n_ok = __reduce_min_sync(0xFFFFFFFFu, n_ok);
-        if (active && (tid & 1) && tid * 3 + 2 < n_ok) snap[i0 + my_it] = nz_value(ef, T[2]);
+        u32 n_ok = total_ops;
+#pragma unroll
+        for (u32 w = 0; w < 8; w++) n_ok = min(n_ok, wbad[buf][w]);
+        if (active && tid * 6 + 5 < n_ok) snap[i0 + tid] = nz_value(ef, T[5]);
         if (n_ok > 0) {
-            const u32 owner = (n_ok - 1) / 3, oq = (n_ok - 1) - owner * 3;
-            if (tid == owner) sstate[buf] = nz_value(ef, oq == 0 ? T[0] : (oq == 1 ? T[1] : T[2]));
+            const u32 owner = (n_ok - 1) / 6, oq = (n_ok - 1) - owner * 6;
+            if (tid == owner) {
+                i64 Tl = T[0];
+#pragma unroll
+                for (u32 q = 1; q < 6; q++) if (q == oq) Tl = T[q];
+                sstate[buf] = nz_value(ef, Tl);
+            }
         }
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
@@ -433,7 +427,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
-        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): two warps
+        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): one warp
         if (ib < 4) serial_left = 1;
     }
     if (tid == 0 && nv.stats) {
@@ -442,7 +436,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     }
 }
 
-// grid (2 + ceil(max_chunks / 8), max_seqs), 512 threads, BK_NZ_SEQ_SMEM dynamic shared memory
+// grid (2 + ceil(max_chunks / 8), max_seqs), 256 threads, BK_NZ_SEQ_SMEM dynamic shared memory
 __global__ void __launch_bounds__(BK_NZ_SEQ_THREADS) k_noise_seq(NoiseView nv) {
     extern __shared__ __align__(16) u8 nz_sm[];
     const NzSeq s = nz_seq(nv, blockIdx.y);

@@ -76,6 +76,7 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     v.diff = diff.data();
     v.gen = gen.data(); v.gen_shift = 64 - gen_log2; v.gen_mask = (1u << gen_log2) - 1;
     v.gen_full = &gen_full;
+    v.nov = nullptr; v.nov_cap = 0; v.nov_n = nullptr;
     v.desc = desc.data(); v.desc_cap = desc_cap; v.n_desc = &n_desc;
     auto ld = [&](u32 i) { return words[i]; };
     auto ldr4 = [&](u32 i4) { W4 r; r.x = d.refnib[4 * i4]; r.y = d.refnib[4 * i4 + 1]; r.z = d.refnib[4 * i4 + 2]; r.w = d.refnib[4 * i4 + 3]; return r; };

@@ -247,6 +247,38 @@ def test_shared_index_between_contexts(ctx_sars):
         c1.close()
 
 
+def test_novel_kmers_in_global_table(sars_paths, oracle, monkeypatch):
+    """BK_NOVEL_TABLE: novel k-mers counted in the global open-addressing table (what the read-sharded mode uses)
+    instead of list → bins → shared-memory tables."""
+    import bronko_b200
+    monkeypatch.setenv("BK_NOVEL_TABLE", "1")
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, sars_paths)
+        oi = oracle.Index.build(21, sars_paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[0]), 400, sim.SEED0 + 47)
+        run_both(c, oi, [(r1, o1), (r2, o2)])
+    finally:
+        c.close()
+
+
+def test_heavy_hitter_and_fixed_capacity(ctx_hpv):
+    """One foreign read repeated 3,000 times (a novel k-mer with thousands of copies lands in one bin: equal keys are
+    merged per warp, large bins are walked in rounds) and a caller-fixed list capacity (table_log2)."""
+    import bronko_b200
+    from util import reads_from_strings
+    c, oi = ctx_hpv
+    rng = np.random.default_rng(9)
+    g = "".join(chr(x) for x in sim.load_genome(sim.HPV16))
+    foreign = "".join("ACGT"[i] for i in rng.integers(0, 4, size=150))
+    seqs = [foreign] * 3000 + [g[i:i + 150] for i in range(0, 7000, 7)] * 4
+    run_both(c, oi, [reads_from_strings(seqs)])
+    run_both(c, oi, [reads_from_strings(seqs)], bronko_b200.CallArgs(table_log2=20))
+    with pytest.raises(bronko_b200.BkError) as e:           # 2^12 entries cannot hold 390,000 novel occurrences
+        c.call_sample([reads_from_strings(seqs)], bronko_b200.CallArgs(table_log2=12))
+    assert e.value.code == -5
+
+
 def test_two_pass_map_on_small_db(sars_paths, oracle, monkeypatch):
     """BK_NO_FUSED_MAP: tallies, selection, then a second pass for the selected genome's pileup (what databases of
     more than four genomes and the read-sharded mode use) instead of the one-pass map of small databases."""
