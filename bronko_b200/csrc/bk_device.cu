@@ -73,6 +73,7 @@ struct IndexDev {
     HostIndex ix;
     DerivedIndex d;
     DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
+    DevBuf<BucketSlotD> d_group_slots, d_group_recs;
     DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
@@ -80,7 +81,7 @@ struct IndexDev {
     u32 max_seqs_per_genome = 1;
     ~IndexDev() {
         cudaSetDevice(device);
-        d_bucket_slots.release(); d_bucket_entries.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
+        d_bucket_slots.release(); d_bucket_entries.release(); d_group_slots.release(); d_group_recs.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
         d_exact.release(); d_slot2id.release(); d_id_kmer.release(); d_genome_row0.release(); d_genome_seq_off.release();
         d_seq_row0.release(); d_genome_len.release(); d_ref_code.release();
     }
@@ -121,6 +122,7 @@ struct bk_ctx {
     bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
     bool no_fused_map = false;              // tests: BK_NO_FUSED_MAP keeps the two-pass map on small databases
+    bool no_group_map = false;              // tests: BK_NO_GROUP_MAP probes the per-bucket table instead of the grouped one
     bool novel_table = false;               // tests: BK_NOVEL_TABLE counts novel k-mers in the global hash table (what the sharded mode uses)
 
     // results
@@ -213,6 +215,7 @@ int bk_create(bk_ctx** out, int device) {
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
     ctx->no_fused_map = getenv("BK_NO_FUSED_MAP") != nullptr;
     ctx->novel_table = getenv("BK_NOVEL_TABLE") != nullptr;
+    ctx->no_group_map = getenv("BK_NO_GROUP_MAP") != nullptr;
     *out = ctx;
     return BK_OK;
 }
@@ -281,6 +284,13 @@ static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
     BK_CUDA(ctx->I->d_bucket_entries.reserve(d.bucket_entries.size()));
     if (!d.bucket_entries.empty())
         BK_CUDA(cudaMemcpyAsync(ctx->I->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
+    if (d.rekeyed) {
+        BK_CUDA(ctx->I->d_group_slots.reserve(d.group_slots.size()));
+        BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_slots.p, d.group_slots.data(), d.group_slots.size() * 16, cudaMemcpyHostToDevice, st));
+        BK_CUDA(ctx->I->d_group_recs.reserve(std::max<size_t>(d.group_recs.size(), 1)));
+        if (!d.group_recs.empty())
+            BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_recs.p, d.group_recs.data(), d.group_recs.size() * 16, cudaMemcpyHostToDevice, st));
+    }
     BK_CUDA(ctx->I->d_exact.reserve(d.exact_slots.size()));
     BK_CUDA(cudaMemcpyAsync(ctx->I->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
     BK_CUDA(ctx->I->d_refnib.upload(d.refnib, st));
@@ -696,6 +706,9 @@ static MapView make_map_view(bk_ctx* ctx) {
     m.slots = ctx->I->d_bucket_slots.p; m.shift = 64 - ctx->I->d.bucket_log2; m.mask = (1u << ctx->I->d.bucket_log2) - 1;
     m.entries = ctx->I->d_bucket_entries.p;
     m.n_genomes = ctx->I->d.n_genomes; m.genome_row0 = ctx->I->d_genome_row0.p;
+    const bool grouped = ctx->I->d.rekeyed && !ctx->no_group_map;
+    m.gslots = grouped ? ctx->I->d_group_slots.p : nullptr; m.grecs = ctx->I->d_group_recs.p;
+    m.gshift = 64 - ctx->I->d.group_log2; m.gmask = (1u << ctx->I->d.group_log2) - 1; m.gmid = ctx->I->d.group_mid;
     return m;
 }
 
@@ -720,7 +733,8 @@ static int stage_map_fused(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        if (m.gslots) k_map_grp<2><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        else k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
         ctx->launches++;
     }
     k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
@@ -744,7 +758,8 @@ static int stage_map_stats(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        if (small_db && m.gslots) k_map_grp<0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        else if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
@@ -769,7 +784,8 @@ static int stage_select_pileup(bk_ctx* ctx) {
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        if (small_db && m.gslots) k_map_grp<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        else if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         ctx->launches++;
     }

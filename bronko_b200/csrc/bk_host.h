@@ -73,6 +73,16 @@ struct DerivedIndex {
     bool rekeyed = false;
     u32 bucket_log2 = 0;
     std::vector<BucketSlot> bucket_slots;
+    // Grouped form of the re-keyed table (only when rekeyed).  The 16 buckets of a query k-mer differ in ONE digit
+    // each, so the buckets with index < k/2 all share the k-mer's low half and the others its high half: records are
+    // sorted by (side, shared half) and a query finds all its buckets with two group probes followed by two short
+    // contiguous reads, instead of 16 independent random probes.
+    //   group key = (side << 62) | shared half value;  group_slots: open addressing {key, first record, count};
+    //   group_recs: {(index << 58) | masked canonical k-mer, off, len} (same meaning as bucket_slots), grouped.
+    u32 group_mid = 0;                       // bucket indices < group_mid are on side 0 (shared half = digits mid..k-1)
+    u32 group_log2 = 0;
+    std::vector<BucketSlot> group_slots;     // key == ~0 → empty; off = first record, len = count
+    std::vector<BucketSlot> group_recs;
     std::vector<BucketEntry> bucket_entries;
     // oriented reference store (forward and reverse-complement of every sequence), 2-bit packed,
     // MSB-first, 32 bases per u64; global base index space with REF_PAD_BASES of padding in front

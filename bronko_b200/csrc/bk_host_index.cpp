@@ -352,6 +352,37 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         d.bucket_slots[h] = BucketSlot{slot_key[i], (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
     }
 
+    if (d.rekeyed) {                          // grouped form (bk_host.h)
+        const u32 mid = k / 2;
+        d.group_mid = mid;
+        const u32 lo_bits = 2 * (k - mid);                                   // digits mid..k-1
+        struct Rec { u64 g; BucketSlot r; };
+        std::vector<Rec> recs(ix.keys.size());
+        for (size_t i = 0; i < ix.keys.size(); i++) {
+            const u64 key = slot_key[i];
+            const u32 idx = (u32)(key >> 58);
+            const u64 m = key & ((1ull << 58) - 1);
+            const u64 half = idx < mid ? (m & ((1ull << lo_bits) - 1)) : (m >> lo_bits);
+            recs[i].g = ((u64)(idx < mid ? 0 : 1) << 62) | half;
+            recs[i].r = BucketSlot{key, (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
+        }
+        std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.g != b.g ? a.g < b.g : a.r.key < b.r.key; });
+        size_t n_groups = 0;
+        for (size_t i = 0; i < recs.size(); i++) if (i == 0 || recs[i].g != recs[i - 1].g) n_groups++;
+        d.group_log2 = log2_cap(n_groups);
+        d.group_slots.assign(1ull << d.group_log2, BucketSlot{~0ull, 0, 0});
+        d.group_recs.resize(recs.size());
+        const u64 gmask = (1ull << d.group_log2) - 1;
+        for (size_t i = 0; i < recs.size();) {
+            size_t j = i;
+            while (j < recs.size() && recs[j].g == recs[i].g) { d.group_recs[j] = recs[j].r; j++; }
+            u64 h = hash_slot_host(recs[i].g, 64 - d.group_log2);
+            while (d.group_slots[h].key != ~0ull) h = (h + 1) & gmask;
+            d.group_slots[h] = BucketSlot{recs[i].g, (u32)i, (u32)(j - i)};
+            i = j;
+        }
+    }
+
     // oriented reference store
     struct Occ { u64 kmer; u32 gidx; u32 oseq; };
     std::vector<Occ> occ;

@@ -417,6 +417,8 @@ struct MapView {
     const BucketSlotD* slots; u32 shift, mask;
     const BucketEntryD* entries;
     u32 n_genomes; const u32* genome_row0;
+    // grouped form of the re-keyed table (bk_host.h: group_slots / group_recs); null when not available
+    const BucketSlotD* gslots; u32 gshift, gmask; const BucketSlotD* grecs; u32 gmid;
 };
 
 __device__ __forceinline__ u64 revcomp_dev(u64 v, u32 k) {
@@ -614,6 +616,112 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
                 }
                 num_a += (cur == 0) ? 1 : 0;
                 mask >>= 2; p >>= 2;
+            }
+        }
+        if (MODE != 1) {                                                     // src/call.rs:1389-1419
+            u32 n_perfect = 0;
+#pragma unroll
+            for (u32 g = 0; g < 4; g++) n_perfect += (((hits4 >> (16 * g)) & 0xFFFFu) == nb && nb != 0) ? 1u : 0u;
+#pragma unroll
+            for (u32 g = 0; g < 4; g++) {
+                const u32 h = (u32)((hits4 >> (16 * g)) & 0xFFFFu);
+                const bool perfect = h != 0 && h == nb;
+                const u32 mp = __ballot_sync(0xFFFFFFFFu, perfect);
+                const u32 mv = __ballot_sync(0xFFFFFFFFu, h != 0 && !perfect);
+                const u32 mu_ = __ballot_sync(0xFFFFFFFFu, perfect && n_perfect == 1);
+                if (lane == 0) { acc[g * 3] += __popc(mp); acc[g * 3 + 1] += __popc(mv); acc[g * 3 + 2] += __popc(mu_); }
+            }
+        }
+    }
+    if (MODE != 1 && lane == 0) {
+        for (u32 g = 0; g < m.n_genomes && g < 4; g++) {
+            if (acc[g * 3]) atomicAdd(gstats + g * 4, acc[g * 3]);
+            if (acc[g * 3 + 1]) atomicAdd(gstats + g * 4 + 1, acc[g * 3 + 1]);
+            if (acc[g * 3 + 2]) atomicAdd(gstats + g * 4 + 2, acc[g * 3 + 2]);
+            if (acc[g * 3] | acc[g * 3 + 1]) gstats[g * 4 + 3] = 1;
+        }
+    }
+}
+
+// k_map_grp — the thread-per-k-mer map on the GROUPED table: the buckets of a k-mer with index < k/2 share its low
+// half, the others its high half, so two group probes (issued together) and two short contiguous reads replace the
+// 16 independent random probes of k_map_small (which is bound by the number of outstanding L2 misses an SM can hold).
+// A record matches bucket i iff it equals (i << 58) | (k-mer with digit i zeroed).  Modes as k_map_small.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
+          u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
+    const u32 n = min(*n_ptr, n_cap);
+    const u32 k = m.k;
+    const u32 lane = threadIdx.x & 31;
+    i32 best = -1; u32 g_row0 = 0;
+    if (MODE == 1) {
+        best = *best_ptr;
+        if (best < 0) return;
+        g_row0 = m.genome_row0[best];
+    }
+    const u32 nb = m.b1 - m.b0;
+    const u32 lo_bits = 2 * (k - m.gmid);
+    u32 acc[12];
+#pragma unroll
+    for (u32 i = 0; i < 12; i++) acc[i] = 0;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (n + 31) & ~31u;
+    for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
+        const bool live = t < n && nb != 0;
+        u64 hits4 = 0;
+        if (live) {
+            const u64 fwd = __ldg(kmers + t);
+            const u32 cnt = __ldg(counts + t);
+            const u64 rev = revcomp_dev(fwd, k);
+            const bool rc = !(fwd < rev);
+            const u64 kb = rc ? rev : fwd;
+            // the two groups: probe both tables before looking at either
+            u64 gk[2]; u32 gh[2]; uint4 gs[2];
+            gk[0] = kb & ((1ull << lo_bits) - 1);
+            gk[1] = (1ull << 62) | (kb >> lo_bits);
+#pragma unroll
+            for (u32 sd = 0; sd < 2; sd++) { gh[sd] = hash_slot(gk[sd], m.gshift); gs[sd] = __ldg(reinterpret_cast<const uint4*>(m.gslots) + gh[sd]); }
+#pragma unroll
+            for (u32 sd = 0; sd < 2; sd++) {
+                // side 0 serves bucket indices [b0, min(b1, mid)), side 1 [max(b0, mid), b1)
+                const u32 i_lo = sd == 0 ? m.b0 : max(m.b0, m.gmid), i_hi = sd == 0 ? min(m.b1, m.gmid) : m.b1;
+                if (i_lo >= i_hi) continue;
+                u32 h = gh[sd];
+                uint4 sl = gs[sd];
+                u32 first = 0, count = 0;
+                for (;;) {
+                    const u64 key = ((u64)sl.y << 32) | sl.x;
+                    if (key == gk[sd]) { first = sl.z; count = sl.w; break; }
+                    if (key == BK_EMPTY) break;
+                    h = (h + 1) & m.gmask;
+                    sl = __ldg(reinterpret_cast<const uint4*>(m.gslots) + h);
+                }
+                for (u32 r = 0; r < count; r++) {
+                    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(m.grecs) + first + r);
+                    const u64 rkey = ((u64)rec.y << 32) | rec.x;
+                    const u32 i = (u32)(rkey >> 58);
+                    if (i < i_lo || i >= i_hi) continue;
+                    if ((rkey & ((1ull << 58) - 1)) != (kb & ~(3ull << (2 * (k - 1 - i))))) continue;
+                    const u32 off = rec.z, len = rec.w;
+                    for (u32 j = 0; j < len; j++) {
+                        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+                        const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
+                        if (row == 0xFFFFFFFFu) continue;
+                        if (MODE != 1) hits4 += 1ull << (16 * file_id);       // src/call.rs:1316-1318
+                        if (MODE == 2 || (MODE == 1 && (i32)file_id == best)) {
+                            u32 bit; bool to_fwd;
+                            if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
+                            else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
+                            u32* gp = pile;
+                            u32 r0 = g_row0;
+                            if (MODE == 2) { gp = pile + (size_t)file_id * 4 * pile_stride; r0 = __ldg(m.genome_row0 + file_id); }
+                            const u32 cell = (row + idx - r0) * 4 + bit;
+                            atomicAdd(gp + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
+                            atomicMax(gp + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
+                        }
+                    }
+                }
             }
         }
         if (MODE != 1) {                                                     // src/call.rs:1389-1419

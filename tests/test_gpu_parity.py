@@ -279,6 +279,23 @@ def test_heavy_hitter_and_fixed_capacity(ctx_hpv):
     assert e.value.code == -5
 
 
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_per_bucket_table_map(sars_paths, oracle, monkeypatch, two_pass):
+    """BK_NO_GROUP_MAP: 16 independent probes of the per-bucket table instead of two group probes."""
+    import bronko_b200
+    monkeypatch.setenv("BK_NO_GROUP_MAP", "1")
+    if two_pass:
+        monkeypatch.setenv("BK_NO_FUSED_MAP", "1")
+    c = bronko_b200.Bronko(0)
+    try:
+        c.build_index(21, sars_paths)
+        oi = oracle.Index.build(21, sars_paths)
+        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[3]), 400, sim.SEED0 + 48)
+        run_both(c, oi, [(r1, o1), (r2, o2)])
+    finally:
+        c.close()
+
+
 def test_two_pass_map_on_small_db(sars_paths, oracle, monkeypatch):
     """BK_NO_FUSED_MAP: tallies, selection, then a second pass for the selected genome's pileup (what databases of
     more than four genomes and the read-sharded mode use) instead of the one-pass map of small databases."""
