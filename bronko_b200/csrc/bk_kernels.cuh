@@ -647,6 +647,31 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
 // half, the others its high half, so two group probes (issued together) and two short contiguous reads replace the
 // 16 independent random probes of k_map_small (which is bound by the number of outstanding L2 misses an SM can hold).
 // A record matches bucket i iff it equals (i << 58) | (k-mer with digit i zeroed).  Modes as k_map_small.
+// entries [off, off+len) of one bucket hit: tallies and / or pileup updates (src/call.rs:1309-1385)
+#define BK_MAP_QUEUE 4
+template <int MODE>
+__device__ __forceinline__ void map_walk(const MapView& m, u32 off, u32 len, u64 kb, bool rc, u32 cnt, i32 best, u32 g_row0,
+                                         u32* pile, u32 pile_stride, u64& hits4) {
+    const u32 k = m.k;
+    for (u32 j = 0; j < len; j++) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+        const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
+        if (row == 0xFFFFFFFFu) continue;
+        if (MODE != 1) hits4 += 1ull << (16 * file_id);       // src/call.rs:1316-1318
+        if (MODE == 2 || (MODE == 1 && (i32)file_id == best)) {
+            u32 bit; bool to_fwd;
+            if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
+            else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
+            u32* gp = pile;
+            u32 r0 = g_row0;
+            if (MODE == 2) { gp = pile + (size_t)file_id * 4 * pile_stride; r0 = __ldg(m.genome_row0 + file_id); }
+            const u32 cell = (row + idx - r0) * 4 + bit;
+            atomicAdd(gp + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
+            atomicMax(gp + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
@@ -670,6 +695,8 @@ k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ coun
     for (u32 t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += stride) {
         const bool live = t < n && nb != 0;
         u64 hits4 = 0;
+        u32 qo0 = 0, qo1 = 0, qo2 = 0, qo3 = 0, ql0 = 0, ql1 = 0, ql2 = 0, ql3 = 0, nq = 0;     // hits waiting
+        u64 kb_keep = 0; bool rc_keep = false; u32 cnt_keep = 0;
         if (live) {
             const u64 fwd = __ldg(kmers + t);
             const u32 cnt = __ldg(counts + t);
@@ -703,26 +730,21 @@ k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ coun
                     const u32 i = (u32)(rkey >> 58);
                     if (i < i_lo || i >= i_hi) continue;
                     if ((rkey & ((1ull << 58) - 1)) != (kb & ~(3ull << (2 * (k - 1 - i))))) continue;
-                    const u32 off = rec.z, len = rec.w;
-                    for (u32 j = 0; j < len; j++) {
-                        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
-                        const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
-                        if (row == 0xFFFFFFFFu) continue;
-                        if (MODE != 1) hits4 += 1ull << (16 * file_id);       // src/call.rs:1316-1318
-                        if (MODE == 2 || (MODE == 1 && (i32)file_id == best)) {
-                            u32 bit; bool to_fwd;
-                            if (canon) { bit = (u32)((kb >> (2 * idx)) & 3) ^ 3u; to_fwd = rc; }        // src/call.rs:1330-1357
-                            else { bit = (u32)((kb >> (2 * (k - idx - 1))) & 3); to_fwd = !rc; }     // src/call.rs:1358-1384
-                            u32* gp = pile;
-                            u32 r0 = g_row0;
-                            if (MODE == 2) { gp = pile + (size_t)file_id * 4 * pile_stride; r0 = __ldg(m.genome_row0 + file_id); }
-                            const u32 cell = (row + idx - r0) * 4 + bit;
-                            atomicAdd(gp + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
-                            atomicMax(gp + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
-                        }
-                    }
+                    // a hit: remember it; the entries are walked after the scan, all lanes of the warp together (walked
+                    // lane by lane as the hits turned up, that part ran with 1.7 of 32 lanes active).  Shift-in queue:
+                    // no dynamic indexing; a fifth hit evicts the oldest, which is walked at once.
+                    if (nq == BK_MAP_QUEUE) { map_walk<MODE>(m, qo3, ql3, kb, rc, cnt, best, g_row0, pile, pile_stride, hits4); nq--; }
+                    qo3 = qo2; ql3 = ql2; qo2 = qo1; ql2 = ql1; qo1 = qo0; ql1 = ql0; qo0 = rec.z; ql0 = rec.w; nq++;
                 }
             }
+            kb_keep = kb; rc_keep = rc; cnt_keep = cnt;
+        }
+        // the queued hits, slot by slot, in lockstep
+        const u32 qo[BK_MAP_QUEUE] = {qo0, qo1, qo2, qo3}, ql[BK_MAP_QUEUE] = {ql0, ql1, ql2, ql3};
+#pragma unroll
+        for (u32 q = 0; q < BK_MAP_QUEUE; q++) {
+            if (!__any_sync(0xFFFFFFFFu, q < nq)) break;
+            if (q < nq) map_walk<MODE>(m, qo[q], ql[q], kb_keep, rc_keep, cnt_keep, best, g_row0, pile, pile_stride, hits4);
         }
         if (MODE != 1) {                                                     // src/call.rs:1389-1419
             u32 n_perfect = 0;
