@@ -20,9 +20,9 @@
 namespace bk {
 
 #define BK_BIN_G_THREADS 1024
-#define BK_BIN_SLOTS 4096                    // shared-memory table of k_bin_count: 4096 x (8 + 4) bytes
+#define BK_BIN_SLOTS 4096                    // shared-memory table of k_bin_count: 4096 x (8 + 4 + 2) bytes
 #define BK_BIN_ROUND 2048                    // occurrences one round may hold (distinct <= occurrences <= half the slots, in expectation)
-#define BK_BIN_SMEM (BK_BIN_SLOTS * 12)
+#define BK_BIN_SMEM (BK_BIN_SLOTS * 14)       // keys, counts, list of occupied slots
 
 __device__ __forceinline__ u64 bin_hash(u64 x) { return (x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull; }
 
@@ -79,14 +79,16 @@ __global__ void __launch_bounds__(BK_BIN_G_THREADS) k_bin_scatter(BinView b) {
 }
 
 // grid P, 256 threads, BK_BIN_SMEM bytes of shared memory.  Appends to the counted list of the file.
-// A round: clear the table; insert (the keys of up to eight iterations are loaded before the first is inserted);
-// look the distinct k-mers up in the reference table (first probes of eight slots together; a reference k-mer adds
-// its count to idcnt and leaves the table); compact what passes the KMC cut-offs to the counted list.
+// A round: clear the table; insert (the keys of up to eight iterations are loaded before the first is inserted; the
+// thread that claims an empty slot also appends it to the list of occupied slots); then, over that dense list:
+// look the distinct k-mers up in the reference table (first probes of four k-mers together; a reference k-mer adds
+// its count to idcnt and drops out) and compact what passes the KMC cut-offs to the counted list.
 __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, u32* full) {
     extern __shared__ __align__(16) u8 bsm[];
-    __shared__ u32 s_base;
+    __shared__ u32 s_base, s_nocc;
     u64* keys = reinterpret_cast<u64*>(bsm);
     u32* cnts = reinterpret_cast<u32*>(bsm + BK_BIN_SLOTS * 8);
+    unsigned short* occ = reinterpret_cast<unsigned short*>(bsm + BK_BIN_SLOTS * 12);     // occupied slots, in claim order
     const u32 lane = threadIdx.x & 31;
     const u32 s = b.cnt[(size_t)blockIdx.x * b.G], e = b.cnt[(size_t)(blockIdx.x + 1) * b.G];
     if (e == s) return;
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
     u32 uniq = 0; u64 total = 0;
     for (u32 r = 0; r < rounds; r++) {
         for (u32 i = threadIdx.x; i < BK_BIN_SLOTS; i += blockDim.x) { keys[i] = BK_HOLE; cnts[i] = 0; }
+        if (threadIdx.x == 0) s_nocc = 0;
         __syncthreads();
         const u32 n_round = ((e - s + 31) & ~31u);
         for (u32 i0 = 0; i0 < n_round; i0 += 8 * 256) {
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                     u32 probes = 0;
                     for (;;) {
                         const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot), (unsigned long long)BK_HOLE, (unsigned long long)key);
+                        if (old == BK_HOLE) occ[atomicAdd(&s_nocc, 1u)] = (unsigned short)slot;
                         if (old == BK_HOLE || old == key) { atomicAdd(cnts + slot, w); break; }
                         slot = (slot + 1) & (BK_BIN_SLOTS - 1);
                         if (++probes >= BK_BIN_SLOTS) { *full = 1; break; }
@@ -130,52 +134,51 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
             }
         }
         __syncthreads();
-        // reference k-mers leave the table (their count goes to idcnt); what fails the cut-offs is marked with a
-        // zero count; statistics of the novel k-mers
-        u32 mine = 0;
+        // the occupied slots, four per thread and pass: reference k-mers leave (their count goes to idcnt), what fails
+        // the cut-offs is dropped, the rest is compacted to the counted list
+        const u32 n_occ = s_nocc;
+        __syncthreads();                                 // (the next round resets the counter)
+        for (u32 p0 = 0; p0 < n_occ; p0 += 4 * 256) {
+            u64 kk[4]; u32 cc[4], hh[4]; ExactSlotD e0[4];
+            u32 mine = 0;
 #pragma unroll
-        for (u32 q0 = 0; q0 < BK_BIN_SLOTS / 256; q0 += 8) {
-            u64 kk[8]; u32 hh[8]; ExactSlotD e0[8];
-#pragma unroll
-            for (u32 j = 0; j < 8; j++) {
-                kk[j] = keys[(q0 + j) * 256 + threadIdx.x];
-                hh[j] = hash_slot(kk[j], b.exact_shift);
+            for (u32 j = 0; j < 4; j++) {
+                const u32 p = p0 + j * 256 + threadIdx.x;
+                kk[j] = BK_HOLE; cc[j] = 0; hh[j] = 0;
                 e0[j].key = BK_EMPTY; e0[j].gidx = 0; e0[j].oseq = 0;
-                if (kk[j] != BK_HOLE) e0[j] = load_exact(b.exact + hh[j]);
+                if (p < n_occ) {
+                    const u32 slot = occ[p];
+                    kk[j] = keys[slot]; cc[j] = cnts[slot];
+                    hh[j] = hash_slot(kk[j], b.exact_shift);
+                    e0[j] = load_exact(b.exact + hh[j]);
+                }
             }
 #pragma unroll
-            for (u32 j = 0; j < 8; j++) {
-                const u32 i = (q0 + j) * 256 + threadIdx.x;
+            for (u32 j = 0; j < 4; j++) {
                 if (kk[j] == BK_HOLE) continue;
-                const u32 c = cnts[i];
                 u32 h = hh[j];
                 ExactSlotD sl = e0[j];
                 bool is_ref = false;
                 for (;;) {                               // same probe sequence as bk_core.cuh: exact_lookup
-                    if (sl.key == kk[j]) { atomicAdd(b.idcnt + __ldg(b.slot2id + sl.gidx), c); is_ref = true; break; }
+                    if (sl.key == kk[j]) { atomicAdd(b.idcnt + __ldg(b.slot2id + sl.gidx), cc[j]); is_ref = true; break; }
                     if (sl.key == BK_EMPTY) break;
                     h = (h + 1) & b.exact_mask;
                     sl = load_exact(b.exact + h);
                 }
-                if (!is_ref) { uniq++; total += c; }
-                const bool keep = !is_ref && c >= a.ci && c <= 1000000000u;
-                if (!keep) cnts[i] = 0; else mine++;
+                if (!is_ref) { uniq++; total += cc[j]; }
+                const bool keep = !is_ref && cc[j] >= a.ci && cc[j] <= 1000000000u;
+                if (keep) mine++; else kk[j] = BK_HOLE;
             }
-        }
-        u32 tot;
-        u32 o = block_excl_scan_256(mine, &tot);
-        if (threadIdx.x == 0) s_base = tot ? atomicAdd(&a.fc->n_counted, tot) : 0u;
-        __syncthreads();
-        o += s_base;
-        if (tot) {
+            u32 tot;
+            u32 o = block_excl_scan_256(mine, &tot);
+            if (threadIdx.x == 0) s_base = tot ? atomicAdd(&a.fc->n_counted, tot) : 0u;
+            __syncthreads();
+            o += s_base;
 #pragma unroll
-            for (u32 q = 0; q < BK_BIN_SLOTS / 256; q++) {
-                const u32 i = q * 256 + threadIdx.x;
-                const u32 c = cnts[i];
-                if (c) { if (o < a.out_cap) { a.out_kmers[o] = keys[i]; a.out_counts[o] = min(c, a.cs); } o++; }
-            }
+            for (u32 j = 0; j < 4; j++)
+                if (kk[j] != BK_HOLE) { if (o < a.out_cap) { a.out_kmers[o] = kk[j]; a.out_counts[o] = min(cc[j], a.cs); } o++; }
+            __syncthreads();
         }
-        __syncthreads();
     }
     // one pair of atomics per CTA (thousands of CTAs, one address each)
     __shared__ u32 s_uniq; __shared__ unsigned long long s_total;
