@@ -20,6 +20,7 @@
 namespace bk {
 
 #define BK_BIN_G_THREADS 1024
+#define BK_BIN_G_PER_SM 1                    // CTAs of k_bin_hist / k_bin_scatter per SM (2 measured slower: shorter runs per bin)
 #define BK_BIN_SLOTS 4096                    // shared-memory table of k_bin_count: 4096 x (8 + 4 + 2) bytes
 #define BK_BIN_ROUND 2048                    // occurrences one round may hold (distinct <= occurrences <= half the slots, in expectation)
 #define BK_BIN_SMEM (BK_BIN_SLOTS * 14)       // keys, counts, list of occupied slots

@@ -333,7 +333,7 @@ static int size_for_index(bk_ctx* ctx) {
     }
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
-    BK_CUDA(ctx->d_bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count) / BK_PS_BLOCK + 2));
+    BK_CUDA(ctx->d_bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count * BK_BIN_G_PER_SM) / BK_PS_BLOCK + 2));
     for (FileState& f : ctx->file) {
         BK_CUDA(f.diff.reserve((size_t)d.n_raw + 2));
         BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
@@ -672,7 +672,7 @@ static int stage_compact(bk_ctx* ctx, int slot) {
         u32 lp = 6;                          // a round of a bin is sized for 1/32 of the room: 3 % of the bases novel
         while (lp < 14 && ((u64)BK_BIN_ROUND << lp) < f.nov_ub / 32) lp++;
         f.bin_log2p = lp;
-        const u32 P = 1u << lp, G = (u32)ctx->sm_count, PG = P * G;
+        const u32 P = 1u << lp, G = (u32)ctx->sm_count * BK_BIN_G_PER_SM, PG = P * G;
         const u32 nb = (PG + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
         BK_CUDA(f.bin_cnt.reserve((size_t)PG + 1));
         BK_CUDA(ctx->d_nov_sorted.reserve(std::max<size_t>(f.nov.cap, 1)));
