@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--ref-depth", type=int, default=2000, help="bounded sample depth for the CPU arm")
     ap.add_argument("--cpu-depth", type=int, default=2000, help="bounded sample depth for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer runs: skip the host-buffer leg (e2e is null)")
     ap.add_argument("--in-flight", type=int, default=4,
                     help="samples in flight per GPU (one bk_ctx + stream each); 1 = strictly one sample at a time")
     args = ap.parse_args()
@@ -268,13 +269,16 @@ def main():
     value = total_bases / (ms_step * 1e-3)
 
     # ---- e2e: pinned host buffers through the public API, wall clock incl. H2D + result D2H ------
-    run_steps(2 * S, step_e2e)
-    barrier()
-    t0 = time.perf_counter()
-    run_steps(args.steps, step_e2e)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total_bases * args.steps / e2e_s
+    if not args.no_e2e:
+        run_steps(2 * S, step_e2e)
+        barrier()
+        t0 = time.perf_counter()
+        run_steps(args.steps, step_e2e)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = total_bases * args.steps / e2e_s
+    else:
+        e2e_value = None
     h2d = sum(hb.numel() - 64 + ho.numel() * 4 for hb, ho, _ in pinned)
     d2h = int(len(res.variants) * 72 + 120 + 2 * 4 * 16)
 

@@ -8,7 +8,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libbronko_b200.so")
+# BRONKO_B200_LIB: another build of the same library (tools/build_variant.sh: A/B runs of kernel variants)
+SO_PATH = os.environ.get("BRONKO_B200_LIB") or os.path.join(CSRC, "libbronko_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "bronko_b200.h")
 
 u8p, u32, u64, P = C.POINTER(C.c_uint8), C.c_uint32, C.c_uint64, C.c_void_p

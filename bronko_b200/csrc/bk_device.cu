@@ -472,6 +472,15 @@ static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     return v;
 }
 
+// Developer builds only (tools/build_variant.sh ... -DBK_ABLATE): BK_ABLATE=scan,leftover,bins,map,noise skips the kernels of a
+// stage so that its marginal cost with several samples in flight can be measured.  Results are garbage; the product
+// build compiles this to `false`.
+#ifdef BK_ABLATE
+static bool ablated(const char* stage) { const char* e = getenv("BK_ABLATE"); return e && strstr(e, stage); }
+#else
+static inline bool ablated(const char*) { return false; }
+#endif
+
 // first use of a file slot in this sample: zero its difference array and (re)initialise its table
 static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
     FileState& f = ctx->file[slot];
@@ -532,13 +541,14 @@ static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_o
     if (tile_reads < 32) tile_reads = BK_SCAN_THREADS;   // long reads: tiles will not fit; kernel reads global memory
     const u32 n_tiles = (n + tile_reads - 1) / tile_reads;
     int sp = ctx->span_begin(ST_SCAN);
-    k_scan<<<grid_for(ctx, n_tiles, 1, 16), BK_SCAN_THREADS, tile_bytes + 64, ctx->stream>>>(
+    if (!ablated("scan")) k_scan<<<grid_for(ctx, n_tiles, 1, 16), BK_SCAN_THREADS, tile_bytes + 64, ctx->stream>>>(
         v, d_bases, d_off, off_bias, r_begin, r_end, tile_reads, tile_bytes, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->span_end(sp);
     ctx->launches++; ctx->scan_launches++;
     BK_CUDA(cudaGetLastError());
     sp = ctx->span_begin(ST_LEFTOVER);
-    if (f.list_mode) k_leftover<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    if (ablated("leftover")) {}
+    else if (f.list_mode) k_leftover<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
     else k_leftover<0><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->launches++;
     ctx->span_end(sp);
@@ -680,12 +690,14 @@ static int stage_compact(bk_ctx* ctx, int slot) {
         b.sorted = ctx->d_nov_sorted.p; b.cnt = f.bin_cnt.p; b.log2p = lp; b.G = G;
         b.exact = ctx->I->d_exact.p; b.exact_shift = 64 - d.exact_log2; b.exact_mask = (1u << d.exact_log2) - 1;
         b.slot2id = ctx->I->d_slot2id.p; b.idcnt = f.idcnt.p;
+        if (!ablated("bins")) {
         k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
         k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
         k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
         k_excl_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
         k_bin_scatter<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
-        k_bin_count<<<P, 256, BK_BIN_SMEM, ctx->stream>>>(b, a, &ctx->d_ctr.p->gen_full);
+        if (!ablated("bincount")) k_bin_count<<<P, 256, BK_BIN_SMEM, ctx->stream>>>(b, a, &ctx->d_ctr.p->gen_full);
+        }
         k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);   // after the bins: they add to idcnt
         ctx->launches += 7;
     }
@@ -733,7 +745,8 @@ static int stage_map_fused(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (m.gslots) k_map_grp<2><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        if (ablated("map")) {}
+        else if (m.gslots) k_map_grp<2><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
         else k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
         ctx->launches++;
     }
@@ -815,7 +828,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     const u32 nseq = ctx->I->max_seqs_per_genome;
     if (ctx->noise_debug) cudaMemsetAsync(ctx->d_nz_stats.p, 0, 64, st);
     k_noise_fracs<<<dim3((d.max_genome_rows + BK_NZ_PAD + 255) / 256, nseq), 256, 0, st>>>(nv);
-    k_noise_seq<<<dim3(2 + (ctx->nz_max_chunks + 7) / 8, nseq), BK_NZ_SEQ_THREADS, BK_NZ_SEQ_SMEM, st>>>(nv);
+    if (!ablated("noise")) k_noise_seq<<<dim3(2 + (ctx->nz_max_chunks + 7) / 8, nseq), BK_NZ_SEQ_THREADS, BK_NZ_SEQ_SMEM, st>>>(nv);
     k_noise_fix<<<dim3(1, nseq), 256, 0, st>>>(nv);
     k_noise_tau<<<dim3((d.max_genome_rows + BK_NOISE_HALF + 255) / 256, nseq), 256, 0, st>>>(nv);
     if (ctx->noise_debug) {        // BK_NOISE_DEBUG=1

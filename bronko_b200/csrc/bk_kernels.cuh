@@ -649,12 +649,27 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
 // A record matches bucket i iff it equals (i << 58) | (k-mer with digit i zeroed).  Modes as k_map_small.
 // entries [off, off+len) of one bucket hit: tallies and / or pileup updates (src/call.rs:1309-1385)
 #define BK_MAP_QUEUE 4
+#ifndef BK_MAP_BATCH
+#define BK_MAP_BATCH 4          // independent record / entry loads issued together
+#endif
+#ifndef BK_MAP_GRP_CTAS
+#define BK_MAP_GRP_CTAS 3       // resident CTAs per SM the register budget is set for
+#endif
 template <int MODE>
 __device__ __forceinline__ void map_walk(const MapView& m, u32 off, u32 len, u64 kb, bool rc, u32 cnt, i32 best, u32 g_row0,
                                          u32* pile, u32 pile_stride, u64& hits4) {
     const u32 k = m.k;
-    for (u32 j = 0; j < len; j++) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+    // the entries of a hit are independent loads: BK_MAP_BATCH of them are in flight before the first is used (walked
+    // one by one, waiting for each entry was a fifth of the kernel's stall samples)
+    for (u32 j0 = 0; j0 < len; j0 += BK_MAP_BATCH) {
+      uint2 rawb[BK_MAP_BATCH];
+#pragma unroll
+      for (u32 jj = 0; jj < BK_MAP_BATCH; jj++)
+          rawb[jj] = j0 + jj < len ? __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j0 + jj) : make_uint2(0xFFFFFFFFu, 0u);
+#pragma unroll
+      for (u32 jj = 0; jj < BK_MAP_BATCH; jj++) {
+        if (jj && j0 + jj >= len) break;
+        const uint2 raw = rawb[jj];
         const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
         if (row == 0xFFFFFFFFu) continue;
         if (MODE != 1) hits4 += 1ull << (16 * file_id);       // src/call.rs:1316-1318
@@ -669,11 +684,12 @@ __device__ __forceinline__ void map_walk(const MapView& m, u32 off, u32 len, u64
             atomicAdd(gp + (to_fwd ? 2u : 3u) * pile_stride + cell, 1u);
             atomicMax(gp + (to_fwd ? 0u : 1u) * pile_stride + cell, cnt);
         }
+      }
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BK_MAP_GRP_CTAS)
 k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, const u32* n_ptr, u32 n_cap,
           u32* gstats, const i32* best_ptr, u32* pile, u32 pile_stride) {
     const u32 n = min(*n_ptr, n_cap);
@@ -724,8 +740,15 @@ k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ coun
                     h = (h + 1) & m.gmask;
                     sl = __ldg(reinterpret_cast<const uint4*>(m.gslots) + h);
                 }
-                for (u32 r = 0; r < count; r++) {
-                    const uint4 rec = __ldg(reinterpret_cast<const uint4*>(m.grecs) + first + r);
+                for (u32 rb = 0; rb < count; rb += BK_MAP_BATCH) {        // records of the group, BK_MAP_BATCH loads in flight
+                  uint4 recb[BK_MAP_BATCH];
+#pragma unroll
+                  for (u32 jj = 0; jj < BK_MAP_BATCH; jj++)
+                      recb[jj] = rb + jj < count ? __ldg(reinterpret_cast<const uint4*>(m.grecs) + first + rb + jj) : make_uint4(0u, 0xFC000000u, 0u, 0u);   // index 63: never queried
+#pragma unroll
+                  for (u32 jj = 0; jj < BK_MAP_BATCH; jj++) {
+                    if (jj && rb + jj >= count) break;
+                    const uint4 rec = recb[jj];
                     const u64 rkey = ((u64)rec.y << 32) | rec.x;
                     const u32 i = (u32)(rkey >> 58);
                     if (i < i_lo || i >= i_hi) continue;
@@ -735,6 +758,7 @@ k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ coun
                     // no dynamic indexing; a fifth hit evicts the oldest, which is walked at once.
                     if (nq == BK_MAP_QUEUE) { map_walk<MODE>(m, qo3, ql3, kb, rc, cnt, best, g_row0, pile, pile_stride, hits4); nq--; }
                     qo3 = qo2; ql3 = ql2; qo2 = qo1; ql2 = ql1; qo1 = qo0; ql1 = ql0; qo0 = rec.z; ql0 = rec.w; nq++;
+                  }
                 }
             }
             kb_keep = kb; rc_keep = rc; cnt_keep = cnt;
