@@ -73,7 +73,7 @@ struct IndexDev {
     HostIndex ix;
     DerivedIndex d;
     DevBuf<BucketSlotD> d_bucket_slots; DevBuf<BucketEntryD> d_bucket_entries;
-    DevBuf<BucketSlotD> d_group_slots, d_group_recs;
+    DevBuf<BucketSlotD> d_group_slots, d_group_centers; DevBuf<uint2> d_group_buckets;
     DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
@@ -81,7 +81,7 @@ struct IndexDev {
     u32 max_seqs_per_genome = 1;
     ~IndexDev() {
         cudaSetDevice(device);
-        d_bucket_slots.release(); d_bucket_entries.release(); d_group_slots.release(); d_group_recs.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
+        d_bucket_slots.release(); d_bucket_entries.release(); d_group_slots.release(); d_group_centers.release(); d_group_buckets.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
         d_exact.release(); d_slot2id.release(); d_id_kmer.release(); d_genome_row0.release(); d_genome_seq_off.release();
         d_seq_row0.release(); d_genome_len.release(); d_ref_code.release();
     }
@@ -284,12 +284,16 @@ static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
     BK_CUDA(ctx->I->d_bucket_entries.reserve(d.bucket_entries.size()));
     if (!d.bucket_entries.empty())
         BK_CUDA(cudaMemcpyAsync(ctx->I->d_bucket_entries.p, d.bucket_entries.data(), d.bucket_entries.size() * 8, cudaMemcpyHostToDevice, st));
-    if (d.rekeyed) {
+    if (!d.group_slots.empty()) {
+        static_assert(sizeof(OffLen) == sizeof(uint2), "layout");
         BK_CUDA(ctx->I->d_group_slots.reserve(d.group_slots.size()));
         BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_slots.p, d.group_slots.data(), d.group_slots.size() * 16, cudaMemcpyHostToDevice, st));
-        BK_CUDA(ctx->I->d_group_recs.reserve(std::max<size_t>(d.group_recs.size(), 1)));
-        if (!d.group_recs.empty())
-            BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_recs.p, d.group_recs.data(), d.group_recs.size() * 16, cudaMemcpyHostToDevice, st));
+        BK_CUDA(ctx->I->d_group_centers.reserve(std::max<size_t>(d.group_centers.size(), 1)));
+        if (!d.group_centers.empty())
+            BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_centers.p, d.group_centers.data(), d.group_centers.size() * 16, cudaMemcpyHostToDevice, st));
+        BK_CUDA(ctx->I->d_group_buckets.reserve(d.group_buckets.size() + 4));     // (+4: batched loads may run past a side's last bucket)
+        if (!d.group_buckets.empty())
+            BK_CUDA(cudaMemcpyAsync(ctx->I->d_group_buckets.p, d.group_buckets.data(), d.group_buckets.size() * 8, cudaMemcpyHostToDevice, st));
     }
     BK_CUDA(ctx->I->d_exact.reserve(d.exact_slots.size()));
     BK_CUDA(cudaMemcpyAsync(ctx->I->d_exact.p, d.exact_slots.data(), d.exact_slots.size() * 16, cudaMemcpyHostToDevice, st));
@@ -718,8 +722,8 @@ static MapView make_map_view(bk_ctx* ctx) {
     m.slots = ctx->I->d_bucket_slots.p; m.shift = 64 - ctx->I->d.bucket_log2; m.mask = (1u << ctx->I->d.bucket_log2) - 1;
     m.entries = ctx->I->d_bucket_entries.p;
     m.n_genomes = ctx->I->d.n_genomes; m.genome_row0 = ctx->I->d_genome_row0.p;
-    const bool grouped = ctx->I->d.rekeyed && !ctx->no_group_map;
-    m.gslots = grouped ? ctx->I->d_group_slots.p : nullptr; m.grecs = ctx->I->d_group_recs.p;
+    const bool grouped = ctx->I->d.rekeyed && !ctx->I->d.group_slots.empty() && !ctx->no_group_map;
+    m.gslots = grouped ? ctx->I->d_group_slots.p : nullptr; m.gcenters = ctx->I->d_group_centers.p; m.gbuckets = ctx->I->d_group_buckets.p;
     m.gshift = 64 - ctx->I->d.group_log2; m.gmask = (1u << ctx->I->d.group_log2) - 1; m.gmid = ctx->I->d.group_mid;
     return m;
 }

@@ -57,6 +57,7 @@ std::string fmt_fixed(double v, int prec);
 struct BucketSlot { u64 key; u32 off; u32 len; };                 // 16 B; key == ~0 → empty
 struct BucketEntry { u32 row; u16 file_id; u8 idx; u8 canonical; }; // 8 B; row = global pileup row of `location`
 struct ExactSlot { u64 key; u32 gidx; u32 oseq; };                // 16 B; key == ~0 → empty
+struct OffLen { u32 off; u32 len; };                              // 8 B; entries [off, off + len) of one bucket
 
 struct DerivedIndex {
     u32 k = 0, n_genomes = 0, n_seqs = 0;
@@ -73,16 +74,24 @@ struct DerivedIndex {
     bool rekeyed = false;
     u32 bucket_log2 = 0;
     std::vector<BucketSlot> bucket_slots;
-    // Grouped form of the re-keyed table (only when rekeyed).  The 16 buckets of a query k-mer differ in ONE digit
-    // each, so the buckets with index < k/2 all share the k-mer's low half and the others its high half: records are
-    // sorted by (side, shared half) and a query finds all its buckets with two group probes followed by two short
-    // contiguous reads, instead of 16 independent random probes.
-    //   group key = (side << 62) | shared half value;  group_slots: open addressing {key, first record, count};
-    //   group_recs: {(index << 58) | masked canonical k-mer, off, len} (same meaning as bucket_slots), grouped.
+    // Grouped form of the re-keyed table (only when rekeyed and n_genomes <= 4: the thread-per-k-mer map kernels).
+    // A query k-mer Q hits bucket (i, Q without digit i) iff some reference k-mer equals Q everywhere except possibly
+    // at digit i.  Such a reference k-mer shares Q's low half (digits mid..k-1) when i < mid and Q's high half
+    // otherwise, so the canonical reference k-mers ("centers") are grouped by (side, shared half):
+    //   group key = (side << 62) | shared half value;  group_slots: open addressing {key, first center, count};
+    //   group_centers: {center k-mer C, first of its buckets in group_buckets, bit mask of the bucket indices present};
+    //   group_buckets: per center and side, for every index i of that side (0..mid-1 / mid..k-1): {off, len} of the
+    //                  entries of bucket (i, C without digit i) — the same (off, len) bucket_slots holds.
+    // A query needs two group probes, its one or two centers per side, and then one {off, len} per hit: C == Q hits
+    // every bucket of the side, C differing from Q in exactly digit j hits bucket j, anything else nothing.  Centers are
+    // the verified first-entry k-mers of the keys: every existing bucket (i, M) has such a center C with C without
+    // digit i == M, so a query that hits the bucket is within one digit (i) of C and finds it; several centers can
+    // lead to the same bucket (they differ in digit i only), the kernel takes each index once.
     u32 group_mid = 0;                       // bucket indices < group_mid are on side 0 (shared half = digits mid..k-1)
     u32 group_log2 = 0;
-    std::vector<BucketSlot> group_slots;     // key == ~0 → empty; off = first record, len = count
-    std::vector<BucketSlot> group_recs;
+    std::vector<BucketSlot> group_slots;     // key == ~0 → empty; off = first center, len = count
+    std::vector<BucketSlot> group_centers;   // key = center, off = first bucket, len = present mask
+    std::vector<OffLen> group_buckets;
     std::vector<BucketEntry> bucket_entries;
     // oriented reference store (forward and reverse-complement of every sequence), 2-bit packed,
     // MSB-first, 32 bases per u64; global base index space with REF_PAD_BASES of padding in front

@@ -325,8 +325,11 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
     // index not produced by `bronko build`) keeps the id-keyed table.
     std::vector<u64> slot_key(ix.keys.begin(), ix.keys.end());
     d.rekeyed = allow_rekey && k <= 29;
+    const bool want_groups = d.n_genomes <= 4;                // the grouped form serves the thread-per-k-mer map kernels only
+    std::vector<u64> center;                                  // per key: the canonical k-mer its first entry was verified with
     if (d.rekeyed) {
         std::vector<u64> ids(k);
+        if (want_groups) center.resize(ix.keys.size());
         for (size_t i = 0; i < ix.keys.size() && d.rekeyed; i++) {
             if (ix.entry_off[i + 1] == ix.entry_off[i]) { d.rekeyed = false; break; }
             const bk_bucket_info& e = ix.entries[ix.entry_off[i]];
@@ -342,6 +345,7 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
             assign_buckets_host(kb, (int)k, ids.data());
             if (ids[e.idx] != ix.keys[i]) { d.rekeyed = false; break; }
             slot_key[i] = ((u64)e.idx << 58) | (kb & ~(3ull << (2 * (k - 1 - e.idx))));
+            if (want_groups) center[i] = kb;
         }
         if (!d.rekeyed) slot_key.assign(ix.keys.begin(), ix.keys.end());
     }
@@ -352,33 +356,54 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         d.bucket_slots[h] = BucketSlot{slot_key[i], (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
     }
 
-    if (d.rekeyed) {                          // grouped form (bk_host.h)
+    if (d.rekeyed && want_groups) {           // grouped form (bk_host.h)
         const u32 mid = k / 2;
         d.group_mid = mid;
         const u32 lo_bits = 2 * (k - mid);                                   // digits mid..k-1
-        struct Rec { u64 g; BucketSlot r; };
-        std::vector<Rec> recs(ix.keys.size());
+        struct Cen { u64 g, c; };
+        std::vector<Cen> cens(ix.keys.size());
         for (size_t i = 0; i < ix.keys.size(); i++) {
-            const u64 key = slot_key[i];
-            const u32 idx = (u32)(key >> 58);
-            const u64 m = key & ((1ull << 58) - 1);
-            const u64 half = idx < mid ? (m & ((1ull << lo_bits) - 1)) : (m >> lo_bits);
-            recs[i].g = ((u64)(idx < mid ? 0 : 1) << 62) | half;
-            recs[i].r = BucketSlot{key, (u32)ix.entry_off[i], (u32)(ix.entry_off[i + 1] - ix.entry_off[i])};
+            const u32 idx = (u32)(slot_key[i] >> 58);
+            const u64 c = center[i];
+            const u64 half = idx < mid ? (c & ((1ull << lo_bits) - 1)) : (c >> lo_bits);
+            cens[i] = Cen{((u64)(idx < mid ? 0 : 1) << 62) | half, c};
         }
-        std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.g != b.g ? a.g < b.g : a.r.key < b.r.key; });
+        std::sort(cens.begin(), cens.end(), [](const Cen& a, const Cen& b) { return a.g != b.g ? a.g < b.g : a.c < b.c; });
+        cens.erase(std::unique(cens.begin(), cens.end(), [](const Cen& a, const Cen& b) { return a.g == b.g && a.c == b.c; }), cens.end());
         size_t n_groups = 0;
-        for (size_t i = 0; i < recs.size(); i++) if (i == 0 || recs[i].g != recs[i - 1].g) n_groups++;
+        for (size_t i = 0; i < cens.size(); i++) if (i == 0 || cens[i].g != cens[i - 1].g) n_groups++;
         d.group_log2 = log2_cap(n_groups);
         d.group_slots.assign(1ull << d.group_log2, BucketSlot{~0ull, 0, 0});
-        d.group_recs.resize(recs.size());
+        d.group_centers.resize(cens.size());
+        d.group_buckets.clear();
         const u64 gmask = (1ull << d.group_log2) - 1;
-        for (size_t i = 0; i < recs.size();) {
+        auto find_bucket = [&](u64 key, u32* off, u32* len) {            // the probe sequence of the device
+            u64 h = hash_slot_host(key, 64 - d.bucket_log2);
+            for (;;) {
+                const BucketSlot& sl = d.bucket_slots[h];
+                if (sl.key == key) { *off = sl.off; *len = sl.len; return true; }
+                if (sl.key == ~0ull) return false;
+                h = (h + 1) & bmask;
+            }
+        };
+        for (size_t i = 0; i < cens.size();) {
             size_t j = i;
-            while (j < recs.size() && recs[j].g == recs[i].g) { d.group_recs[j] = recs[j].r; j++; }
-            u64 h = hash_slot_host(recs[i].g, 64 - d.group_log2);
+            while (j < cens.size() && cens[j].g == cens[i].g) {
+                // the buckets of this center on this side: index i2 in [lo, hi) → (off, len) of bucket (i2, center without digit i2)
+                const u32 side = (u32)(cens[j].g >> 62), lo = side ? mid : 0, hi = side ? k : mid;
+                const u32 boff = (u32)d.group_buckets.size();
+                u32 present = 0;
+                for (u32 i2 = lo; i2 < hi; i2++) {
+                    u32 off = 0, len = 0;
+                    if (find_bucket(((u64)i2 << 58) | (cens[j].c & ~(3ull << (2 * (k - 1 - i2)))), &off, &len)) present |= 1u << i2;
+                    d.group_buckets.push_back(OffLen{off, len});
+                }
+                d.group_centers[j] = BucketSlot{cens[j].c, boff, present};
+                j++;
+            }
+            u64 h = hash_slot_host(cens[i].g, 64 - d.group_log2);
             while (d.group_slots[h].key != ~0ull) h = (h + 1) & gmask;
-            d.group_slots[h] = BucketSlot{recs[i].g, (u32)i, (u32)(j - i)};
+            d.group_slots[h] = BucketSlot{cens[i].g, (u32)i, (u32)(j - i)};
             i = j;
         }
     }

@@ -418,7 +418,7 @@ struct MapView {
     const BucketEntryD* entries;
     u32 n_genomes; const u32* genome_row0;
     // grouped form of the re-keyed table (bk_host.h: group_slots / group_recs); null when not available
-    const BucketSlotD* gslots; u32 gshift, gmask; const BucketSlotD* grecs; u32 gmid;
+    const BucketSlotD* gslots; u32 gshift, gmask; const BucketSlotD* gcenters; const uint2* gbuckets; u32 gmid;
 };
 
 __device__ __forceinline__ u64 revcomp_dev(u64 v, u32 k) {
@@ -643,10 +643,12 @@ k_map_small(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ co
     }
 }
 
-// k_map_grp — the thread-per-k-mer map on the GROUPED table: the buckets of a k-mer with index < k/2 share its low
-// half, the others its high half, so two group probes (issued together) and two short contiguous reads replace the
-// 16 independent random probes of k_map_small (which is bound by the number of outstanding L2 misses an SM can hold).
-// A record matches bucket i iff it equals (i << 58) | (k-mer with digit i zeroed).  Modes as k_map_small.
+// k_map_grp — the thread-per-k-mer map on the GROUPED table (bk_host.h: group_slots / group_centers / group_buckets).
+// The reference k-mers that can share a bucket with the query share its low half (bucket index < k/2) or its high half,
+// so two group probes (issued together) find the one or two "centers" per side; a center equal to the query hits every
+// bucket of the side, a center that differs in exactly digit j hits bucket j, and each hit costs one {off, len} load.
+// This replaces the 16 independent random probes of k_map_small (bound by the outstanding L2 misses an SM can hold)
+// and the scan over ~10 bucket records per side of the first grouped layout.  Modes as k_map_small.
 // entries [off, off+len) of one bucket hit: tallies and / or pileup updates (src/call.rs:1309-1385)
 #define BK_MAP_QUEUE 4
 #ifndef BK_MAP_BATCH
@@ -740,25 +742,43 @@ k_map_grp(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ coun
                     h = (h + 1) & m.gmask;
                     sl = __ldg(reinterpret_cast<const uint4*>(m.gslots) + h);
                 }
-                for (u32 rb = 0; rb < count; rb += BK_MAP_BATCH) {        // records of the group, BK_MAP_BATCH loads in flight
-                  uint4 recb[BK_MAP_BATCH];
+                const u32 side_lo = sd == 0 ? 0u : m.gmid;
+                const u32 range = ((1u << i_hi) - 1u) & ~((1u << i_lo) - 1u);              // queried indices of this side (k <= 29)
+                u32 done = 0;                                                             // indices already taken
+                for (u32 cb = 0; cb < count; cb += 2) {                                    // centers, two loads in flight
+                    uint4 cen[2];
+                    cen[0] = __ldg(reinterpret_cast<const uint4*>(m.gcenters) + first + cb);
+                    cen[1] = cb + 1 < count ? __ldg(reinterpret_cast<const uint4*>(m.gcenters) + first + cb + 1) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                  for (u32 jj = 0; jj < BK_MAP_BATCH; jj++)
-                      recb[jj] = rb + jj < count ? __ldg(reinterpret_cast<const uint4*>(m.grecs) + first + rb + jj) : make_uint4(0u, 0xFC000000u, 0u, 0u);   // index 63: never queried
+                    for (u32 cc = 0; cc < 2; cc++) {
+                        const u64 x = kb ^ (((u64)cen[cc].y << 32) | cen[cc].x);
+                        u32 cand = cen[cc].w & range;                                      // center == query: every bucket present
+                        if (x) {
+                            const u64 nz = (x | (x >> 1)) & 0x5555555555555555ull;       // one bit per differing digit
+                            cand = (nz & (nz - 1)) ? 0u : cand & (1u << (k - 1 - ((63u - (u32)__clzll((long long)nz)) >> 1)));
+                        }
+                        cand &= ~done;
+                        done |= cand;
+                        const u32 b_first = cen[cc].z;                                     // bucket of index side_lo
+                        while (cand) {                                                     // hits: {off, len} of up to BK_MAP_BATCH buckets together
+                            u32 bi[BK_MAP_BATCH]; uint2 ol[BK_MAP_BATCH];
 #pragma unroll
-                  for (u32 jj = 0; jj < BK_MAP_BATCH; jj++) {
-                    if (jj && rb + jj >= count) break;
-                    const uint4 rec = recb[jj];
-                    const u64 rkey = ((u64)rec.y << 32) | rec.x;
-                    const u32 i = (u32)(rkey >> 58);
-                    if (i < i_lo || i >= i_hi) continue;
-                    if ((rkey & ((1ull << 58) - 1)) != (kb & ~(3ull << (2 * (k - 1 - i))))) continue;
-                    // a hit: remember it; the entries are walked after the scan, all lanes of the warp together (walked
-                    // lane by lane as the hits turned up, that part ran with 1.7 of 32 lanes active).  Shift-in queue:
-                    // no dynamic indexing; a fifth hit evicts the oldest, which is walked at once.
-                    if (nq == BK_MAP_QUEUE) { map_walk<MODE>(m, qo3, ql3, kb, rc, cnt, best, g_row0, pile, pile_stride, hits4); nq--; }
-                    qo3 = qo2; ql3 = ql2; qo2 = qo1; ql2 = ql1; qo1 = qo0; ql1 = ql0; qo0 = rec.z; ql0 = rec.w; nq++;
-                  }
+                            for (u32 jj = 0; jj < BK_MAP_BATCH; jj++) {
+                                bi[jj] = cand ? (u32)__ffs((int)cand) - 1u : 0xFFFFFFFFu;
+                                cand &= cand - 1;
+                                ol[jj] = bi[jj] != 0xFFFFFFFFu ? __ldg(m.gbuckets + (b_first + bi[jj] - side_lo)) : make_uint2(0u, 0u);
+                            }
+#pragma unroll
+                            for (u32 jj = 0; jj < BK_MAP_BATCH; jj++) {
+                                if (bi[jj] == 0xFFFFFFFFu) break;
+                                // a hit: remember it; the entries are walked after the lookups, all lanes of the warp together
+                                // (walked lane by lane as the hits turned up, that part ran with 1.7 of 32 lanes active).
+                                // Shift-in queue: no dynamic indexing; a fifth hit evicts the oldest, which is walked at once.
+                                if (nq == BK_MAP_QUEUE) { map_walk<MODE>(m, qo3, ql3, kb, rc, cnt, best, g_row0, pile, pile_stride, hits4); nq--; }
+                                qo3 = qo2; ql3 = ql2; qo2 = qo1; ql2 = ql1; qo1 = qo0; ql1 = ql0; qo0 = ol[jj].x; ql0 = ol[jj].y; nq++;
+                            }
+                        }
+                    }
                 }
             }
             kb_keep = kb; rc_keep = rc; cnt_keep = cnt;

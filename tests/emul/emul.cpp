@@ -36,6 +36,68 @@ void* emul_create_fasta(u32 k, u32 n, const char** paths) {
     return e;
 }
 void emul_free(void* h) { delete (Emul*)h; }
+
+// The lookup of k_map_grp (bk_kernels.cuh) stepped on the host tables: for every canonical query k-mer the set of
+// (bucket index, off, len) found through group_slots / group_centers / group_buckets must equal what k direct probes
+// of bucket_slots find.  Returns the number of queries that disagree (0 = the grouped form is an exact re-indexing);
+// ~0 if the index has no grouped form.
+u64 emul_group_check(void* h, const u64* queries, u64 n, u32 b0, u32 b1) {
+    const DerivedIndex& d = ((Emul*)h)->d;
+    if (!d.rekeyed || d.group_slots.empty()) return ~0ull;
+    const u32 k = d.k, mid = d.group_mid, lo_bits = 2 * (k - mid);
+    const u64 bmask = (1ull << d.bucket_log2) - 1, gmask = (1ull << d.group_log2) - 1;
+    u64 bad = 0;
+    for (u64 q = 0; q < n; q++) {
+        const u64 kb = queries[q];
+        std::vector<u64> direct, grouped;                       // (index << 40) ^ off ^ (len << 32) is enough to compare sets
+        for (u32 i = b0; i < b1; i++) {
+            const u64 key = ((u64)i << 58) | (kb & ~(3ull << (2 * (k - 1 - i))));
+            u64 hh = hash_slot_host(key, 64 - d.bucket_log2);
+            for (;;) {
+                const BucketSlot& sl = d.bucket_slots[hh];
+                if (sl.key == key) { direct.push_back(((u64)i << 56) | ((u64)sl.len << 32) | sl.off); break; }
+                if (sl.key == ~0ull) break;
+                hh = (hh + 1) & bmask;
+            }
+        }
+        for (u32 sd = 0; sd < 2; sd++) {
+            const u32 i_lo = sd == 0 ? b0 : std::max(b0, mid), i_hi = sd == 0 ? std::min(b1, mid) : b1;
+            if (i_lo >= i_hi) continue;
+            const u64 gk = sd == 0 ? (kb & ((1ull << lo_bits) - 1)) : ((1ull << 62) | (kb >> lo_bits));
+            u64 hh = hash_slot_host(gk, 64 - d.group_log2);
+            u32 first = 0, count = 0;
+            for (;;) {
+                const BucketSlot& sl = d.group_slots[hh];
+                if (sl.key == gk) { first = sl.off; count = sl.len; break; }
+                if (sl.key == ~0ull) break;
+                hh = (hh + 1) & gmask;
+            }
+            const u32 side_lo = sd == 0 ? 0u : mid;
+            const u32 range = ((1u << i_hi) - 1u) & ~((1u << i_lo) - 1u);
+            u32 done = 0;
+            for (u32 c = 0; c < count; c++) {
+                const BucketSlot& cen = d.group_centers[first + c];
+                const u64 x = kb ^ cen.key;
+                u32 cand = cen.len & range;
+                if (x) {
+                    const u64 nz = (x | (x >> 1)) & 0x5555555555555555ull;
+                    cand = (nz & (nz - 1)) ? 0u : cand & (1u << (k - 1 - ((63u - (u32)BK_CLZLL(nz)) >> 1)));
+                }
+                cand &= ~done;
+                done |= cand;
+                for (u32 i = 0; i < 32; i++)
+                    if ((cand >> i) & 1) {
+                        const OffLen& ol = d.group_buckets[cen.off + i - side_lo];
+                        grouped.push_back(((u64)i << 56) | ((u64)ol.len << 32) | ol.off);
+                    }
+            }
+        }
+        std::sort(direct.begin(), direct.end());
+        std::sort(grouped.begin(), grouped.end());
+        if (direct != grouped) bad++;
+    }
+    return bad;
+}
 u64 emul_n_keys(void* h) { return ((Emul*)h)->ix.keys.size(); }
 u64 emul_n_entries(void* h) { return ((Emul*)h)->ix.entries.size(); }
 void emul_export(void* h, u64* keys, u64* off, bk_bucket_info* ent) {

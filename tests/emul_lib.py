@@ -24,7 +24,7 @@ def lib():
             "emul_revcomp": (u64, [u64, C.c_int]), "emul_tau_table": (None, [P]),
             "emul_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),
             "emul_count": (u64, [P, P, P, u64, u32, u32, u32, u32, P, P]), "emul_count_get": (None, [P, P, P]),
-            "emul_noise": (C.c_int, [P, P, u32, P, P]),
+            "emul_noise": (C.c_int, [P, P, u32, P, P]), "emul_group_check": (u64, [P, P, u64, u32, u32]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -64,6 +64,11 @@ class Emul:
         ent = np.zeros(ne, dtype=BUCKETINFO_DTYPE)
         lib().emul_export(self.h, ptr(keys), ptr(off), ptr(ent))
         return keys, off, ent
+
+    def group_check(self, canonical_kmers, b0, b1):
+        """Queries the grouped map tables disagree on with the per-bucket table (0 = exact)."""
+        q = np.ascontiguousarray(canonical_kmers, dtype=np.uint64)
+        return int(lib().emul_group_check(self.h, ptr(q), len(q), b0, b1))
 
     def save(self, path):
         assert lib().emul_save(self.h, path.encode()) == 0

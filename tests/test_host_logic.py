@@ -159,3 +159,41 @@ def test_simulator_is_seeded_and_shaped():
     n = round(50 * 7906 / 300)
     assert len(a[1]) == n + 1 and len(a[0]) == n * 150 and set(np.unique(a[0]).tolist()) <= set(b"ACGT")
     assert len(a[4]["pos"]) == 30 and sorted(set(a[4]["af"].tolist())) == [0.03, 0.05, 0.1, 0.2, 0.4, 1.0]
+
+
+def _canonical(kmers, k):
+    """canonical form (src/lcb.rs:87-95) of an array of k-mer values"""
+    out = np.empty_like(kmers)
+    for i, v in enumerate(kmers.tolist()):
+        r, x = 0, v
+        for _ in range(k):
+            r = (r << 2) | (3 - (x & 3))
+            x >>= 2
+        out[i] = v if v < r else r
+    return out
+
+
+@pytest.mark.parametrize("which,k", [("sars", 21), ("hpv", 21), ("hpv15", 15), ("hpv29", 29)])
+def test_grouped_map_tables_are_an_exact_reindexing(sars_emul, hpv_emul, hpv_fasta, which, k):
+    """group_slots / group_centers / group_buckets (bk_host.h) against k direct probes of the bucket table, with the
+    lookup of k_map_grp stepped on the CPU: reference k-mers, all kinds of neighbours (one substitution anywhere — the
+    case that must hit exactly one bucket —, two substitutions, substitutions at both ends) and random k-mers; the
+    default bucket range, --use-full-kmer and an n_fixed that leaves one side empty."""
+    e = {"sars": sars_emul, "hpv": hpv_emul}.get(which) or Emul.from_fasta(k, [hpv_fasta])
+    genome = sim._CODE[sim.load_genome(sim.SARS4[1] if which == "sars" else sim.HPV16)].astype(np.uint64)
+    rng = np.random.default_rng(11)
+    starts = rng.integers(0, len(genome) - k, size=1500)
+    ref = np.array([int("".join(str(int(b)) for b in genome[s:s + k]), 4) for s in starts], dtype=np.uint64)
+    queries = [ref]
+    for n_sub in (1, 1, 2):
+        q = ref.copy()
+        for _ in range(n_sub):
+            pos = rng.integers(0, k, size=len(q)).astype(np.uint64)
+            q ^= rng.integers(1, 4, size=len(q)).astype(np.uint64) << (np.uint64(2) * pos)
+        queries.append(q)
+    ends = ref ^ np.uint64(1) ^ (np.uint64(2) << np.uint64(2 * (k - 1)))
+    queries += [ends, rng.integers(0, 4 ** k, size=500, dtype=np.uint64)]
+    q = _canonical(np.concatenate(queries), k)
+    for b0, b1 in ((2, k - 3), (0, k), (k // 2, k - k // 2 - 1 + (k // 2 + 1 > k - k // 2 - 1)), (0, 1)):
+        if b0 < b1:
+            assert e.group_check(q, b0, b1) == 0
