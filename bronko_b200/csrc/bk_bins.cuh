@@ -96,7 +96,14 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
     const u32 rounds = (e - s + BK_BIN_ROUND - 1) / BK_BIN_ROUND;
     u32 uniq = 0; u64 total = 0;
     for (u32 r = 0; r < rounds; r++) {
-        for (u32 i = threadIdx.x; i < BK_BIN_SLOTS; i += blockDim.x) { keys[i] = BK_HOLE; cnts[i] = 0; }
+        {                                                                      // clear: 16-byte stores
+            uint4* k4 = reinterpret_cast<uint4*>(keys); uint4* c4 = reinterpret_cast<uint4*>(cnts);
+            const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (u32 i = 0; i < BK_BIN_SLOTS / 2 / 256; i++) k4[i * 256 + threadIdx.x] = ones;
+#pragma unroll
+            for (u32 i = 0; i < BK_BIN_SLOTS / 4 / 256; i++) c4[i * 256 + threadIdx.x] = zero;
+        }
         if (threadIdx.x == 0) s_nocc = 0;
         __syncthreads();
         const u32 n_round = ((e - s + 31) & ~31u);
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                 const u64 key = kq[j];
                 const u64 h = bin_hash(key);
                 bool take = key != BK_HOLE;
-                if (take && rounds > 1) take = ((u32)((h * 0xD6E8FEB86659FD93ull) >> 40) % rounds) == r;
+                if (rounds > 1) take = take && ((u32)((h * 0xD6E8FEB86659FD93ull) >> 40) % rounds) == r;     // (uniform branch: one round is the rule)
                 // a k-mer repeated a million times must not serialise on one shared-memory word: if many lanes hold
                 // the key of the first taking lane, that lane adds for all of them
                 u32 w = 1;
@@ -121,16 +128,27 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                     const u32 same = __ballot_sync(0xFFFFFFFFu, take && key == key0);
                     if (__popc(same) >= 4) { if (lane == first) w = __popc(same); else if ((same >> lane) & 1) take = false; }
                 }
+                bool claimed = false;
+                u32 slot = (u32)(h >> (52 - b.log2p)) & (BK_BIN_SLOTS - 1);
                 if (take) {
-                    u32 slot = (u32)(h >> (52 - b.log2p)) & (BK_BIN_SLOTS - 1);
                     u32 probes = 0;
                     for (;;) {
                         const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot), (unsigned long long)BK_HOLE, (unsigned long long)key);
-                        if (old == BK_HOLE) occ[atomicAdd(&s_nocc, 1u)] = (unsigned short)slot;
+                        claimed = old == BK_HOLE;
                         if (old == BK_HOLE || old == key) { atomicAdd(cnts + slot, w); break; }
                         slot = (slot + 1) & (BK_BIN_SLOTS - 1);
                         if (++probes >= BK_BIN_SLOTS) { *full = 1; break; }
                     }
+                }
+                // the slots this warp claimed join the list of occupied slots: one atomic on the shared counter per warp
+                // (one per claiming lane serialised on that one word)
+                const u32 cm = __ballot_sync(0xFFFFFFFFu, claimed);
+                if (cm) {
+                    const u32 leader = (u32)__ffs(cm) - 1;
+                    u32 base = 0;
+                    if (lane == leader) base = atomicAdd(&s_nocc, (u32)__popc(cm));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (claimed) occ[base + __popc(cm & ((1u << lane) - 1u))] = (unsigned short)slot;
                 }
             }
         }

@@ -92,6 +92,23 @@ struct IndexDev {
 struct bk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    // Stage priorities.  `stream` is the stream the sample's work is currently issued to: stage_stream[0] while reads are
+    // pushed (scan / leftover), [1] for finalize + map, [2] for the score stage, each with a higher CUDA priority than the
+    // one before and chained by an event.  Every big kernel fills the SMs' register files, so with several samples in
+    // flight (one context each) a kernel's CTAs only start as CTAs of other kernels retire, and without priorities the
+    // handful of CTAs of a sample's last, latency-bound stages (the noise chains) queue behind thousands of pending CTAs
+    // of other samples' first stages.  BK_PRIO=0 keeps everything on one stream.
+    cudaStream_t stage_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chain = nullptr;
+    int level = 0, prio_mode = 2;
+    void use_level(int lvl) {
+        if (prio_mode == 0) return;
+        if (prio_mode == 1) lvl = lvl == 2 ? 2 : 0;
+        if (lvl == level) return;
+        cudaEventRecord(ev_chain, stage_stream[level]);
+        cudaStreamWaitEvent(stage_stream[lvl], ev_chain, 0);
+        level = lvl; stream = stage_stream[lvl];
+    }
     std::string err;
     int sm_count = 148;
 
@@ -188,10 +205,19 @@ int bk_create(bk_ctx** out, int device) {
     bk_ctx* ctx = new bk_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);              // numerically lower = higher priority
+    if (const char* e = getenv("BK_PRIO")) ctx->prio_mode = atoi(e);
+    if (prio_greatest >= prio_least) ctx->prio_mode = 0;
+    bool ok = cudaStreamCreateWithPriority(&ctx->stage_stream[0], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    if (ok && ctx->prio_mode != 0)
+        ok = cudaStreamCreateWithPriority(&ctx->stage_stream[1], cudaStreamNonBlocking, std::max(prio_greatest, prio_least - 1)) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&ctx->stage_stream[2], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    ctx->stream = ctx->stage_stream[0];
     for (int i = 0; i < 2 && ok; i++)
         ok = cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->stage_copied[i], cudaEventDisableTiming) == cudaSuccess;
@@ -237,13 +263,14 @@ void bk_destroy(bk_ctx* ctx) {
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (cudaStream_t st : ctx->stage_stream) if (st) cudaStreamDestroy(st);
+    if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
 const char* bk_last_error(bk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-void* bk_stream(bk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* bk_stream(bk_ctx* ctx) { return ctx ? (void*)ctx->stage_stream[0] : nullptr; }     // the stream pushes are issued to
 
 void* bk_host_alloc(uint64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
 void bk_host_free(void* p) { if (p) cudaFreeHost(p); }
@@ -453,6 +480,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     ctx->in_sample = true; ctx->finished = false;
     for (FileState& f : ctx->file) { f.used = false; f.folded = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; f.nov_ub = 0; }
     ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0;
+    ctx->use_level(0);                    // (after the previous sample's last stage, by the event chain)
     ctx->variants.clear();
     memset(&ctx->result, 0, sizeof ctx->result);
     ctx->result.best_genome = -1;
@@ -644,6 +672,7 @@ int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
 
 // stage 1: prefix sum of the difference array + fold onto distinct reference k-mers → idcnt
 static int stage_fold(bk_ctx* ctx, int slot) {
+    ctx->use_level(1);
     FileState& f = ctx->file[slot];
     if (f.folded) return BK_OK;
     const DerivedIndex& d = ctx->I->d;
@@ -736,6 +765,7 @@ static bool can_fuse_map(const bk_ctx* ctx) {
     return ctx->I->d.n_genomes <= 4 && ctx->I->d.rekeyed && !ctx->force_warp_map && ctx->shard_n == 1 && !ctx->no_fused_map;
 }
 static int stage_map_fused(bk_ctx* ctx) {
+    ctx->use_level(1);
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
@@ -764,6 +794,7 @@ static int stage_map_fused(bk_ctx* ctx) {
 
 // stage 3: map_kmers tallies of every file (src/call.rs:1389-1430)
 static int stage_map_stats(bk_ctx* ctx) {
+    ctx->use_level(1);
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
@@ -787,6 +818,7 @@ static int stage_map_stats(bk_ctx* ctx) {
 
 // stage 4: pick_best_genome(_paired) + the selected genome's pileup (src/call.rs:1324-1385)
 static int stage_select_pileup(bk_ctx* ctx) {
+    ctx->use_level(1);
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
@@ -813,6 +845,7 @@ static int stage_select_pileup(bk_ctx* ctx) {
 
 // stage 5: noise baseline + call_variants, read everything back, fill bk_sample_result
 static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
+    ctx->use_level(2);
     const DerivedIndex& d = ctx->I->d;
     const int n_files = n_files_used(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;

@@ -40,7 +40,9 @@ typedef long long i64;
 #define BK_NZ_WARM 256           // warm-up iterations in front of a chunk
 #define BK_NZ_ROUND 256          // iterations per chain round (= threads of the chain block)
 #define BK_NZ_TILE 1024          // iterations of fractions staged per shared-memory tile of a chain block
-#define BK_NZ_SERIAL 8           // iterations executed serially when a round cannot make progress
+#ifndef BK_NZ_SERIAL
+#define BK_NZ_SERIAL 8           // iterations executed serially per batch (after a stop, and for as long as the exponent keeps moving)
+#endif
 #define BK_NZ_PAD_LO 100         // zero positions in front of every sequence in the fraction array
 #define BK_NZ_PAD (BK_NZ_PAD_LO + 150)   // total padding positions per sequence
 #define BK_NZ_MASK52 0xFFFFFFFFFFFFFull
@@ -326,7 +328,8 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     const u32 pos_total = sq.len + BK_NZ_PAD;                                   // positions present in mafp
     double s = 0.0;
     u32 i0 = 0, tile_lo = 0, tile_hi = 0;                                       // tile covers iterations [tile_lo, tile_hi)
-    u32 round = 0, serial_left = 0, width = BK_NZ_ROUND;                        // width: iterations tried per round
+    u32 round = 0, serial_left = 0;
+    const u32 width = BK_NZ_ROUND;                                              // iterations tried per round
     u32 st_rounds = 0, st_stops = 0, st_serial = 0;
     const long long t_begin = clock64();
     while (i0 < iters) {
@@ -345,14 +348,18 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         const u32 ef = (u32)(sb >> 52);
         if (ef < 64u || ef >= 0x7FFu || serial_left) {
             // s is zero / subnormal / negative / non-finite, or rounds stopped making progress: like the reference
+            // A serial iteration costs ~1/30 of a round, and a sum that hovers at a binade border crosses it in
+            // nearly every iteration for tens to hundreds of iterations: stay serial for as long as the exponent
+            // keeps moving (a round would be stopped by its first operations again).
             const u32 n_ser = min(tile_hi - i0, (u32)BK_NZ_SERIAL);
+            bool moved = false;
             for (u32 it = 0; it < n_ser; it++) {
 #pragma unroll
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
+                for (u32 q = 0; q < 6; q++) { s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q)); moved = moved || (u32)(nz_b(s) >> 52) != ef; }
                 if (tid == 0) snap[i0 + it] = s;
             }
             i0 += n_ser; st_serial += n_ser;
-            serial_left = 0;
+            serial_left = moved ? 1u : 0u;
             continue;
         }
         const u32 buf = round & 1;
@@ -420,15 +427,14 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         }
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
-        if (n_ok == total_ops) { i0 += n_it; width = BK_NZ_ROUND; continue; }
+        if (n_ok == total_ops) { i0 += n_it; continue; }
         // the operation that ended the accepted prefix and the rest of its iteration, in real FP64
         st_stops++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
-        width = 32;                                    // stops come in bursts (the sum hovers at a binade border): one warp
-        if (ib < 4) serial_left = 1;
+        serial_left = 1;                               // stops come in bursts (the sum hovers at a binade border)
     }
     if (tid == 0 && nv.stats) {
         atomicAdd(nv.stats + 2, st_rounds); atomicAdd(nv.stats + 3, st_stops); atomicAdd(nv.stats + 4, st_serial);

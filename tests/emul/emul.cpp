@@ -205,18 +205,20 @@ void emul_count_get(void* h, u64* kmers, u32* counts) {
 template <bool SQUARE, class LdM>
 static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
     double s = 0.0;
-    u32 i0 = 0, serial_left = 0, width = BK_NZ_ROUND;
+    u32 i0 = 0, serial_left = 0;
+    const u32 width = BK_NZ_ROUND;
     while (i0 < iters) {
         const u32 n_it = std::min<u32>(width, iters - i0);
         const u64 sb = nz_b(s);
         const u32 ef = (u32)(sb >> 52);
         if (ef < 64u || ef >= 0x7FFu || serial_left) {
             const u32 n_ser = std::min<u32>(iters - i0, BK_NZ_SERIAL);
+            bool moved = false;
             for (u32 it = 0; it < n_ser; it++) {
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
+                for (u32 q = 0; q < 6; q++) { s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q)); moved = moved || (u32)(nz_b(s) >> 52) != ef; }
                 snap[i0 + it] = s;
             }
-            i0 += n_ser; stats[4] += n_ser; serial_left = 0;
+            i0 += n_ser; stats[4] += n_ser; serial_left = moved ? 1 : 0;
             continue;
         }
         stats[2]++;
@@ -251,14 +253,13 @@ static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
         }
         for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz_value(ef, T[t * 6 + 5]);
         if (n_ok > 0) s = nz_value(ef, T[n_ok - 1]);
-        if (n_ok == n_it * 6) { i0 += n_it; width = BK_NZ_ROUND; continue; }
+        if (n_ok == n_it * 6) { i0 += n_it; continue; }
         stats[3]++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         snap[i0 + ib] = s;
         i0 += ib + 1;
-        width = 32;
-        if (ib < 4) serial_left = 1;
+        serial_left = 1;
     }
 }
 
