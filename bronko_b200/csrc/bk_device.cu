@@ -504,6 +504,12 @@ static CountView make_count_view(bk_ctx* ctx, FileState& f) {
     return v;
 }
 
+// CTAs per SM of the grid-stride kernels (leftover, map).  More and shorter-lived CTAs let the CTAs of higher-priority
+// stages of other samples in flight start sooner (a CTA slot only frees when a CTA retires).
+#ifndef BK_STRIDE_WAVES
+#define BK_STRIDE_WAVES 8
+#endif
+
 // Developer builds only (tools/build_variant.sh ... -DBK_ABLATE): BK_ABLATE=scan,leftover,bins,map,noise skips the kernels of a
 // stage so that its marginal cost with several samples in flight can be measured.  Results are garbage; the product
 // build compiles this to `false`.
@@ -580,8 +586,8 @@ static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_o
     BK_CUDA(cudaGetLastError());
     sp = ctx->span_begin(ST_LEFTOVER);
     if (ablated("leftover")) {}
-    else if (f.list_mode) k_leftover<1><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
-    else k_leftover<0><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    else if (f.list_mode) k_leftover<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    else k_leftover<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
@@ -780,8 +786,8 @@ static int stage_map_fused(bk_ctx* ctx) {
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
         if (ablated("map")) {}
-        else if (m.gslots) k_map_grp<2><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
-        else k_map_small<2, 1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        else if (m.gslots) k_map_grp<2><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+        else k_map_small<2, 1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
         ctx->launches++;
     }
     k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
@@ -806,9 +812,9 @@ static int stage_map_stats(bk_ctx* ctx) {
         FileState& fs = ctx->file[f];
         BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && m.gslots) k_map_grp<0><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * 8, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        if (small_db && m.gslots) k_map_grp<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        else if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+        else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
         ctx->launches++;
     }
     ctx->span_end(sp);
@@ -833,9 +839,9 @@ static int stage_select_pileup(bk_ctx* ctx) {
     for (int f = 0; f < n_files; f++) {
         FileState& fs = ctx->file[f];
         const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && m.gslots) k_map_grp<1><<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * 8, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        if (small_db && m.gslots) k_map_grp<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        else if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+        else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
         ctx->launches++;
     }
     ctx->span_end(sp);
