@@ -128,27 +128,16 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                     const u32 same = __ballot_sync(0xFFFFFFFFu, take && key == key0);
                     if (__popc(same) >= 4) { if (lane == first) w = __popc(same); else if ((same >> lane) & 1) take = false; }
                 }
-                bool claimed = false;
-                u32 slot = (u32)(h >> (52 - b.log2p)) & (BK_BIN_SLOTS - 1);
                 if (take) {
+                    u32 slot = (u32)(h >> (52 - b.log2p)) & (BK_BIN_SLOTS - 1);
                     u32 probes = 0;
                     for (;;) {
                         const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot), (unsigned long long)BK_HOLE, (unsigned long long)key);
-                        claimed = old == BK_HOLE;
+                        if (old == BK_HOLE) occ[atomicAdd(&s_nocc, 1u)] = (unsigned short)slot;     // (one atomic per warp through a ballot: measured slower)
                         if (old == BK_HOLE || old == key) { atomicAdd(cnts + slot, w); break; }
                         slot = (slot + 1) & (BK_BIN_SLOTS - 1);
                         if (++probes >= BK_BIN_SLOTS) { *full = 1; break; }
                     }
-                }
-                // the slots this warp claimed join the list of occupied slots: one atomic on the shared counter per warp
-                // (one per claiming lane serialised on that one word)
-                const u32 cm = __ballot_sync(0xFFFFFFFFu, claimed);
-                if (cm) {
-                    const u32 leader = (u32)__ffs(cm) - 1;
-                    u32 base = 0;
-                    if (lane == leader) base = atomicAdd(&s_nocc, (u32)__popc(cm));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    if (claimed) occ[base + __popc(cm & ((1u << lane) - 1u))] = (unsigned short)slot;
                 }
             }
         }
