@@ -27,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+OUT = sys.stdout
 METRIC = "read_bases_per_sec_kmer_to_pileup"
 UNIT = "bases/s"
 
@@ -128,10 +129,15 @@ def run_reference(args, rank, world):
         "config": {"workload": "C2: SARS-CoV-2 single sample vs 4-strain k=21 db, 150bp PE, bounded sample at %dx" % sample_depth},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=OUT, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON: everything libraries print to fd 1 (NCCL's version banner under
+    # torchrun, ...) is sent to stderr, and the line is written to the saved descriptor
+    global OUT
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -289,8 +295,8 @@ def main():
     alg_bytes = (n_bases + 4 * (n_reads + 2)) / 2.0            # per launch: one file's bases + u32 offsets
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch at this workload, from the committed
-    # `ncu --set full` capture (profiles/r01_ncu_full_summary.csv: 158.04 MB + 5.32 MB); other depths: not captured
-    traffic = 163.35e6 if args.depth == 10000 else None
+    # `ncu --set full` capture (profiles/r01_ncu_full_summary.csv: 158.05 MB + 4.95 / 5.42 MB, two launches); other depths: not captured
+    traffic = 163.2e6 if args.depth == 10000 else None
     alone_total = max(alone.get("total_ms", 0.0), 1e-9)
     roofline = {"bound": "hbm", "kernel": "k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -331,7 +337,7 @@ def main():
                        "parallelism": "sample-per-GPU x%d, no collective" % world,
                        "samples_in_flight_per_gpu": S},
             "latency_ms_single_sample": latency_ms,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(stage_acc["launches"]),
             "roofline": roofline,
             "roofline_path": {"alg_bytes_per_step": 1.03 * n_bases, "achieved_gbs": 1.03 * n_bases * world / (ms_step * 1e-3) / 1e9,
@@ -341,7 +347,7 @@ def main():
             "stage_ms_per_step_in_flight": stages, "stage_ms_single_sample": alone,
             "result_check": {"best_genome": int(res.best_genome), "n_variants": int(len(res.variants))},
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=OUT, flush=True)
     for c in ctxs:
         c.close()
     if dist is not None:
