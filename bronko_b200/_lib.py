@@ -77,6 +77,11 @@ SIGNATURES = {
     "bk_reads_push": (C.c_int, [P, C.c_int, P, P, u64]),
     "bk_reads_push_device": (C.c_int, [P, C.c_int, P, P, u64, u64, u32]),
     "bk_reads_push_fastq": (C.c_int, [P, C.c_int, C.c_char_p]),
+    "bk_fastq_decode": (C.c_int, [C.c_char_p, C.POINTER(P), C.c_char_p, u64]),
+    "bk_reads_n_chunks": (u64, [P]),
+    "bk_reads_chunk": (C.c_int, [P, u64, C.POINTER(P), C.POINTER(P), C.POINTER(u64), C.POINTER(u64)]),
+    "bk_reads_push_decoded": (C.c_int, [P, C.c_int, P]),
+    "bk_reads_free": (None, [P]),
     "bk_sample_finish": (C.c_int, [P, C.POINTER(SampleResult)]),
     "bk_sample_variants": (C.c_int, [P, P, u64]),
     "bk_sample_genome_stats": (C.c_int, [P, C.c_int, P]),

@@ -59,6 +59,41 @@ def clean_sample_id(path):
     return buf.value.decode()
 
 
+class DecodedReads:
+    """One FASTQ(.gz) file decoded on the host (bk_fastq_decode: no context, no GPU, thread-safe — ctypes drops the
+    GIL, so files of the next samples can be decoded on other threads while the GPU works)."""
+
+    def __init__(self, path):
+        self._lib = L.lib()
+        h, err = C.c_void_p(), C.create_string_buffer(512)
+        rc = self._lib.bk_fastq_decode(path.encode(), C.byref(h), err, 512)
+        if rc != 0:
+            raise BkError(rc, err.value.decode())
+        self.h = h
+
+    def chunks(self):
+        """[(bases uint8 view, offsets uint32 view)] — valid until close()."""
+        out = []
+        for i in range(self._lib.bk_reads_n_chunks(self.h)):
+            b, o, nr, nb = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+            self._lib.bk_reads_chunk(self.h, i, C.byref(b), C.byref(o), C.byref(nr), C.byref(nb))
+            bases = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint8)), shape=(max(nb.value, 1),))[:nb.value]
+            off = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint32)), shape=(nr.value + 1,))
+            out.append((bases, off))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.bk_reads_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Bronko:
     """One GPU context (bk_ctx).  Samples are processed sequentially per context."""
 
@@ -162,6 +197,9 @@ class Bronko:
 
     def push_fastq(self, file_slot, path):
         self._check(self._lib.bk_reads_push_fastq(self.h, file_slot, path.encode()))
+
+    def push_decoded(self, file_slot, reads: DecodedReads):
+        self._check(self._lib.bk_reads_push_decoded(self.h, file_slot, reads.h))
 
     def finish(self):
         res = L.SampleResult()

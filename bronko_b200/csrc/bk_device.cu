@@ -658,20 +658,34 @@ int bk_reads_push(bk_ctx* ctx, int slot, const uint8_t* bases, const uint32_t* r
     return BK_OK;
 }
 
+int bk_reads_push_decoded(bk_ctx* ctx, int slot, const bk_reads* reads) {
+    int rc = check_push(ctx, slot);
+    if (rc) return rc;
+    if (!reads) return ctx->fail(BK_ERR_ARG, "bk_reads_push_decoded: null reads");
+    const uint64_t n_chunks = bk_reads_n_chunks(reads);
+    bool any = false;
+    for (uint64_t i = 0; i < n_chunks; i++) {
+        const uint8_t* bases; const uint32_t* off; uint64_t n_reads, n_bases;
+        bk_reads_chunk(reads, i, &bases, &off, &n_reads, &n_bases);
+        if (n_reads == 0) continue;
+        any = true;
+        if ((rc = bk_reads_push(ctx, slot, bases, off, n_reads))) return rc;
+        BK_CUDA(cudaStreamSynchronize(ctx->stream));    // pageable source: the caller may free `reads` when this returns
+    }
+    if (!any) return file_prepare(ctx, slot, 0);          // an empty file is still a file of the sample
+    return BK_OK;
+}
+
 int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
     int rc = check_push(ctx, slot);
     if (rc) return rc;
     if (!path) return ctx->fail(BK_ERR_ARG, "bk_reads_push_fastq: null path");
-    std::vector<HostReads> chunks;
-    std::string err;
-    if (!fastq_read(path, chunks, 1ull << 30, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
-    for (HostReads& c : chunks) {
-        c.bases.resize(c.bases.size() + 64, '*');       // readable slack past the last read
-        if ((rc = bk_reads_push(ctx, slot, c.bases.data(), c.off.data(), c.off.size() - 1))) return rc;
-        BK_CUDA(cudaStreamSynchronize(ctx->stream));    // pageable source: the driver staged it, buffers die with `chunks`
-    }
-    if (chunks.empty() || (chunks.size() == 1 && chunks[0].off.size() == 1)) return file_prepare(ctx, slot, 0);
-    return BK_OK;
+    bk_reads* reads = nullptr;
+    char err[512] = "";
+    if (bk_fastq_decode(path, &reads, err, sizeof err) != BK_OK) return ctx->fail(BK_ERR_IO, "%s", err);
+    rc = bk_reads_push_decoded(ctx, slot, reads);
+    bk_reads_free(reads);
+    return rc;
 }
 
 // ---- stages of bk_sample_finish (also driven one by one in the read-sharded mode) ---------------

@@ -3,6 +3,8 @@
 // and the Thompson-tau table (reference src/call.rs:922-929; statrs 0.18 StudentsT::inverse_cdf).
 #include "bk_host.h"
 
+#include <zlib.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -10,33 +12,55 @@
 
 namespace bk {
 
+// Streaming decode: the file is inflated block by block (gzread also passes plain text through) and only the
+// sequence lines (line index 1 of every 4-line record) are kept; a line may span blocks.  '\r' before the line end is
+// dropped; a last line without '\n' counts.
 bool fastq_read(const std::string& path, std::vector<HostReads>& chunks, u64 max_chunk_bases, std::string& err) {
-    std::string txt;
-    if (!slurp_maybe_gz(path, txt)) { err = "Failed to read reads file: " + path; return false; }
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) { err = "Failed to read reads file: " + path; return false; }
+    gzbuffer(g, 1 << 20);
     chunks.clear();
     chunks.emplace_back();
     chunks.back().off.push_back(0);
-    size_t pos = 0, line = 0;
-    const size_t n = txt.size();
-    while (pos < n) {
-        const char* nl = (const char*)memchr(txt.data() + pos, '\n', n - pos);
-        size_t eol = nl ? (size_t)(nl - txt.data()) : n;
-        size_t le = eol;
-        if (le > pos && txt[le - 1] == '\r') le--;
-        if ((line & 3) == 1) {
-            const u64 len = le - pos;
-            if (chunks.back().bases.size() + len > max_chunk_bases && chunks.back().off.size() > 1) {
-                chunks.emplace_back();
-                chunks.back().off.push_back(0);
-            }
-            HostReads& c = chunks.back();
-            c.bases.insert(c.bases.end(), txt.begin() + pos, txt.begin() + le);
-            c.off.push_back((u32)c.bases.size());
-            if (len > c.max_len) c.max_len = (u32)len;
+    std::vector<char> buf(8u << 20);
+    std::string carry;                        // the part of a sequence line that ended the previous block
+    u64 line = 0;
+    auto end_read = [&](const char* p, size_t len) {             // a complete sequence line (without its '\n')
+        const char* q = p; size_t n = len;
+        if (!carry.empty()) { carry.append(p, len); q = carry.data(); n = carry.size(); }
+        if (n > 0 && q[n - 1] == '\r') n--;
+        if (chunks.back().bases.size() + n > max_chunk_bases && chunks.back().off.size() > 1) {
+            chunks.emplace_back();
+            chunks.back().off.push_back(0);
         }
-        line++;
-        pos = eol + 1;
+        HostReads& c = chunks.back();
+        c.bases.insert(c.bases.end(), (const u8*)q, (const u8*)q + n);
+        c.off.push_back((u32)c.bases.size());
+        if (n > c.max_len) c.max_len = (u32)n;
+        carry.clear();
+    };
+    int got;
+    bool open_line = false;                   // bytes of an unterminated line have been seen
+    while ((got = gzread(g, buf.data(), (unsigned)buf.size())) > 0) {
+        const char* p = buf.data();
+        const char* const e = p + got;
+        while (p < e) {
+            const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) {                        // the line continues in the next block
+                if ((line & 3) == 1) carry.append(p, (size_t)(e - p));
+                open_line = true;
+                break;
+            }
+            if ((line & 3) == 1) end_read(p, (size_t)(nl - p));
+            line++;
+            open_line = false;
+            p = nl + 1;
+        }
     }
+    const bool ok = got == 0;
+    gzclose(g);
+    if (!ok) { err = "Failed to read reads file: " + path; return false; }
+    if (open_line && (line & 3) == 1) end_read("", 0);           // last line without a newline
     return true;
 }
 
@@ -203,3 +227,39 @@ void tau_table(double* tab301) {
 }
 
 }  // namespace bk
+
+// ---- the host decode stage of the C ABI (include/bronko_b200.h): no context, no GPU, thread-safe ----------------
+struct bk_reads { std::vector<bk::HostReads> chunks; };
+
+extern "C" {
+
+int bk_fastq_decode(const char* path, bk_reads** out, char* err, uint64_t err_cap) {
+    if (out) *out = nullptr;
+    if (!path || !out) return BK_ERR_ARG;
+    bk_reads* r = new bk_reads();
+    std::string e;
+    if (!bk::fastq_read(path, r->chunks, 1ull << 30, e)) {
+        if (err && err_cap) { snprintf(err, (size_t)err_cap, "%s", e.c_str()); }
+        delete r;
+        return BK_ERR_IO;
+    }
+    for (bk::HostReads& c : r->chunks) c.bases.resize(c.bases.size() + 64, '*');      // readable slack past the last read
+    *out = r;
+    return BK_OK;
+}
+
+uint64_t bk_reads_n_chunks(const bk_reads* r) { return r ? r->chunks.size() : 0; }
+
+int bk_reads_chunk(const bk_reads* r, uint64_t i, const uint8_t** bases, const uint32_t** read_off, uint64_t* n_reads, uint64_t* n_bases) {
+    if (!r || i >= r->chunks.size()) return BK_ERR_ARG;
+    const bk::HostReads& c = r->chunks[i];
+    if (bases) *bases = c.bases.data();
+    if (read_off) *read_off = c.off.data();
+    if (n_reads) *n_reads = c.off.size() - 1;
+    if (n_bases) *n_bases = c.off.back();
+    return BK_OK;
+}
+
+void bk_reads_free(bk_reads* r) { delete r; }
+
+}  // extern "C"

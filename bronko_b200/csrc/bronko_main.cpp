@@ -12,6 +12,8 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <deque>
+#include <future>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -224,10 +226,35 @@ static void write_counts_txt(bk_ctx* ctx, int slot, uint32_t k, const std::strin
     fclose(f);
 }
 
-static OutputInfo process_sample(bk_ctx* ctx, const Args& a, const bk_params& p, const std::string& r1, const std::string* r2) {
+// The host decode stage (FASTQ(.gz) → bases; KMC's reader in the reference).  gzip inflate runs at a few hundred MB/s
+// per thread and the GPU path at hundreds of GB/s, so the files of the next samples are decoded on other threads
+// while the GPU works on this one: R1 and R2 of a sample concurrently, up to `lookahead` samples ahead (-t bounds it).
+struct DecodedSample {
+    bk_reads* r[2] = {nullptr, nullptr};
+    std::string err;
+};
+static bk_reads* decode_file(const std::string& path, std::string* err) {
+    bk_reads* r = nullptr;
+    char msg[512] = "";
+    if (bk_fastq_decode(path.c_str(), &r, msg, sizeof msg) != 0) { *err = msg[0] ? msg : ("Failed to read reads file: " + path); return nullptr; }
+    return r;
+}
+static DecodedSample decode_sample(std::string r1, std::string r2, bool paired) {
+    DecodedSample d;
+    std::string e2;
+    std::future<bk_reads*> second;
+    if (paired) second = std::async(std::launch::async, decode_file, r2, &e2);
+    d.r[0] = decode_file(r1, &d.err);
+    if (paired) { d.r[1] = second.get(); if (d.err.empty()) d.err = e2; }
+    return d;
+}
+
+static OutputInfo process_sample(bk_ctx* ctx, const Args& a, const bk_params& p, const std::string& r1, const std::string* r2, DecodedSample d) {
+    if (!d.err.empty()) die(d.err);
     CK(bk_sample_begin(ctx, &p));
-    CK(bk_reads_push_fastq(ctx, 0, r1.c_str()));
-    if (r2) CK(bk_reads_push_fastq(ctx, 1, r2->c_str()));
+    CK(bk_reads_push_decoded(ctx, 0, d.r[0]));
+    if (r2) CK(bk_reads_push_decoded(ctx, 1, d.r[1]));
+    bk_reads_free(d.r[0]); bk_reads_free(d.r[1]);
     bk_sample_result res;
     const int rc = bk_sample_finish(ctx, &res);
     if (rc == BK_ERR_NO_GENOME) die("Unable to pick a best genome");       // src/call.rs:230-233, 320-323
@@ -339,13 +366,24 @@ static int run_call(const Args& a) {
     p.min_af = a.min_af; p.strand_balance_ratio = a.balance_ratio; p.strand_odds_max = a.strand_odds; p.variant_multiplier = a.noise_multiplier;
     p.table_log2 = (uint32_t)a.table_log2;
     std::vector<OutputInfo> infos;
-    for (const std::string& r : a.reads) {                            // src/call.rs:213
-        info("Processing " + r);
-        infos.push_back(process_sample(ctx, a, p, r, nullptr));
-    }
-    for (size_t i = 0; i < a.first_pairs.size(); i++) {               // src/call.rs:298
-        info("Processing paired reads " + a.first_pairs[i] + ", " + a.second_pairs[i]);
-        infos.push_back(process_sample(ctx, a, p, a.first_pairs[i], &a.second_pairs[i]));
+    // samples in the reference's order (single-end files, then pairs: src/call.rs:213, 298), decoded ahead of the GPU
+    struct Job { std::string r1, r2; bool paired; };
+    std::vector<Job> jobs;
+    for (const std::string& r : a.reads) jobs.push_back(Job{r, "", false});
+    for (size_t i = 0; i < a.first_pairs.size(); i++) jobs.push_back(Job{a.first_pairs[i], a.second_pairs[i], true});
+    const size_t lookahead = (size_t)std::min<long>(3, std::max<long>(0, a.threads / 2 - 1));    // two decode threads per sample in the window
+    std::deque<std::future<DecodedSample>> ahead;
+    size_t next = 0;
+    for (size_t i = 0; i < jobs.size(); i++) {
+        while (next < jobs.size() && ahead.size() < lookahead + 1) {
+            ahead.push_back(std::async(std::launch::async, decode_sample, jobs[next].r1, jobs[next].r2, jobs[next].paired));
+            next++;
+        }
+        const Job& j = jobs[i];
+        if (j.paired) info("Processing paired reads " + j.r1 + ", " + j.r2); else info("Processing " + j.r1);
+        DecodedSample d = ahead.front().get();
+        ahead.pop_front();
+        infos.push_back(process_sample(ctx, a, p, j.r1, j.paired ? &j.r2 : nullptr, d));
     }
     info("Printing overview");
     print_output_info(a, infos);

@@ -160,6 +160,18 @@ int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
                          uint32_t max_read_len);
 /* Decode a FASTQ(.gz) file on the host (KMC reader contract) and push it. */
 int bk_reads_push_fastq(bk_ctx* ctx, int file_slot, const char* fastq_path);
+/* The host decode stage on its own — the step in front of the path (KMC's FASTQ reader inside count_kmers_kmc,
+ * src/call.rs:1166-1181; contract in SURVEY.md Appendix B: 4-line records, only the sequence line is used, gz detected).
+ * Needs no context and no GPU and is thread-safe: decode the files of the next samples on other host threads while
+ * the GPU works (inflate runs at a few hundred MB/s per thread, the path at hundreds of GB/s).  Decoded reads are
+ * chunks of at most 2^30 bases (offsets are u32), each with 64 readable bytes past its last base. */
+typedef struct bk_reads bk_reads;
+int bk_fastq_decode(const char* fastq_path, bk_reads** out, char* err, uint64_t err_cap);
+uint64_t bk_reads_n_chunks(const bk_reads* reads);
+int bk_reads_chunk(const bk_reads* reads, uint64_t i, const uint8_t** bases, const uint32_t** read_off,
+                   uint64_t* n_reads, uint64_t* n_bases);
+int bk_reads_push_decoded(bk_ctx* ctx, int file_slot, const bk_reads* reads);   /* every chunk, then returns */
+void bk_reads_free(bk_reads* reads);
 /* map_kmers ×n_files → pick_best_genome(_paired) → call_variants (src/call.rs:224-268 / 314-360).
  * Returns BK_ERR_NO_GENOME where the reference exits with "Unable to pick a best genome". */
 int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out);

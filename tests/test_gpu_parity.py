@@ -398,3 +398,30 @@ def test_device_resident_push_matches_host_push(ctx_sars):
         c.push_device(slot, tb.data_ptr(), to.data_ptr(), n, nb, 150)
     s = c.finish()
     assert s.variants.tobytes() == hv.tobytes() and (s.pileup() == hp).all()
+
+
+def test_decoded_fastq_push_matches_host_push(ctx_sars, tmp_path):
+    """bk_fastq_decode + bk_reads_push_decoded (and bk_reads_push_fastq on top of them) against pushing the same
+    reads from numpy buffers: gz and plain files, one of them with CRLF line ends."""
+    import bronko_b200
+    from test_gpu_fullsize import assert_snapshots_equal, snapshot
+    c, _ = ctx_sars
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[3]), 300, sim.SEED0 + 91)
+    f1, f2 = str(tmp_path / "d_R1.fastq.gz"), str(tmp_path / "d_R2.fastq")
+    sim.write_fastq(f1, r1, o1, "d", 1)
+    sim.write_fastq(f2, r2, o2, "d", 2)
+    with open(f2, "rb") as f:
+        crlf = f.read().replace(b"\n", b"\r\n")
+    with open(f2, "wb") as f:
+        f.write(crlf)
+    base = snapshot(c.call_sample([(r1, o1), (r2, o2)]), 2)
+    d1, d2 = bronko_b200.DecodedReads(f1), bronko_b200.DecodedReads(f2)
+    c.begin()
+    c.push_decoded(0, d1)
+    c.push_decoded(1, d2)
+    d1.close(); d2.close()
+    assert_snapshots_equal(base, snapshot(c.finish(), 2))
+    c.begin()
+    c.push_fastq(0, f1)
+    c.push_fastq(1, f2)
+    assert_snapshots_equal(base, snapshot(c.finish(), 2))
