@@ -4,8 +4,11 @@
 #include "bk_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <thread>
 #include <zlib.h>
 
 namespace bk {
@@ -78,8 +81,49 @@ struct Sink {
 };
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// host threads: a 200-strain database is 1.25e8 (bucket id, entry) pairs — one stable sort of them on one thread was
+// 20 of the 28 s of building or loading it
+// ---------------------------------------------------------------------------------------------
+static unsigned host_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::min(16u, std::max(1u, hw));
+}
+// fn(i) for i in [0, n) on up to host_threads() threads (dynamic distribution)
+static void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+    const unsigned T = (unsigned)std::min<size_t>(host_threads(), n);
+    if (T <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; t++)
+        th.emplace_back([&] { for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
+    for (std::thread& t : th) t.join();
+}
+// stable sort: chunks sorted in parallel, then rounds of pairwise std::merge (stable: ties keep the left run first)
+template <class T, class Less>
+static void parallel_stable_sort(std::vector<T>& v, Less less) {
+    const size_t n = v.size();
+    unsigned P = host_threads();
+    while (P & (P - 1)) P &= P - 1;                           // power of two
+    if (n < (1u << 20) || P == 1) { std::stable_sort(v.begin(), v.end(), less); return; }
+    std::vector<size_t> cut(P + 1);
+    for (unsigned i = 0; i <= P; i++) cut[i] = n / P * i + std::min<size_t>(i, n % P);
+    parallel_for(P, [&](size_t i) { std::stable_sort(v.begin() + cut[i], v.begin() + cut[i + 1], less); });
+    std::vector<T> tmp(n);
+    T* src = v.data();
+    T* dst = tmp.data();
+    for (unsigned width = 1; width < P; width *= 2) {
+        parallel_for(P / (2 * width), [&](size_t j) {
+            const size_t a = cut[2 * width * j], m = cut[2 * width * j + width], b = cut[2 * width * j + 2 * width];
+            std::merge(src + a, src + m, src + m, src + b, dst + a, less);
+        });
+        std::swap(src, dst);
+    }
+    if (src != v.data()) v.swap(tmp);
+}
+
 void index_from_pairs(HostIndex& ix, std::vector<KeyedEntry>& pairs) {
-    std::stable_sort(pairs.begin(), pairs.end(), [](const KeyedEntry& a, const KeyedEntry& b) { return a.key < b.key; });
+    parallel_stable_sort(pairs, [](const KeyedEntry& a, const KeyedEntry& b) { return a.key < b.key; });
     ix.keys.clear(); ix.entry_off.clear(); ix.entries.clear();
     ix.entries.reserve(pairs.size());
     for (size_t i = 0; i < pairs.size(); i++) {
@@ -94,21 +138,26 @@ bool bkdb_decode(const u8* data, u64 n, HostIndex& ix, std::string& err) {
     ix = HostIndex();
     ix.k = (u32)c.varint();
     const u64 n_keys = c.varint();
-    std::vector<KeyedEntry> pairs;
-    pairs.reserve(n_keys + n_keys / 8);
+    // the file holds the map in hash-table order: entries are kept as they come and only one record per key is sorted
+    struct KeyRec { u64 key; u64 first; u64 count; };
+    std::vector<KeyRec> recs;
+    std::vector<bk_bucket_info> raw;
+    recs.reserve((size_t)std::min<u64>(n_keys, n / 2));
+    raw.reserve((size_t)std::min<u64>(n_keys + n_keys / 8, n / 5));
     for (u64 i = 0; i < n_keys && c.ok; i++) {
         const u64 key = c.varint();
         const u64 m = c.varint();
+        recs.push_back(KeyRec{key, (u64)raw.size(), 0});
         for (u64 j = 0; j < m && c.ok; j++) {
-            KeyedEntry ke; memset(&ke, 0, sizeof ke);
-            ke.key = key;
-            ke.e.file_id = (u16)c.varint();
-            ke.e.seq_id = c.byte();
-            ke.e.location = (u32)c.varint();
-            ke.e.idx = c.byte();
-            ke.e.canonical = c.byte();
-            pairs.push_back(ke);
+            bk_bucket_info e; memset(&e, 0, sizeof e);
+            e.file_id = (u16)c.varint();
+            e.seq_id = c.byte();
+            e.location = (u32)c.varint();
+            e.idx = c.byte();
+            e.canonical = c.byte();
+            raw.push_back(e);
         }
+        recs.back().count = (u64)raw.size() - recs.back().first;
     }
     const u64 n_files = c.varint();
     for (u64 f = 0; f < n_files && c.ok; f++) {
@@ -132,8 +181,16 @@ bool bkdb_decode(const u8* data, u64 n, HostIndex& ix, std::string& err) {
     }
     ix.meta_k = c.varint();
     if (!c.ok) { err = "truncated or malformed .bkdb"; return false; }
-    // a map never holds one key twice, so a stable sort by key keeps each key's entry order
-    index_from_pairs(ix, pairs);
+    // a map never holds one key twice; should a file do so anyway, the stable sort keeps the file's order and the
+    // entries of equal keys are joined (what sorting the (key, entry) pairs themselves would give)
+    parallel_stable_sort(recs, [](const KeyRec& a, const KeyRec& b) { return a.key < b.key; });
+    ix.keys.clear(); ix.entry_off.clear(); ix.entries.clear();
+    ix.entries.reserve(raw.size());
+    for (size_t i = 0; i < recs.size(); i++) {
+        if (i == 0 || recs[i].key != recs[i - 1].key) { ix.keys.push_back(recs[i].key); ix.entry_off.push_back(ix.entries.size()); }
+        ix.entries.insert(ix.entries.end(), raw.begin() + recs[i].first, raw.begin() + recs[i].first + recs[i].count);
+    }
+    ix.entry_off.push_back(ix.entries.size());
     return true;
 }
 
@@ -213,12 +270,16 @@ static std::string path_stem(const std::string& path) {
 bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIndex& ix, std::string& err) {
     ix = HostIndex();
     ix.k = k; ix.meta_k = k;
-    std::vector<KeyedEntry> pairs;
-    u64 ids[32];
-    for (size_t file_id = 0; file_id < paths.size(); file_id++) {
+    // one file = one genome (build.rs:145-231): the files are parsed and their (bucket id, entry) pairs generated on
+    // several threads, then joined in file order — the order the reference merges its per-file maps in (223-227)
+    struct FileOut { HostGenome g; std::vector<KeyedEntry> pairs; bool ok = true; };
+    std::vector<FileOut> outs(paths.size());
+    parallel_for(paths.size(), [&](size_t file_id) {
+        FileOut& o = outs[file_id];
+        u64 ids[32];
         std::string txt;
-        if (!slurp_maybe_gz(paths[file_id], txt)) { err = "Failed to parse fasta file: " + paths[file_id]; return false; }
-        HostGenome g;
+        if (!slurp_maybe_gz(paths[file_id], txt)) { o.ok = false; return; }
+        HostGenome& g = o.g;
         g.name = path_stem(paths[file_id]);
         size_t pos = 0;
         while (pos < txt.size()) {
@@ -242,6 +303,7 @@ bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIn
             if (L >= k) {
                 const u64 kmask = (1ull << (2 * k)) - 1;
                 u64 fwd = 0;
+                o.pairs.reserve(o.pairs.size() + (size_t)(L - k + 1) * k);
                 for (u64 i = 0; i < L; i++) {
                     fwd = ((fwd << 2) | nt_to_bits_host(q.bases[i])) & kmask;
                     if (i + 1 < k) continue;
@@ -254,13 +316,24 @@ bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIn
                         ke.key = ids[j];
                         ke.e.file_id = (u16)file_id; ke.e.seq_id = seq_id; ke.e.location = (u32)start;
                         ke.e.idx = (u8)j; ke.e.canonical = rc;
-                        pairs.push_back(ke);
+                        o.pairs.push_back(ke);
                     }
                 }
             }
             seq_id++;
         }
-        ix.genomes.push_back(std::move(g));
+    });
+    size_t total = 0;
+    for (size_t file_id = 0; file_id < paths.size(); file_id++) {
+        if (!outs[file_id].ok) { err = "Failed to parse fasta file: " + paths[file_id]; return false; }
+        total += outs[file_id].pairs.size();
+    }
+    std::vector<KeyedEntry> pairs;
+    pairs.reserve(total);
+    for (FileOut& o : outs) {
+        pairs.insert(pairs.end(), o.pairs.begin(), o.pairs.end());
+        std::vector<KeyedEntry>().swap(o.pairs);
+        ix.genomes.push_back(std::move(o.g));
     }
     index_from_pairs(ix, pairs);
     return true;

@@ -197,3 +197,20 @@ def test_grouped_map_tables_are_an_exact_reindexing(sars_emul, hpv_emul, hpv_fas
     for b0, b1 in ((2, k - 3), (0, k), (k // 2, k - k // 2 - 1 + (k // 2 + 1 > k - k // 2 - 1)), (0, 1)):
         if b0 < b1:
             assert e.group_check(q, b0, b1) == 0
+
+
+def test_multi_genome_db_roundtrip_through_bkdb(oracle, sars_emul, sars_paths, tmp_path):
+    """4-strain db (703,025 keys / 2,501,142 entries — large enough for the threaded sort and the per-file builder):
+    product writer → product reader and → oracle reader, all three equal to the oracle's own build."""
+    want = oracle.Index.build(21, sars_paths).export()
+    p = str(tmp_path / "sars4.bkdb")
+    sars_emul.save(p)
+    back = Emul.from_bkdb(p).export()
+    assert (back[0] == want[0]).all() and (back[1] == want[1]).all() and back[2].tobytes() == want[2].tobytes()
+    r = oracle.Index.load(p).export()
+    assert (r[0] == want[0]).all() and (r[1] == want[1]).all() and r[2].tobytes() == want[2].tobytes()
+    # file order matters (entries of a key are in file order, then position): a permuted file list is another index
+    perm = Emul.from_fasta(21, sars_paths[::-1]).export()
+    assert (perm[0] == want[0]).all() and perm[2].tobytes() != want[2].tobytes()
+    want_perm = oracle.Index.build(21, sars_paths[::-1]).export()
+    assert (perm[1] == want_perm[1]).all() and perm[2].tobytes() == want_perm[2].tobytes()
