@@ -250,6 +250,10 @@ def main():
     # single-sample latency and per-kernel times with nothing else in flight (the roofline of the scan kernel is
     # quoted on the kernel timed alone; under S-in-flight other samples' kernels share the SMs)
     torch.cuda.synchronize()
+    # clocks / throttle reasons are sampled from here to the end of the e2e leg: the GPU is under load throughout, and
+    # the device-timed region alone (~0.1 s) is shorter than nvidia-smi's start-up
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     alone = {}
     n_alone = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
@@ -258,16 +262,13 @@ def main():
         for k_, v_ in ctx.stage_times().items():
             alone[k_] = alone.get(k_, 0.0) + v_ / n_alone
     latency_ms = (time.perf_counter() - t0) * 1e3 / n_alone
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     run_steps(args.steps, step_device, collect=True)
     torch.cuda.synchronize()
     e1.record()
     barrier()
-    clk = clocks.stop()
     res = last["res"]
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
@@ -285,6 +286,8 @@ def main():
         e2e_value = total_bases * args.steps / e2e_s
     else:
         e2e_value = None
+    clk = clocks.stop()
+    clk["window"] = "single-sample latency leg + device-timed region + e2e leg (GPU under load throughout)"
     h2d = sum(hb.numel() - 64 + ho.numel() * 4 for hb, ho, _ in pinned)
     d2h = int(len(res.variants) * 72 + 120 + 2 * 4 * 16)
 
