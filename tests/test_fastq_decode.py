@@ -78,3 +78,21 @@ def test_decode_runs_on_several_threads(tmp_path):
         t.join()
     for (p, seqs), got in zip(files, out):
         assert got == seqs
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("shift", [-2, -1, 0, 1, 2])
+def test_line_ends_at_block_boundaries(tmp_path, gz, shift):
+    """the 8 MB inflate blocks may end anywhere: inside a sequence line, between its '\\r' and '\\n', right after the
+    '\\n', inside the header of the next record"""
+    block = 8 << 20
+    first = b"@pad " + b"x" * 100 + b"\r\nACGTACGT\r\n+\r\nIIIIIIII\r\n"
+    seq = b"GATTACA" * 11
+    # choose the second header so that the '\n' ending the second sequence line is byte (block + shift - 1)
+    head_len = block + shift - 1 - len(first) - len(seq) - 1 - 2        # "\r\n" after the header, '\r' before the '\n'
+    second = b"@" + b"h" * (head_len - 1) + b"\r\n" + seq + b"\r\n+\r\n" + b"I" * len(seq) + b"\r\n"
+    data = first + second + b"@last\r\nTTTT\r\n+\r\nIIII\r\n"
+    assert data[block + shift - 1:block + shift] == b"\n" and data[block + shift - 2:block + shift - 1] == b"\r"
+    p = tmp_path / ("b.fastq.gz" if gz else "b.fastq")
+    p.write_bytes(gzip.compress(data, 1) if gz else data)
+    assert decode(p) == [b"ACGTACGT", seq, b"TTTT"] == parse_py(data)
