@@ -55,7 +55,7 @@ struct FileState {
     DevBuf<u32> gstats;
     u32 gen_log2 = 0;
     DevBuf<u64> xk; DevBuf<u32> xc;          // sharded mode: novel (k-mer, count) pairs grouped by owner rank
-    DevBuf<u64> nov, nov_sorted;             // list mode (bk_bins.cuh): novel k-mer occurrences, then grouped by bin
+    DevBuf<u64> nov;                         // list mode (bk_bins.cuh): novel k-mer occurrences of the file (grouped by bin in ctx->d_nov_sorted)
     DevBuf<u32> bin_cnt;
     bool list_mode = false;                  // novel k-mers through the list + bins instead of the gen table
     u64 nov_ub = 0;                          // upper bound of list entries the pushes so far were given room for
@@ -251,7 +251,7 @@ void bk_destroy(bk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->I.reset();                         // the last context sharing an index frees its device copies
-    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); f.nov.release(); f.nov_sorted.release(); f.bin_cnt.release(); }
+    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); f.nov.release(); f.bin_cnt.release(); }
     ctx->d_part.release();
     ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_nov_sorted.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();

@@ -417,7 +417,7 @@ struct MapView {
     const BucketSlotD* slots; u32 shift, mask;
     const BucketEntryD* entries;
     u32 n_genomes; const u32* genome_row0;
-    // grouped form of the re-keyed table (bk_host.h: group_slots / group_recs); null when not available
+    // grouped form of the re-keyed table (bk_host.h: group_slots / group_centers / group_buckets); null when not available
     const BucketSlotD* gslots; u32 gshift, gmask; const BucketSlotD* gcenters; const uint2* gbuckets; u32 gmid;
 };
 
