@@ -377,7 +377,9 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
     d.bucket_log2 = log2_cap(ix.keys.size());
     d.bucket_slots.assign(1ull << d.bucket_log2, BucketSlot{~0ull, 0, 0});
     d.bucket_entries.resize(ix.entries.size());
-    for (size_t i = 0; i < ix.entries.size(); i++) {
+    const size_t ECHUNK = 1u << 20;
+    parallel_for((ix.entries.size() + ECHUNK - 1) / ECHUNK, [&](size_t c) {
+    for (size_t i = c * ECHUNK, i_end = std::min(ix.entries.size(), (c + 1) * ECHUNK); i < i_end; i++) {
         const bk_bucket_info& e = ix.entries[i];
         BucketEntry be;
         u32 r = 0xFFFFFFFFu;
@@ -392,6 +394,7 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         be.row = r; be.file_id = e.file_id; be.idx = e.idx; be.canonical = e.canonical ? 1 : 0;
         d.bucket_entries[i] = be;
     }
+    });
     // Re-key: bucket id j of a canonical k-mer is a perfect rank of (j, k-mer without digit j), so the device can probe
     // with that pair directly and skip the id arithmetic.  Every key is verified against its first entry (the
     // reference k-mer at `location`, canonicalised, digit idx zeroed must rank to exactly this key); one failure (an
@@ -401,26 +404,30 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
     const bool want_groups = d.n_genomes <= 4;                // the grouped form serves the thread-per-k-mer map kernels only
     std::vector<u64> center;                                  // per key: the canonical k-mer its first entry was verified with
     if (d.rekeyed) {
-        std::vector<u64> ids(k);
         if (want_groups) center.resize(ix.keys.size());
-        for (size_t i = 0; i < ix.keys.size() && d.rekeyed; i++) {
-            if (ix.entry_off[i + 1] == ix.entry_off[i]) { d.rekeyed = false; break; }
-            const bk_bucket_info& e = ix.entries[ix.entry_off[i]];
-            bool ok = e.file_id < d.n_genomes && e.idx < k;
-            const HostSeq* q = nullptr;
-            if (ok) { const HostGenome& g = ix.genomes[e.file_id]; ok = e.seq_id < g.seqs.size(); if (ok) q = &g.seqs[e.seq_id]; }
-            if (ok) ok = (u64)e.location + k <= q->bases.size();
-            if (!ok) { d.rekeyed = false; break; }
-            u64 fwd = 0;
-            for (u32 b = 0; b < k; b++) fwd = (fwd << 2) | nt_to_bits_host(q->bases[e.location + b]);
-            const u64 rev = revcomp_host(fwd, (int)k);
-            const u64 kb = fwd < rev ? fwd : rev;                       // src/lcb.rs:87-95
-            assign_buckets_host(kb, (int)k, ids.data());
-            if (ids[e.idx] != ix.keys[i]) { d.rekeyed = false; break; }
-            slot_key[i] = ((u64)e.idx << 58) | (kb & ~(3ull << (2 * (k - 1 - e.idx))));
-            if (want_groups) center[i] = kb;
-        }
-        if (!d.rekeyed) slot_key.assign(ix.keys.begin(), ix.keys.end());
+        std::atomic<bool> failed{false};
+        const size_t KCHUNK = 1u << 18;
+        parallel_for((ix.keys.size() + KCHUNK - 1) / KCHUNK, [&](size_t c) {
+            u64 ids[32];
+            for (size_t i = c * KCHUNK, i_end = std::min(ix.keys.size(), (c + 1) * KCHUNK); i < i_end && !failed.load(std::memory_order_relaxed); i++) {
+                if (ix.entry_off[i + 1] == ix.entry_off[i]) { failed = true; break; }
+                const bk_bucket_info& e = ix.entries[ix.entry_off[i]];
+                bool ok = e.file_id < d.n_genomes && e.idx < k;
+                const HostSeq* q = nullptr;
+                if (ok) { const HostGenome& g = ix.genomes[e.file_id]; ok = e.seq_id < g.seqs.size(); if (ok) q = &g.seqs[e.seq_id]; }
+                if (ok) ok = (u64)e.location + k <= q->bases.size();
+                if (!ok) { failed = true; break; }
+                u64 fwd = 0;
+                for (u32 b = 0; b < k; b++) fwd = (fwd << 2) | nt_to_bits_host(q->bases[e.location + b]);
+                const u64 rev = revcomp_host(fwd, (int)k);
+                const u64 kb = fwd < rev ? fwd : rev;                       // src/lcb.rs:87-95
+                assign_buckets_host(kb, (int)k, ids);
+                if (ids[e.idx] != ix.keys[i]) { failed = true; break; }
+                slot_key[i] = ((u64)e.idx << 58) | (kb & ~(3ull << (2 * (k - 1 - e.idx))));
+                if (want_groups) center[i] = kb;
+            }
+        });
+        if (failed) { d.rekeyed = false; slot_key.assign(ix.keys.begin(), ix.keys.end()); }
     }
     const u64 bmask = (1ull << d.bucket_log2) - 1;
     for (size_t i = 0; i < ix.keys.size(); i++) {
@@ -520,7 +527,7 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         wd = (wd & ~(0xFu << sh)) | ((u32)codes[i] << sh);
     }
 
-    std::sort(occ.begin(), occ.end(), [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.gidx < b.gidx; });
+    parallel_stable_sort(occ, [](const Occ& a, const Occ& b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.gidx < b.gidx; });      // (a total order)
     d.slot2id.assign(d.n_raw, 0xFFFFFFFFu);
     for (size_t i = 0; i < occ.size(); i++) {
         if (i == 0 || occ[i].kmer != occ[i - 1].kmer) d.id_kmer.push_back(occ[i].kmer);
