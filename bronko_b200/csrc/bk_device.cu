@@ -894,6 +894,10 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
         cudaStreamSynchronize(st);
         fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u; kcycles: s %u, s2 %u, slowest table lane %u\n",
                 h[0], h[1], h[2], h[3], h[4], h[5] / 64, h[6] / 64, h[7] / 64);
+#ifdef BK_NZ_PHASES
+        fprintf(stderr, "[noise] s2 chain kcycles by phase: tile %u, operands+maps %u, warp scan %u, combine %u, check+reduce %u, prefix %u, stop %u, serial %u\n",
+                h[8] / 64, h[9] / 64, h[10] / 64, h[11] / 64, h[12] / 64, h[13] / 64, h[14] / 64, h[15] / 64);
+#endif
     }
     CallParams cp;
     const bk_params& p = ctx->params;

@@ -316,6 +316,20 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
 #define BK_NZ_TABLE_SMEM (BK_NZ_TABLE_WARPS * BK_NZ_TABLE_POS * 3 * 8)
 #define BK_NZ_SEQ_SMEM (BK_NZ_TABLE_SMEM > BK_NZ_CHAIN_SMEM ? BK_NZ_TABLE_SMEM : BK_NZ_CHAIN_SMEM)
 
+// Developer builds only (tools/build_variant.sh ... -DBK_NZ_PHASES, run with BK_NOISE_DEBUG=1): cycles of the s² chain
+// by phase of a round — 0 tile staging, 1 operands + increments + per-thread maps, 2 warp scan, 3 barrier + cross-warp
+// combine, 4 sums + range check + reduction + barrier, 5 accepted prefix + barrier, 6 the stop's iteration, 7 serial
+// batches — into stats[8..15] (cycles / 16).  The product build compiles none of it.
+#ifdef BK_NZ_PHASES
+#define BK_NZ_PH_DECL long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define BK_NZ_PH(i) do { const long long ph_n = clock64(); ph_acc[i] += (unsigned long long)(ph_n - ph_t); ph_t = ph_n; } while (0)
+#define BK_NZ_PH_STORE do { if (tid == 0 && nv.stats && SQUARE) for (int ph_i = 0; ph_i < 8; ph_i++) nv.stats[8 + ph_i] = (u32)(ph_acc[ph_i] >> 4); } while (0)
+#else
+#define BK_NZ_PH_DECL
+#define BK_NZ_PH(i) do {} while (0)
+#define BK_NZ_PH_STORE do {} while (0)
+#endif
+
 template <bool SQUARE>
 __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* mt) {
     __shared__ i64 wt0[2][8], wt1[2][8];
@@ -332,6 +346,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
     const u32 width = BK_NZ_ROUND;                                              // iterations tried per round
     u32 st_rounds = 0, st_stops = 0, st_serial = 0;
     const long long t_begin = clock64();
+    BK_NZ_PH_DECL
     while (i0 < iters) {
         if (i0 + 1 > tile_hi || (i0 + BK_NZ_ROUND > tile_hi && tile_hi < iters)) {
             __syncthreads();
@@ -340,6 +355,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
             const size_t x0 = (size_t)tile_lo * 3;                               // mafp index of position tile_lo-100
             for (u32 x = tid; x < nx; x += BK_NZ_SEQ_THREADS) mt[x] = (tile_lo + x / 3 < pos_total) ? mafp[x0 + x] : 0.0;
             __syncthreads();
+            BK_NZ_PH(0);
         }
         const u32 tl = tile_lo;
         auto M = [mt, tl](i32 p, u32 j) { return mt[(u32)(p + BK_NOISE_WINDOW - (i32)tl) * 3 + j]; };
@@ -360,6 +376,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
             }
             i0 += n_ser; st_serial += n_ser;
             serial_left = moved ? 1u : 0u;
+            BK_NZ_PH(7);
             continue;
         }
         const u32 buf = round & 1;
@@ -381,6 +398,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
                 pre0[q] = run0; pre1[q] = run1;
                 if (!ok && bad == 6) bad = q;
             }
+            BK_NZ_PH(1);
             // inclusive scan of the parity maps over the warp
             i64 f0 = run0, f1 = run1;
 #pragma unroll
@@ -396,10 +414,12 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
             for (u32 q = 0; q < 6; q++) { pre0[q] = 0; pre1[q] = 0; }
             if (lane == 31) { wt0[buf][wid] = 0; wt1[buf][wid] = 0; }
         }
+        BK_NZ_PH(2);
         __syncthreads();
         i64 base = S0;
         for (u32 w = 0; w < wid; w++) base += (base & 1) ? wt1[buf][w] : wt0[buf][w];
         base += (base & 1) ? x1 : x0;
+        BK_NZ_PH(3);
         const bool odd = (base & 1) != 0;
         i64 T[6];
 #pragma unroll
@@ -412,6 +432,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         mine = __reduce_min_sync(0xFFFFFFFFu, mine);
         if (lane == 0) wbad[buf][wid] = mine;
         __syncthreads();
+        BK_NZ_PH(4);
         u32 n_ok = total_ops;
 #pragma unroll
         for (u32 w = 0; w < 8; w++) n_ok = min(n_ok, wbad[buf][w]);
@@ -427,6 +448,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         }
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
+        BK_NZ_PH(5);
         if (n_ok == total_ops) { i0 += n_it; continue; }
         // the operation that ended the accepted prefix and the rest of its iteration, in real FP64
         st_stops++;
@@ -435,7 +457,9 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
         serial_left = 1;                               // stops come in bursts (the sum hovers at a binade border)
+        BK_NZ_PH(6);
     }
+    BK_NZ_PH_STORE;
     if (tid == 0 && nv.stats) {
         atomicAdd(nv.stats + 2, st_rounds); atomicAdd(nv.stats + 3, st_stops); atomicAdd(nv.stats + 4, st_serial);
         nv.stats[SQUARE ? 6 : 5] = (u32)((clock64() - t_begin) >> 4);            // cycles / 16
