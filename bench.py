@@ -246,14 +246,14 @@ def main():
         return float(t.item())
 
     # ---- value: inputs resident in HBM, device-timed ------------------------------------------
-    # clocks / throttle reasons are sampled from the warm-up to the end of the device-timed region (the GPU runs the
-    # same device-resident workload throughout; the timed region alone, ~0.1 s, is shorter than nvidia-smi's start-up)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     run_steps(args.warmup * S, step_device)
     # single-sample latency and per-kernel times with nothing else in flight (the roofline of the scan kernel is
     # quoted on the kernel timed alone; under S-in-flight other samples' kernels share the SMs)
     torch.cuda.synchronize()
+    # clocks / throttle reasons: sampled from here, through the device-timed region, to the end of an un-timed leg of the
+    # same load behind it (the timed region alone, ~0.1 s, is shorter than nvidia-smi's start-up)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     alone = {}
     n_alone = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
@@ -269,9 +269,13 @@ def main():
     torch.cuda.synchronize()
     e1.record()
     barrier()
-    clk = clocks.stop()
-    clk["window"] = "warm-up + single-sample latency leg + device-timed region"
     res = last["res"]
+    t_end = time.perf_counter() + 0.5
+    while time.perf_counter() < t_end:                     # same work, same samples in flight, not timed
+        run_steps(max(S, args.steps // 4), step_device)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    clk["window"] = "single-sample latency leg + device-timed region + 0.5 s of the same load behind it"
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     total_bases = n_bases * world
