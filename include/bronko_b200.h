@@ -115,7 +115,10 @@ typedef struct {
 int bk_create(bk_ctx** out, int device);
 void bk_destroy(bk_ctx* ctx);
 const char* bk_last_error(bk_ctx* ctx);      /* ctx may be NULL: last bk_create error */
-void* bk_stream(bk_ctx* ctx);                /* cudaStream_t all work is enqueued on */
+void* bk_stream(bk_ctx* ctx);                /* cudaStream_t the pushes (counting kernels) are enqueued on: order device
+                                              * buffers handed to bk_reads_push_device against it.  Later stages of a
+                                              * sample run on internal streams of higher priority chained to it by
+                                              * events; every call that returns results synchronises. */
 const char* bk_version(void);
 
 /* ---- index: replaces the bincode decode at src/call.rs:179-200 / build_indexes at 170-178 ---- */
