@@ -42,7 +42,8 @@ class SampleResult(C.Structure):
 
 class StageTimes(C.Structure):
     _fields_ = [("scan_ms", C.c_float), ("leftover_ms", C.c_float), ("finalize_ms", C.c_float), ("map_ms", C.c_float),
-                ("score_ms", C.c_float), ("total_ms", C.c_float), ("launches", u32), ("scan_launches", u32)]
+                ("score_ms", C.c_float), ("total_ms", C.c_float), ("launches", u32), ("scan_launches", u32),
+                ("coll_ms", C.c_float), ("coll_calls", u32)]
 
 
 VARIANT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("ref_base", "u1"), ("alt_base", "u1"), ("pad", "u1", 6),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "bk_destroy": (None, [P]),
     "bk_last_error": (C.c_char_p, [P]),
     "bk_stream": (P, [P]),
+    "bk_stream_slot": (P, [P, C.c_int]),
     "bk_version": (C.c_char_p, []),
     "bk_index_load": (C.c_int, [P, u32, u64, P, P, P, u32, P, P, P, P]),
     "bk_index_load_file": (C.c_int, [P, C.c_char_p]),
@@ -83,6 +85,7 @@ SIGNATURES = {
     "bk_reads_push_decoded": (C.c_int, [P, C.c_int, P]),
     "bk_reads_free": (None, [P]),
     "bk_sample_finish": (C.c_int, [P, C.POINTER(SampleResult)]),
+    "bk_sample_result_get": (C.c_int, [P, C.POINTER(SampleResult)]),
     "bk_sample_variants": (C.c_int, [P, P, u64]),
     "bk_sample_genome_stats": (C.c_int, [P, C.c_int, P]),
     "bk_sample_pileup": (C.c_int, [P, C.c_int, P, u64]),
@@ -92,12 +95,11 @@ SIGNATURES = {
     "bk_write_vcf": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bk_write_pileup": (C.c_int, [P, C.c_char_p]),
     "bk_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),
-    "bk_shard_config": (C.c_int, [P, u32, u32]),
-    "bk_shard_begin": (C.c_int, [P, C.c_int, P, P, P, P, P]),
-    "bk_shard_import_novel": (C.c_int, [P, C.c_int, P, P, u64]),
-    "bk_shard_map_stats": (C.c_int, [P, P, P, P, P]),
-    "bk_shard_select_pileup": (C.c_int, [P, P, P, P]),
-    "bk_shard_score": (C.c_int, [P, C.POINTER(SampleResult)]),
+    "bk_shard_unique_id": (C.c_int, [P]),
+    "bk_shard_init": (C.c_int, [P, u32, u32, P]),
+    "bk_shard_info": (C.c_int, [P, P, P]),
+    "bk_shard_local": (C.c_int, [P, u32]),
+    "bk_shard_finish_local": (C.c_int, [P, u32, C.POINTER(SampleResult)]),
     "bk_host_alloc": (P, [u64]),
     "bk_host_free": (None, [P]),
 }

@@ -1,17 +1,21 @@
 // bk_device.cu — bk_ctx, device memory, kernel launches and the C ABI of libbronko_b200.so
 // (include/bronko_b200.h).  There is no CPU fallback anywhere in this file: every stage of a sample
 // runs as a CUDA kernel from bk_kernels.cuh, and bk_create fails without an sm_100 device.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
 #include "bk_host.h"
-#include "bk_kernels.cuh"
+#include "bk_shard.cuh"
 
 using namespace bk;
 
@@ -45,24 +49,31 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum Stage { ST_SCAN = 0, ST_LEFTOVER, ST_FINALIZE, ST_MAP, ST_SCORE, ST_N };
+enum Stage { ST_SCAN = 0, ST_LEFTOVER, ST_FINALIZE, ST_MAP, ST_SCORE, ST_COLL, ST_N };
 
+// Everything one reads file (R1 or R2) owns.  The two files of a pair are independent until the genome is selected
+// (src/call.rs:302-317 counts and maps them one after the other), so each has its own scratch and its own streams.
 struct FileState {
     DevBuf<u32> diff, idcnt;
-    DevBuf<GenSlot> gen;
-    DevBuf<u64> ckmers;
-    DevBuf<u32> ccounts;
+    DevBuf<u64> ckmers; DevBuf<u32> ccounts;   // the counted list: the "KMC dump" of the file
     DevBuf<u32> gstats;
-    u32 gen_log2 = 0;
-    DevBuf<u64> xk; DevBuf<u32> xc;          // sharded mode: novel (k-mer, count) pairs grouped by owner rank
-    DevBuf<u64> nov;                         // list mode (bk_bins.cuh): novel k-mer occurrences of the file (grouped by bin in ctx->d_nov_sorted)
+    DevBuf<uint2> desc;                        // leftover stretches queued by the scan of one push
+    DevBuf<u32> bsum;                          // prefix-sum scratch
+    DevBuf<u64> nov, sorted;                   // novel k-mer occurrences of the file, and the same grouped by bin (bk_bins.cuh)
     DevBuf<u32> bin_cnt;
-    bool list_mode = false;                  // novel k-mers through the list + bins instead of the gen table
-    u64 nov_ub = 0;                          // upper bound of list entries the pushes so far were given room for
-    u64 nov_limit = 0;                       // entries the kernels may use (the allocation can be larger: it is reused)
+    // read-sharded mode: pair counts next to nov / sorted, per-bin pair counts, pairs received from the other ranks
+    DevBuf<u32> wa, wb, dcount, own_off;
+    DevBuf<u64> rk, rsk; DevBuf<u32> rc, rsw;
+    u64 nov_ub = 0;                            // upper bound of list entries the pushes so far were given room for
+    u64 nov_limit = 0;                         // entries the kernels may use (the allocation can be larger: it is reused)
     u32 bin_log2p = 8;
     bool used = false, folded = false, finalized = false;
     u64 total_reads = 0, total_bases = 0;
+    void release() {
+        diff.release(); idcnt.release(); ckmers.release(); ccounts.release(); gstats.release(); desc.release(); bsum.release();
+        nov.release(); sorted.release(); bin_cnt.release(); wa.release(); wb.release(); dcount.release(); own_off.release();
+        rk.release(); rsk.release(); rc.release(); rsw.release();
+    }
 };
 
 // The index on one device: host form, derived tables and their device copies.  Read-only once uploaded, so the
@@ -87,30 +98,39 @@ struct IndexDev {
     }
 };
 
+// The ranks of one read-sharded sample (bk_shard_* in include/bronko_b200.h).  NCCL: one rank per process and GPU,
+// `members` holds this process's context only.  Local: all ranks are contexts of this process on one device (tests).
+struct ShardGroup {
+    u32 n = 1;
+    bool local = false;
+    std::vector<bk_ctx*> members;
+    void* comm = nullptr;                   // ncclComm_t
+    ~ShardGroup();
+};
+
 }  // namespace
 
 struct bk_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    // Stage priorities.  `stream` is the stream the sample's work is currently issued to: stage_stream[0] while reads are
-    // pushed (scan / leftover), [1] for finalize + map, [2] for the score stage, each with a higher CUDA priority than the
-    // one before and chained by an event.  Every big kernel fills the SMs' register files, so with several samples in
-    // flight (one context each) a kernel's CTAs only start as CTAs of other kernels retire, and without priorities the
-    // handful of CTAs of a sample's last, latency-bound stages (the noise chains) queue behind thousands of pending CTAs
-    // of other samples' first stages.  BK_PRIO=0 keeps everything on one stream.
-    cudaStream_t stage_stream[3] = {nullptr, nullptr, nullptr};
+    // Streams.  The two files of a sample run concurrently: file f counts (scan / leftover) on s_count[f] and is
+    // finalized and mapped on s_fin[f]; selection + scoring run on s_score.  The three levels have rising CUDA
+    // priority.  Every big kernel fills the SMs' register files, so with several samples in flight (one context each) a
+    // kernel's CTAs only start as CTAs of other kernels retire, and without priorities the handful of CTAs of a sample's
+    // last, latency-bound stages (the noise chains) queue behind thousands of pending CTAs of other samples' first
+    // stages.  BK_PRIO=0 puts everything on one stream.
+    cudaStream_t s_count[2] = {nullptr, nullptr}, s_fin[2] = {nullptr, nullptr}, s_score = nullptr, copy_stream = nullptr;
+    std::vector<cudaStream_t> owned_streams;
     cudaEvent_t ev_chain = nullptr;
-    int level = 0, prio_mode = 2;
-    void use_level(int lvl) {
-        if (prio_mode == 0) return;
-        if (prio_mode == 1) lvl = lvl == 2 ? 2 : 0;
-        if (lvl == level) return;
-        cudaEventRecord(ev_chain, stage_stream[level]);
-        cudaStreamWaitEvent(stage_stream[lvl], ev_chain, 0);
-        level = lvl; stream = stage_stream[lvl];
+    int prio_mode = 2;
+    // order `dst` after everything issued to `src` so far (one scratch event: a wait captures the record before it)
+    void chain(cudaStream_t src, cudaStream_t dst) {
+        if (src == dst) return;
+        cudaEventRecord(ev_chain, src);
+        cudaStreamWaitEvent(dst, ev_chain, 0);
     }
     std::string err;
     int sm_count = 148;
+    bool spin_wait = false;
 
     std::shared_ptr<IndexDev> I;            // null until an index is loaded / built / shared
 
@@ -120,8 +140,7 @@ struct bk_ctx {
     FileState file[2];
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;              // pinned
-    DevBuf<uint2> d_desc; DevBuf<u32> d_bsum;
-    DevBuf<u64> d_nov_sorted;               // list mode: one file's novel k-mers grouped by bin (files are finalized one after the other)
+    u64* h_stats = nullptr;                 // pinned: globally reduced KMC numbers of a sharded sample
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
     DevBuf<u32> d_pile_all;                 // one such block per genome (databases of at most four genomes: one-pass map)
     DevBuf<double> d_noise;                 // Noise.max per row
@@ -132,15 +151,17 @@ struct bk_ctx {
     // staging for host pushes (double buffered)
     DevBuf<u8> d_stage[2]; DevBuf<u32> d_stage_off;
     cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
+    cudaEvent_t off_free = nullptr, off_copied = nullptr;   // d_stage_off: last kernels that read it / its H2D copy
     int stage_next = 0;
-    u32 shard_rank = 0, shard_n = 1;
-    bk_kmc_stats shard_kmc[2];
-    DevBuf<u32> d_part;
+    // read-sharded deep sample
+    std::shared_ptr<ShardGroup> shard;      // null: this context holds whole samples
+    u32 shard_rank = 0;
+    DevBuf<u64> d_shard_stats;
+    DevBuf<u32> d_shard_sizes;
     bool noise_debug = false;
     bool force_warp_map = false;            // tests: exercise the many-genome map kernel on a small db
     bool no_fused_map = false;              // tests: BK_NO_FUSED_MAP keeps the two-pass map on small databases
     bool no_group_map = false;              // tests: BK_NO_GROUP_MAP probes the per-bucket table instead of the grouped one
-    bool novel_table = false;               // tests: BK_NOVEL_TABLE counts novel k-mers in the global hash table (what the sharded mode uses)
 
     // results
     bk_sample_result result;
@@ -148,29 +169,30 @@ struct bk_ctx {
     std::vector<bk_genome_stats> gstats[2];
 
     // timing
-    struct Span { cudaEvent_t a, b; int stage; };
+    struct Span { cudaEvent_t a, b; int stage; cudaStream_t st; };
     std::vector<Span> spans; size_t spans_used = 0;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    u32 launches = 0, scan_launches = 0;
+    u32 launches = 0, scan_launches = 0, coll_calls = 0;
     bk_stage_times times;
 
+    u32 shard_n() const { return shard ? shard->n : 1u; }
     int fail(int code, const char* fmt, ...) {
         char buf[1024];
         va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
         err = buf;
         return code;
     }
-    int span_begin(int stage) {
+    int span_begin(int stage, cudaStream_t st) {
         if (spans_used == spans.size()) {
-            Span s; s.stage = stage;
+            Span s; s.stage = stage; s.st = st;
             if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return -1;
             spans.push_back(s);
         }
-        spans[spans_used].stage = stage;
-        cudaEventRecord(spans[spans_used].a, stream);
+        spans[spans_used].stage = stage; spans[spans_used].st = st;
+        cudaEventRecord(spans[spans_used].a, st);
         return (int)spans_used++;
     }
-    void span_end(int id) { if (id >= 0) cudaEventRecord(spans[id].b, stream); }
+    void span_end(int id) { if (id >= 0) cudaEventRecord(spans[id].b, spans[id].st); }
 };
 
 static int grid_for(const bk_ctx* ctx, u64 items, u32 per_block, u32 max_waves = 8) {
@@ -181,9 +203,18 @@ static int grid_for(const bk_ctx* ctx, u64 items, u32 per_block, u32 max_waves =
     return (int)g;
 }
 
+// Nothing throws across the ABI: allocation failures and anything else unexpected become a status.
+template <class F>
+static int guarded(bk_ctx* ctx, F&& f) {
+    try { return f(); }
+    catch (const std::bad_alloc&) { return ctx ? ctx->fail(BK_ERR_NOMEM, "out of host memory") : (int)BK_ERR_NOMEM; }
+    catch (const std::exception& e) { return ctx ? ctx->fail(BK_ERR_ARG, "internal error: %s", e.what()) : (int)BK_ERR_ARG; }
+    catch (...) { return ctx ? ctx->fail(BK_ERR_ARG, "internal error") : (int)BK_ERR_ARG; }
+}
+
 extern "C" {
 
-const char* bk_version(void) { return "bronko_b200 0.1.0 (sm_100a)"; }
+const char* bk_version(void) { return "bronko_b200 0.2.0 (sm_100a)"; }
 
 int bk_create(bk_ctx** out, int device) {
     if (!out) return BK_ERR_ARG;
@@ -202,25 +233,37 @@ int bk_create(bk_ctx** out, int device) {
         return BK_ERR_NO_DEVICE;
     }
     if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return BK_ERR_CUDA; }
-    bk_ctx* ctx = new bk_ctx();
+    bk_ctx* ctx = new (std::nothrow) bk_ctx();
+    if (!ctx) { g_create_error = "out of host memory"; return BK_ERR_NOMEM; }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);              // numerically lower = higher priority
     if (const char* e = getenv("BK_PRIO")) ctx->prio_mode = atoi(e);
     if (prio_greatest >= prio_least) ctx->prio_mode = 0;
-    bool ok = cudaStreamCreateWithPriority(&ctx->stage_stream[0], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+    ctx->spin_wait = getenv("BK_SPIN") != nullptr;
+    auto mk = [&](cudaStream_t* s, int prio) {
+        if (cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio) != cudaSuccess) return false;
+        ctx->owned_streams.push_back(*s);
+        return true;
+    };
+    bool ok = mk(&ctx->s_count[0], prio_least) && mk(&ctx->copy_stream, prio_least) &&
               cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) == cudaSuccess &&
-              cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
-    if (ok && ctx->prio_mode != 0)
-        ok = cudaStreamCreateWithPriority(&ctx->stage_stream[1], cudaStreamNonBlocking, std::max(prio_greatest, prio_least - 1)) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&ctx->stage_stream[2], cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
-    ctx->stream = ctx->stage_stream[0];
+              cudaMallocHost((void**)&ctx->h_stats, 8 * sizeof(u64)) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev_begin) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_end, ctx->spin_wait ? cudaEventDefault : cudaEventBlockingSync) == cudaSuccess;
+    if (ok && ctx->prio_mode != 0) {
+        const int mid = std::max(prio_greatest, prio_least - 1);
+        ok = mk(&ctx->s_count[1], prio_least) && mk(&ctx->s_fin[0], mid) && mk(&ctx->s_fin[1], mid) && mk(&ctx->s_score, prio_greatest);
+    } else if (ok) {
+        ctx->s_count[1] = ctx->s_fin[0] = ctx->s_fin[1] = ctx->s_score = ctx->s_count[0];
+    }
     for (int i = 0; i < 2 && ok; i++)
         ok = cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->stage_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&ctx->off_free, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->off_copied, cudaEventDisableTiming) == cudaSuccess;
     if (ok) {
         double tau[301];
         tau_table(tau);
@@ -231,8 +274,11 @@ int bk_create(bk_ctx** out, int device) {
                  cudaFuncSetAttribute(k_map<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_noise_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NZ_SEQ_SMEM) == cudaSuccess &&
                  cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess;
+                 cudaFuncSetAttribute(k_bin_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
     memset(&ctx->result, 0, sizeof ctx->result);
@@ -240,7 +286,6 @@ int bk_create(bk_ctx** out, int device) {
     ctx->force_warp_map = getenv("BK_FORCE_WARP_MAP") != nullptr;
     ctx->noise_debug = getenv("BK_NOISE_DEBUG") != nullptr;
     ctx->no_fused_map = getenv("BK_NO_FUSED_MAP") != nullptr;
-    ctx->novel_table = getenv("BK_NOVEL_TABLE") != nullptr;
     ctx->no_group_map = getenv("BK_NO_GROUP_MAP") != nullptr;
     *out = ctx;
     return BK_OK;
@@ -250,27 +295,34 @@ void bk_destroy(bk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    if (ctx->shard) {                       // leave the group: the other members must not be driven through it any more
+        for (bk_ctx*& m : ctx->shard->members) if (m == ctx) m = nullptr;
+        ctx->shard.reset();
+    }
     ctx->I.reset();                         // the last context sharing an index frees its device copies
-    for (FileState& f : ctx->file) { f.diff.release(); f.idcnt.release(); f.gen.release(); f.ckmers.release(); f.ccounts.release(); f.gstats.release(); f.xk.release(); f.xc.release(); f.nov.release(); f.bin_cnt.release(); }
-    ctx->d_part.release();
-    ctx->d_ctr.release(); ctx->d_desc.release(); ctx->d_bsum.release(); ctx->d_nov_sorted.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
+    for (FileState& f : ctx->file) f.release();
+    ctx->d_ctr.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();
     ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
     ctx->d_nz_flag.release(); ctx->d_nz_stats.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
+    ctx->d_shard_stats.release(); ctx->d_shard_sizes.release();
     for (auto& s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < 2; i++) { if (ctx->stage_free[i]) cudaEventDestroy(ctx->stage_free[i]); if (ctx->stage_copied[i]) cudaEventDestroy(ctx->stage_copied[i]); }
+    if (ctx->off_free) cudaEventDestroy(ctx->off_free);
+    if (ctx->off_copied) cudaEventDestroy(ctx->off_copied);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    for (cudaStream_t st : ctx->stage_stream) if (st) cudaStreamDestroy(st);
+    if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
+    for (cudaStream_t st : ctx->owned_streams) cudaStreamDestroy(st);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
 const char* bk_last_error(bk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-void* bk_stream(bk_ctx* ctx) { return ctx ? (void*)ctx->stage_stream[0] : nullptr; }     // the stream pushes are issued to
+void* bk_stream(bk_ctx* ctx) { return ctx ? (void*)ctx->s_count[0] : nullptr; }
+void* bk_stream_slot(bk_ctx* ctx, int file_slot) { return (ctx && file_slot >= 0 && file_slot < 2) ? (void*)ctx->s_count[file_slot] : nullptr; }
 
 void* bk_host_alloc(uint64_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
 void bk_host_free(void* p) { if (p) cudaFreeHost(p); }
@@ -304,7 +356,7 @@ static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
     const DerivedIndex& d = ctx->I->d;
     if (d.n_genomes == 0 || d.n_genomes > 4096) return ctx->fail(BK_ERR_ARG, "index holds %u genomes (supported: 1..4096)", d.n_genomes);
     if ((u64)d.n_raw + 2 >= 0x7FFFFFFFull) return ctx->fail(BK_ERR_ARG, "reference set too large for 32-bit slot indices");
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->s_count[0];
     static_assert(sizeof(BucketSlot) == sizeof(BucketSlotD) && sizeof(BucketEntry) == sizeof(BucketEntryD) && sizeof(ExactSlot) == sizeof(ExactSlotD), "layout");
     BK_CUDA(ctx->I->d_bucket_slots.reserve(d.bucket_slots.size()));
     BK_CUDA(cudaMemcpyAsync(ctx->I->d_bucket_slots.p, d.bucket_slots.data(), d.bucket_slots.size() * 16, cudaMemcpyHostToDevice, st));
@@ -364,11 +416,11 @@ static int size_for_index(bk_ctx* ctx) {
     }
     BK_CUDA(ctx->d_vars.reserve(rows * 3));
     BK_CUDA(ctx->d_ctr.reserve(1));
-    BK_CUDA(ctx->d_bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count * BK_BIN_G_PER_SM) / BK_PS_BLOCK + 2));
     for (FileState& f : ctx->file) {
         BK_CUDA(f.diff.reserve((size_t)d.n_raw + 2));
         BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
         BK_CUDA(f.gstats.reserve((size_t)d.n_genomes * 4));
+        BK_CUDA(f.bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count * BK_BIN_G_PER_SM) / BK_PS_BLOCK + 2));
     }
     ctx->in_sample = false; ctx->finished = false;
     return BK_OK;
@@ -376,11 +428,13 @@ static int size_for_index(bk_ctx* ctx) {
 
 int bk_index_share(bk_ctx* ctx, bk_ctx* owner) {
     if (!ctx || !owner) return BK_ERR_ARG;
+    return guarded(ctx, [&]() -> int {
     if (!owner->I) return ctx->fail(BK_ERR_ARG, "bk_index_share: the other context holds no index");
     if (owner->device != ctx->device) return ctx->fail(BK_ERR_ARG, "bk_index_share: contexts live on different devices");
     if (ctx->in_sample && !ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_index_share: call between samples");
     ctx->I = owner->I;
     return size_for_index(ctx);
+    });
 }
 
 int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys, const uint64_t* entry_off,
@@ -389,6 +443,7 @@ int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys
     if (!ctx) return BK_ERR_ARG;
     if (!keys || !entry_off || !entries || !genome_seq_off || !seq_len || !seq_base_off || !ref_bases)
         return ctx->fail(BK_ERR_ARG, "bk_index_load: null argument");
+    return guarded(ctx, [&]() -> int {
     auto fresh = std::make_shared<IndexDev>();
     HostIndex& ix = fresh->ix;
     ix.k = k; ix.meta_k = k;
@@ -410,31 +465,38 @@ int bk_index_load(bk_ctx* ctx, uint32_t k, uint64_t n_keys, const uint64_t* keys
         ix.genomes.push_back(std::move(hg));
     }
     return upload_index(ctx, fresh);
+    });
 }
 
 int bk_index_load_file(bk_ctx* ctx, const char* path) {
     if (!ctx || !path) return BK_ERR_ARG;
+    return guarded(ctx, [&]() -> int {
     std::string err;
     auto fresh = std::make_shared<IndexDev>();
     if (!bkdb_read(path, fresh->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
     return upload_index(ctx, fresh);
+    });
 }
 
 int bk_index_build(bk_ctx* ctx, uint32_t k, uint32_t n_files, const char* const* fasta_paths) {
     if (!ctx || !fasta_paths || n_files == 0) return BK_ERR_ARG;
     if (k < 15 || k > 31 || (k & 1) == 0) return ctx->fail(BK_ERR_ARG, "Invalid kmer size, must be odd and between [15-31]");
+    return guarded(ctx, [&]() -> int {
     std::vector<std::string> paths(fasta_paths, fasta_paths + n_files);
     std::string err;
     auto fresh = std::make_shared<IndexDev>();
     if (!index_build_from_fasta(k, paths, fresh->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
     return upload_index(ctx, fresh);
+    });
 }
 
 int bk_index_save(bk_ctx* ctx, const char* path) {
     if (!ctx || !path || !(ctx->I != nullptr)) return BK_ERR_ARG;
+    return guarded(ctx, [&]() -> int {
     std::string err;
     if (!bkdb_write(path, ctx->I->ix, err)) return ctx->fail(BK_ERR_IO, "%s", err.c_str());
     return BK_OK;
+    });
 }
 
 int bk_index_info(bk_ctx* ctx, uint32_t* k, uint64_t* n_keys, uint64_t* n_entries, uint32_t* n_genomes) {
@@ -467,6 +529,8 @@ int bk_index_export(bk_ctx* ctx, uint64_t* keys, uint64_t* entry_off, bk_bucket_
 // ---------------------------------------------------------------------------------------------
 // sample
 // ---------------------------------------------------------------------------------------------
+static bool can_fuse_map(const bk_ctx* ctx);
+
 int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     if (!ctx) return BK_ERR_ARG;
     if (!(ctx->I != nullptr)) return ctx->fail(BK_ERR_ARG, "bk_sample_begin: no index loaded");
@@ -479,28 +543,34 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     ctx->params = *params;
     ctx->in_sample = true; ctx->finished = false;
     for (FileState& f : ctx->file) { f.used = false; f.folded = false; f.finalized = false; f.total_reads = 0; f.total_bases = 0; f.nov_ub = 0; }
-    ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0;
-    ctx->use_level(0);                    // (after the previous sample's last stage, by the event chain)
+    ctx->spans_used = 0; ctx->launches = 0; ctx->scan_launches = 0; ctx->coll_calls = 0;
     ctx->variants.clear();
     memset(&ctx->result, 0, sizeof ctx->result);
     ctx->result.best_genome = -1;
-    cudaEventRecord(ctx->ev_begin, ctx->stream);
-    BK_CUDA(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), ctx->stream));
+    // (every stream of the context is idle here: the previous sample ended with a host wait on its last event)
+    cudaStream_t st = ctx->s_count[0];
+    cudaEventRecord(ctx->ev_begin, st);
+    BK_CUDA(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), st));
+    const size_t pile_bytes = (size_t)ctx->I->d.max_genome_rows * 4 * 4 * 4;
+    if (can_fuse_map(ctx)) BK_CUDA(cudaMemsetAsync(ctx->d_pile_all.p, 0, pile_bytes * ctx->I->d.n_genomes, st));
+    else BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, pile_bytes, st));
+    ctx->chain(st, ctx->s_count[1]);
     return BK_OK;
 }
 
-static CountView make_count_view(bk_ctx* ctx, FileState& f) {
+static CountView make_count_view(bk_ctx* ctx, int slot) {
+    FileState& f = ctx->file[slot];
     CountView v;
     v.k = ctx->I->ix.k;
     v.refnib = ctx->I->d_refnib.p; v.ref_chunks = (u32)(ctx->I->d.refnib.size() / 4);
     v.oseq_start = ctx->I->d_oseq_start.p; v.oseq_len = ctx->I->d_oseq_len.p;
     v.exact = ctx->I->d_exact.p; v.exact_shift = 64 - ctx->I->d.exact_log2; v.exact_mask = (1u << ctx->I->d.exact_log2) - 1;
     v.diff = f.diff.p;
-    v.gen = f.gen.p; v.gen_shift = 64 - f.gen_log2; v.gen_mask = (u32)((1ull << f.gen_log2) - 1);
+    v.gen = nullptr; v.gen_shift = 0; v.gen_mask = 0;      // (the open-addressing table of bk_core.cuh is only used by the CPU stepping of the tests)
     v.gen_full = &ctx->d_ctr.p->gen_full;
-    v.nov = f.list_mode ? f.nov.p : nullptr; v.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
-    v.nov_n = &ctx->d_ctr.p->f[&f - ctx->file].nov_n;
-    v.desc = ctx->d_desc.p; v.desc_cap = (u32)std::min<size_t>(ctx->d_desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->n_desc;
+    v.nov = f.nov.p; v.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
+    v.nov_n = &ctx->d_ctr.p->f[slot].nov_n;
+    v.desc = f.desc.p; v.desc_cap = (u32)std::min<size_t>(f.desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->f[slot].n_desc;
     return v;
 }
 
@@ -519,75 +589,77 @@ static bool ablated(const char* stage) { const char* e = getenv("BK_ABLATE"); re
 static inline bool ablated(const char*) { return false; }
 #endif
 
-// first use of a file slot in this sample: zero its difference array and (re)initialise its table
-static int file_prepare(bk_ctx* ctx, int slot, u64 bases_hint) {
+// first use of a file slot in this sample: zero its difference array and per-id counts
+static int file_prepare(bk_ctx* ctx, int slot) {
     FileState& f = ctx->file[slot];
     if (f.used) return BK_OK;
-    f.list_mode = ctx->shard_n == 1 && !ctx->novel_table;
-    BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->I->d.n_raw + 2) * 4, ctx->stream));
-    BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->I->d.id_kmer.size(), 1) * 4, ctx->stream));
-    if (!f.list_mode) {
-        u32 lg = ctx->params.table_log2;
-        if (lg == 0) {            // auto: ~1 slot per 32 read bases of this first push, clamped to [2^22, 2^27]
-            lg = 22;
-            while (lg < 27 && (1ull << lg) < bases_hint / 32) lg++;
-        }
-        f.gen_log2 = lg;
-        BK_CUDA(f.gen.reserve(1ull << lg));
-        k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
-        ctx->launches++;
-        BK_CUDA(cudaGetLastError());
-    }
+    cudaStream_t st = ctx->s_count[slot];
+    BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->I->d.n_raw + 2) * 4, st));
+    BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->I->d.id_kmer.size(), 1) * 4, st));
     f.used = true;
     return BK_OK;
 }
 
-// list mode: room for the novel k-mer occurrences of a push of n_bases bases (they cannot outnumber the bases);
-// what earlier pushes of the file wrote is kept.  bk_params.table_log2 != 0 fixes the capacity instead.
+// Room in the file's list for the novel k-mer occurrences of a push of n_bases bases.  They cannot outnumber the
+// bases, but at 0.2 % error only ~5 % of them are novel: the bound is kept per push, and when it no longer fits the
+// allocation the real fill of the list is read back first (one sync per such push), so a deep sample pushed in chunks
+// holds what it uses — not 8 bytes per base.  bk_params.table_log2 != 0 fixes the capacity instead.
 static int novel_room(bk_ctx* ctx, int slot, u64 n_bases) {
     FileState& f = ctx->file[slot];
-    if (!f.list_mode) return BK_OK;
-    u64 need;
-    const u64 before = f.nov_ub;
-    if (ctx->params.table_log2) { need = 1ull << ctx->params.table_log2; f.nov_ub = need; }
-    else { f.nov_ub += n_bases + 64; need = f.nov_ub; }
-    need = std::min<u64>(need, 0xFFFFFFF0ull);
-    f.nov_limit = need;
-    if (need <= f.nov.cap) return BK_OK;
-    if (before != 0 && f.nov.p) {                      // not the first push of the file: keep the entries
-        DevBuf<u64> bigger;
-        BK_CUDA(bigger.reserve(need + need / 2));
-        BK_CUDA(cudaMemcpyAsync(bigger.p, f.nov.p, f.nov.cap * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        BK_CUDA(cudaStreamSynchronize(ctx->stream));
-        f.nov.release();
-        f.nov = bigger;
-    } else BK_CUDA(f.nov.reserve(need));
+    cudaStream_t st = ctx->s_count[slot];
+    const u64 LIMIT = 0xFFFFFFF0ull;
+    if (ctx->params.table_log2) {
+        const u64 need = 1ull << ctx->params.table_log2;
+        if (f.nov_ub == 0) BK_CUDA(f.nov.reserve(need));
+        f.nov_ub = need; f.nov_limit = need;
+        return BK_OK;
+    }
+    u64 need = f.nov_ub + n_bases + 64;
+    if (need > f.nov.cap && f.nov_ub != 0) {
+        u32 used = 0;
+        BK_CUDA(cudaMemcpyAsync(&used, &ctx->d_ctr.p->f[slot].nov_n, 4, cudaMemcpyDeviceToHost, st));
+        BK_CUDA(cudaStreamSynchronize(st));
+        f.nov_ub = std::min<u64>(used, f.nov_limit);
+        need = f.nov_ub + n_bases + 64;
+    }
+    if (need > LIMIT) return ctx->fail(BK_ERR_OVERFLOW, "more than 2^32 novel k-mer occurrences in one file");
+    if (need > f.nov.cap) {
+        const u64 want = std::min<u64>(need + need / 4, LIMIT);
+        if (f.nov_ub != 0 && f.nov.p) {                  // not the first push of the file: keep the entries
+            DevBuf<u64> bigger;
+            BK_CUDA(bigger.reserve(want));
+            BK_CUDA(cudaMemcpyAsync(bigger.p, f.nov.p, f.nov_ub * 8, cudaMemcpyDeviceToDevice, st));
+            BK_CUDA(cudaStreamSynchronize(st));
+            f.nov.release();
+            f.nov = bigger;
+        } else BK_CUDA(f.nov.reserve(want));
+    }
+    f.nov_ub = need; f.nov_limit = need;
     return BK_OK;
 }
 
 // scan + leftover kernels over reads [r_begin, r_end) whose bytes live in d_bases (offset by off_bias)
 static int launch_count(bk_ctx* ctx, int slot, const u8* d_bases, const u32* d_off, u32 off_bias, u32 r_begin, u32 r_end, u32 max_len) {
     FileState& f = ctx->file[slot];
+    cudaStream_t st = ctx->s_count[slot];
     const u32 n = r_end - r_begin;
     if (n == 0) return BK_OK;
-    BK_CUDA(ctx->d_desc.reserve((size_t)n * 2 + 4096));
-    BK_CUDA(cudaMemsetAsync(&ctx->d_ctr.p->n_desc, 0, 4, ctx->stream));
-    CountView v = make_count_view(ctx, f);
+    BK_CUDA(f.desc.reserve((size_t)n * 2 + 4096));
+    BK_CUDA(cudaMemsetAsync(&ctx->d_ctr.p->f[slot].n_desc, 0, 4, st));
+    CountView v = make_count_view(ctx, slot);
     const u32 tile_bytes = 40 * 1024;
     u32 tile_reads = BK_SCAN_THREADS;
     if (max_len > 0) tile_reads = std::min<u32>(BK_SCAN_THREADS, std::max<u32>(1, tile_bytes / (max_len + 16)));
     if (tile_reads < 32) tile_reads = BK_SCAN_THREADS;   // long reads: tiles will not fit; kernel reads global memory
     const u32 n_tiles = (n + tile_reads - 1) / tile_reads;
-    int sp = ctx->span_begin(ST_SCAN);
-    if (!ablated("scan")) k_scan<<<grid_for(ctx, n_tiles, 1, 16), BK_SCAN_THREADS, tile_bytes + 64, ctx->stream>>>(
+    int sp = ctx->span_begin(ST_SCAN, st);
+    if (!ablated("scan")) k_scan<<<grid_for(ctx, n_tiles, 1, 16), BK_SCAN_THREADS, tile_bytes + 64, st>>>(
         v, d_bases, d_off, off_bias, r_begin, r_end, tile_reads, tile_bytes, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->span_end(sp);
     ctx->launches++; ctx->scan_launches++;
     BK_CUDA(cudaGetLastError());
-    sp = ctx->span_begin(ST_LEFTOVER);
-    if (ablated("leftover")) {}
-    else if (f.list_mode) k_leftover<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
-    else k_leftover<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, ctx->stream>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
+    sp = ctx->span_begin(ST_LEFTOVER, st);
+    if (!ablated("leftover")) k_leftover<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(v, d_bases, &ctx->d_ctr.p->f[slot].gen_new);
     ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
@@ -607,29 +679,41 @@ int bk_reads_push_device(bk_ctx* ctx, int slot, const uint8_t* d_bases, const ui
                          uint64_t n_bases, uint32_t max_read_len) {
     int rc = check_push(ctx, slot);
     if (rc) return rc;
-    if (n_reads == 0) { return file_prepare(ctx, slot, 0); }
+    if (n_reads == 0) { return file_prepare(ctx, slot); }
     if (!d_bases || !d_off) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: null buffer");
     if (((uintptr_t)d_bases & 15) != 0) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: bases must be 16-byte aligned");
     if (n_reads >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFF0ull) return ctx->fail(BK_ERR_ARG, "bk_reads_push_device: push at most 2^32-16 bases / reads at a time");
-    if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
-    if ((rc = novel_room(ctx, slot, n_bases))) return rc;
-    ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
-    return launch_count(ctx, slot, d_bases, d_off, 0, 0, (u32)n_reads, max_read_len);
+    return guarded(ctx, [&]() -> int {
+        int rc;
+        if ((rc = file_prepare(ctx, slot))) return rc;
+        if ((rc = novel_room(ctx, slot, n_bases))) return rc;
+        ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
+        return launch_count(ctx, slot, d_bases, d_off, 0, 0, (u32)n_reads, max_read_len);
+    });
 }
 
 int bk_reads_push(bk_ctx* ctx, int slot, const uint8_t* bases, const uint32_t* read_off, uint64_t n_reads) {
     int rc = check_push(ctx, slot);
     if (rc) return rc;
-    if (n_reads == 0) return file_prepare(ctx, slot, 0);
+    if (n_reads == 0) return file_prepare(ctx, slot);
     if (!bases || !read_off) return ctx->fail(BK_ERR_ARG, "bk_reads_push: null buffer");
     if (n_reads >= 0xFFFFFFFFull) return ctx->fail(BK_ERR_ARG, "bk_reads_push: too many reads in one push");
+    return guarded(ctx, [&]() -> int {
+    int rc;
+    cudaStream_t st = ctx->s_count[slot];
     const u64 n_bases = read_off[n_reads];
-    if ((rc = file_prepare(ctx, slot, n_bases))) return rc;
+    if ((rc = file_prepare(ctx, slot))) return rc;
     if ((rc = novel_room(ctx, slot, n_bases))) return rc;
     ctx->file[slot].total_reads += n_reads; ctx->file[slot].total_bases += n_bases;
-    // offsets once, bases in chunks through two staging buffers so H2D overlaps the kernels
+    // offsets once, bases in chunks through two staging buffers so H2D overlaps the kernels.  Every copy from the
+    // caller's buffers is issued on copy_stream, which is synchronised before returning: the caller may refill its
+    // (pinned) buffers at once.  The offsets buffer is reused by every push: its copy waits for the kernels of the
+    // previous push that still read it (off_free); a growing reserve() frees only after the device is idle (cudaFree).
+    BK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->off_free, 0));
     BK_CUDA(ctx->d_stage_off.reserve(n_reads + 1));
-    BK_CUDA(cudaMemcpyAsync(ctx->d_stage_off.p, read_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(ctx->d_stage_off.p, read_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    BK_CUDA(cudaEventRecord(ctx->off_copied, ctx->copy_stream));
+    BK_CUDA(cudaStreamWaitEvent(st, ctx->off_copied, 0));
     const u64 CHUNK = 64ull << 20;
     u64 r = 0;
     while (r < n_reads) {
@@ -647,15 +731,16 @@ int bk_reads_push(bk_ctx* ctx, int slot, const uint8_t* bases, const uint32_t* r
         BK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
         BK_CUDA(cudaMemcpyAsync(ctx->d_stage[b].p, bases + c_begin, c_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         BK_CUDA(cudaEventRecord(ctx->stage_copied[b], ctx->copy_stream));
-        BK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_copied[b], 0));
+        BK_CUDA(cudaStreamWaitEvent(st, ctx->stage_copied[b], 0));
         if ((rc = launch_count(ctx, slot, ctx->d_stage[b].p, ctx->d_stage_off.p, c_begin, (u32)r, (u32)r_end, max_len))) return rc;
-        BK_CUDA(cudaEventRecord(ctx->stage_free[b], ctx->stream));
+        BK_CUDA(cudaEventRecord(ctx->stage_free[b], st));
         r = r_end;
     }
+    BK_CUDA(cudaEventRecord(ctx->off_free, st));
     // the caller may reuse its buffers once we return: wait for the copies (not for the kernels)
     BK_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-    BK_CUDA(cudaEventSynchronize(ctx->stage_copied[ctx->stage_next ^ 1]));
     return BK_OK;
+    });
 }
 
 int bk_reads_push_decoded(bk_ctx* ctx, int slot, const bk_reads* reads) {
@@ -670,9 +755,9 @@ int bk_reads_push_decoded(bk_ctx* ctx, int slot, const bk_reads* reads) {
         if (n_reads == 0) continue;
         any = true;
         if ((rc = bk_reads_push(ctx, slot, bases, off, n_reads))) return rc;
-        BK_CUDA(cudaStreamSynchronize(ctx->stream));    // pageable source: the caller may free `reads` when this returns
+        BK_CUDA(cudaStreamSynchronize(ctx->s_count[slot]));    // pageable source: the caller may free `reads` when this returns
     }
-    if (!any) return file_prepare(ctx, slot, 0);          // an empty file is still a file of the sample
+    if (!any) return file_prepare(ctx, slot);             // an empty file is still a file of the sample
     return BK_OK;
 }
 
@@ -688,20 +773,27 @@ int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
     return rc;
 }
 
-// ---- stages of bk_sample_finish (also driven one by one in the read-sharded mode) ---------------
+// ---- stages of bk_sample_finish (the read-sharded mode drives the same stages, bk_shard.inc) ---------------
+
+static void launch_prefix(bk_ctx* ctx, u32* a, u32 n, u32* bsum, cudaStream_t st) {     // a[0..n] := exclusive prefix, a[n] = total
+    const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
+    k_diff_blocksum<<<nb, BK_PS_THREADS, 0, st>>>(a, n, bsum);
+    k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, st>>>(bsum, nb);
+    k_excl_apply<<<nb, BK_PS_THREADS, 0, st>>>(a, n, bsum);
+    ctx->launches += 3;
+}
 
 // stage 1: prefix sum of the difference array + fold onto distinct reference k-mers → idcnt
-static int stage_fold(bk_ctx* ctx, int slot) {
-    ctx->use_level(1);
+static int stage_fold(bk_ctx* ctx, int slot, cudaStream_t st) {
     FileState& f = ctx->file[slot];
     if (f.folded) return BK_OK;
     const DerivedIndex& d = ctx->I->d;
     const u32 n = d.n_raw;
     const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
-    int sp = ctx->span_begin(ST_FINALIZE);
-    k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p);
-    k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
-    k_diff_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.diff.p, n, ctx->d_bsum.p, ctx->I->d_slot2id.p, f.idcnt.p);
+    int sp = ctx->span_begin(ST_FINALIZE, st);
+    k_diff_blocksum<<<nb, BK_PS_THREADS, 0, st>>>(f.diff.p, n, f.bsum.p);
+    k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, st>>>(f.bsum.p, nb);
+    k_diff_apply<<<nb, BK_PS_THREADS, 0, st>>>(f.diff.p, n, f.bsum.p, ctx->I->d_slot2id.p, f.idcnt.p);
     ctx->span_end(sp);
     ctx->launches += 3;
     BK_CUDA(cudaGetLastError());
@@ -709,51 +801,62 @@ static int stage_fold(bk_ctx* ctx, int slot) {
     return BK_OK;
 }
 
-// stage 2: compaction = the KMC dump of one file (threshold, cap, the four stdout numbers)
-static int stage_compact(bk_ctx* ctx, int slot) {
+static CompactArgs make_compact_args(bk_ctx* ctx, int slot, size_t out_cap) {
+    FileState& f = ctx->file[slot];
+    CompactArgs a;
+    a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n();
+    a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
+    a.fc = &ctx->d_ctr.p->f[slot];
+    return a;
+}
+
+// the list of `ub` (an upper bound) entries → bins: P = 2^lp bins sized so that a worst-case round of a bin is ~1/32 of
+// the bound at 3 % of it novel; histogram, prefix, scatter.  W: entries carry weights.
+static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted, cudaStream_t st) {
+    FileState& f = ctx->file[slot];
+    const DerivedIndex& d = ctx->I->d;
+    u32 lp = 6;
+    while (lp < 14 && ((u64)BK_BIN_ROUND << lp) < ub / 32) lp++;
+    f.bin_log2p = lp;
+    const u32 P = 1u << lp, G = (u32)ctx->sm_count * BK_BIN_G_PER_SM, PG = P * G;
+    BK_CUDA(f.bin_cnt.reserve((size_t)PG + 1));
+    b.cnt = f.bin_cnt.p; b.log2p = lp; b.G = G;
+    b.exact = ctx->I->d_exact.p; b.exact_shift = 64 - d.exact_log2; b.exact_mask = (1u << d.exact_log2) - 1;
+    b.slot2id = ctx->I->d_slot2id.p; b.idcnt = f.idcnt.p;
+    k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
+    launch_prefix(ctx, f.bin_cnt.p, PG, f.bsum.p, st);
+    if (weighted) k_bin_scatter<true><<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
+    else k_bin_scatter<false><<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
+    ctx->launches += 2;
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+// stage 2: the KMC dump of one file (threshold, cap, the four stdout numbers): novel k-mers through the bins, then the
+// reference k-mers (after the bins: they add to idcnt)
+static int stage_compact(bk_ctx* ctx, int slot, cudaStream_t st) {
     FileState& f = ctx->file[slot];
     if (f.finalized) return BK_OK;
     const DerivedIndex& d = ctx->I->d;
     const u32 n_ids = (u32)d.id_kmer.size();
-    // the novel part of the list: a kept k-mer stands for >= ci occurrences (list mode) / occupies a table slot
-    const size_t novel_cap = f.list_mode ? std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)) / std::max<u32>(ctx->params.min_kmers, 1) + 1
-                                         : (size_t)(1ull << f.gen_log2);
+    // the novel part of the list: a kept k-mer stands for >= ci occurrences
+    const size_t novel_cap = std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)) / std::max<u32>(ctx->params.min_kmers, 1) + 1;
     const size_t out_cap = (size_t)n_ids + novel_cap;
     BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
-    int sp = ctx->span_begin(ST_FINALIZE);
-    CompactArgs a;
-    a.ci = ctx->params.min_kmers; a.cs = ctx->params.counter_max; a.rank = ctx->shard_rank; a.n_ranks = ctx->shard_n;
-    a.out_kmers = f.ckmers.p; a.out_counts = f.ccounts.p; a.out_cap = (u32)std::min<size_t>(out_cap, 0xFFFFFFFFu);
-    a.fc = &ctx->d_ctr.p->f[slot];
-    if (!f.list_mode) {
-        k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
-        k_compact_gen<<<grid_for(ctx, 1ull << f.gen_log2, 256), 256, 0, ctx->stream>>>(a, f.gen.p, (u32)(1ull << f.gen_log2));
-        ctx->launches += 2;
-    } else {
-        // bins sized for the room the pushes were given (≈ 5 % of it is used at 0.2 % error: a few hundred k-mers per bin)
-        BinView b;
-        u32 lp = 6;                          // a round of a bin is sized for 1/32 of the room: 3 % of the bases novel
-        while (lp < 14 && ((u64)BK_BIN_ROUND << lp) < f.nov_ub / 32) lp++;
-        f.bin_log2p = lp;
-        const u32 P = 1u << lp, G = (u32)ctx->sm_count * BK_BIN_G_PER_SM, PG = P * G;
-        const u32 nb = (PG + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
-        BK_CUDA(f.bin_cnt.reserve((size_t)PG + 1));
-        BK_CUDA(ctx->d_nov_sorted.reserve(std::max<size_t>(f.nov.cap, 1)));
-        b.nov = f.nov.p; b.nov_n = &ctx->d_ctr.p->f[slot].nov_n; b.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
-        b.sorted = ctx->d_nov_sorted.p; b.cnt = f.bin_cnt.p; b.log2p = lp; b.G = G;
-        b.exact = ctx->I->d_exact.p; b.exact_shift = 64 - d.exact_log2; b.exact_mask = (1u << d.exact_log2) - 1;
-        b.slot2id = ctx->I->d_slot2id.p; b.idcnt = f.idcnt.p;
-        if (!ablated("bins")) {
-        k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
-        k_diff_blocksum<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
-        k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, ctx->stream>>>(ctx->d_bsum.p, nb);
-        k_excl_apply<<<nb, BK_PS_THREADS, 0, ctx->stream>>>(f.bin_cnt.p, PG, ctx->d_bsum.p);
-        k_bin_scatter<<<G, BK_BIN_G_THREADS, P * 4, ctx->stream>>>(b);
-        if (!ablated("bincount")) k_bin_count<<<P, 256, BK_BIN_SMEM, ctx->stream>>>(b, a, &ctx->d_ctr.p->gen_full);
-        }
-        k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, ctx->stream>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);   // after the bins: they add to idcnt
-        ctx->launches += 7;
+    BK_CUDA(f.sorted.reserve(std::max<size_t>(std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)), 1)));
+    int sp = ctx->span_begin(ST_FINALIZE, st);
+    const CompactArgs a = make_compact_args(ctx, slot, out_cap);
+    BinView b; memset(&b, 0, sizeof b);
+    b.nov = f.nov.p; b.nov_n = &ctx->d_ctr.p->f[slot].nov_n; b.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
+    b.sorted = f.sorted.p;
+    if (!ablated("bins")) {
+        int rc = launch_bins(ctx, slot, b, f.nov_ub, false, st);
+        if (rc) return rc;
+        if (!ablated("bincount")) k_bin_count<0><<<1u << b.log2p, 256, BK_BIN_SMEM, st>>>(b, a, &ctx->d_ctr.p->gen_full);
+        ctx->launches++;
     }
+    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, st>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
+    ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
     f.finalized = true;
@@ -779,99 +882,92 @@ static MapView make_map_view(bk_ctx* ctx) {
 
 static int n_files_used(bk_ctx* ctx) { return ctx->file[1].used ? 2 : 1; }
 
-// stages 3 + 4 in one pass per file for databases of at most four genomes (re-keyed table, not sharded): tallies and
-// the pileups of all genomes together, selection, then the selected genome's arrays are moved to d_pile
-static bool can_fuse_map(const bk_ctx* ctx) {
-    return ctx->I->d.n_genomes <= 4 && ctx->I->d.rekeyed && !ctx->force_warp_map && ctx->shard_n == 1 && !ctx->no_fused_map;
-}
-static int stage_map_fused(bk_ctx* ctx) {
-    ctx->use_level(1);
+// per-genome hit counts of one k-mer fit the 16-bit fields of the thread-per-k-mer kernels (a query hits at most k buckets)
+static bool hits16_ok(const bk_ctx* ctx) { return (u64)ctx->I->d.max_key_entries * ctx->I->ix.k < 65536ull; }
+static bool small_db(const bk_ctx* ctx) { return ctx->I->d.n_genomes <= 4 && !ctx->force_warp_map && hits16_ok(ctx); }
+// tallies and the pileups of all genomes in ONE pass per file (databases of at most four genomes, re-keyed table),
+// selection afterwards, then the selected genome's arrays are moved to d_pile
+static bool can_fuse_map(const bk_ctx* ctx) { return small_db(ctx) && ctx->I->d.rekeyed && !ctx->no_fused_map; }
+
+// one-pass map of one file (can_fuse_map): tallies + the pileups of every genome (src/call.rs:1316-1385)
+static int stage_map_fused(bk_ctx* ctx, int f, cudaStream_t st) {
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
-    const int n_files = n_files_used(ctx);
     Counters* dc = ctx->d_ctr.p;
-    cudaStream_t st = ctx->stream;
-    int sp = ctx->span_begin(ST_MAP);
-    BK_CUDA(cudaMemsetAsync(ctx->d_pile_all.p, 0, (size_t)pile_stride * 4 * 4 * d.n_genomes, st));
-    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
-    for (int f = 0; f < n_files; f++) {
-        FileState& fs = ctx->file[f];
-        BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
-        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (ablated("map")) {}
-        else if (m.gslots) k_map_grp<2><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
-        else k_map_small<2, 1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
-        ctx->launches++;
-    }
-    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
-    k_pile_pick<<<ctx->sm_count, 256, 0, st>>>(ctx->d_pile_all.p, ctx->d_pile.p, pile_stride, &dc->best);
-    ctx->launches += 2;
+    FileState& fs = ctx->file[f];
+    int sp = ctx->span_begin(ST_MAP, st);
+    BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
+    const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+    if (ablated("map")) {}
+    else if (m.gslots) k_map_grp<2><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+    else k_map_small<2, 1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
+    ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
     return BK_OK;
 }
 
-// stage 3: map_kmers tallies of every file (src/call.rs:1389-1430)
-static int stage_map_stats(bk_ctx* ctx) {
-    ctx->use_level(1);
+// pick_best_genome(_paired) (src/call.rs:422-502); after a fused map also the move of the selected genome's arrays
+static int stage_select(bk_ctx* ctx, bool fused, cudaStream_t st) {
+    const DerivedIndex& d = ctx->I->d;
+    const int n_files = n_files_used(ctx);
+    Counters* dc = ctx->d_ctr.p;
+    int sp = ctx->span_begin(ST_MAP, st);
+    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
+    ctx->launches++;
+    if (fused) { k_pile_pick<<<ctx->sm_count, 256, 0, st>>>(ctx->d_pile_all.p, ctx->d_pile.p, d.max_genome_rows * 4, &dc->best); ctx->launches++; }
+    ctx->span_end(sp);
+    BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+// two-pass map, pass 1: map_kmers tallies of one file (src/call.rs:1389-1430)
+static int stage_map_stats(bk_ctx* ctx, int f, cudaStream_t st) {
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
     const size_t map_smem = (size_t)d.n_genomes * 12 * 4;
-    const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
+    const bool small = small_db(ctx);
     Counters* dc = ctx->d_ctr.p;
-    cudaStream_t st = ctx->stream;
-    int sp = ctx->span_begin(ST_MAP);
-    for (int f = 0; f < n_files_used(ctx); f++) {
-        FileState& fs = ctx->file[f];
-        BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
-        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && m.gslots) k_map_grp<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else if (small_db) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
-        ctx->launches++;
-    }
+    FileState& fs = ctx->file[f];
+    int sp = ctx->span_begin(ST_MAP, st);
+    BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
+    const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+    if (small && m.gslots) k_map_grp<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+    else if (small) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+    else (d.rekeyed ? k_map<0, 1> : k_map<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, map_smem, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
+    ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
     return BK_OK;
 }
 
-// stage 4: pick_best_genome(_paired) + the selected genome's pileup (src/call.rs:1324-1385)
-static int stage_select_pileup(bk_ctx* ctx) {
-    ctx->use_level(1);
+// two-pass map, pass 2: the selected genome's pileup from one file (src/call.rs:1324-1385)
+static int stage_map_pileup(bk_ctx* ctx, int f, cudaStream_t st) {
     const DerivedIndex& d = ctx->I->d;
     const MapView m = make_map_view(ctx);
-    const bool small_db = d.n_genomes <= 4 && !ctx->force_warp_map;
+    const bool small = small_db(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
-    const int n_files = n_files_used(ctx);
     Counters* dc = ctx->d_ctr.p;
-    cudaStream_t st = ctx->stream;
-    int sp = ctx->span_begin(ST_MAP);
-    BK_CUDA(cudaMemsetAsync(ctx->d_pile.p, 0, (size_t)pile_stride * 4 * 4, st));
-    k_select<<<1, 32, 0, st>>>(ctx->file[0].gstats.p, ctx->file[n_files - 1].gstats.p, n_files, d.n_genomes, ctx->I->d_genome_len.p, dc);
+    FileState& fs = ctx->file[f];
+    int sp = ctx->span_begin(ST_MAP, st);
+    const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
+    if (small && m.gslots) k_map_grp<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+    else if (small) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
+    else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
     ctx->launches++;
-    for (int f = 0; f < n_files; f++) {
-        FileState& fs = ctx->file[f];
-        const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
-        if (small_db && m.gslots) k_map_grp<1><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else if (small_db) (d.rekeyed ? k_map_small<1, 1> : k_map_small<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        else (d.rekeyed ? k_map<1, 1> : k_map<1, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, nullptr, &dc->best, ctx->d_pile.p, pile_stride);
-        ctx->launches++;
-    }
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());
     return BK_OK;
 }
 
-// stage 5: noise baseline + call_variants, read everything back, fill bk_sample_result
-static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
-    ctx->use_level(2);
+// last stage: noise baseline + call_variants, read everything back, fill bk_sample_result
+static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     const DerivedIndex& d = ctx->I->d;
     const int n_files = n_files_used(ctx);
     const u32 pile_stride = d.max_genome_rows * 4;
     Counters* dc = ctx->d_ctr.p;
-    cudaStream_t st = ctx->stream;
-    int sp = ctx->span_begin(ST_SCORE);
+    int sp = ctx->span_begin(ST_SCORE, st);
     ScoreView sv;
     sv.n_genomes = d.n_genomes; sv.genome_row0 = ctx->I->d_genome_row0.p; sv.genome_seq_off = ctx->I->d_genome_seq_off.p;
     sv.seq_row0 = ctx->I->d_seq_row0.p; sv.ref_code = ctx->I->d_ref_code.p; sv.ctr = dc; sv.pile = ctx->d_pile.p; sv.pile_stride = pile_stride;
@@ -916,10 +1012,16 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
         hg[f].resize((size_t)d.n_genomes * 4);
         BK_CUDA(cudaMemcpyAsync(hg[f].data(), ctx->file[f].gstats.p, hg[f].size() * 4, cudaMemcpyDeviceToHost, st));
     }
-    BK_CUDA(cudaStreamSynchronize(st));
+    if (ctx->shard) {                                    // the globally reduced KMC numbers of both files (bk_shard.cuh: k_shard_pack)
+        const u32 stride = 4 + d.n_genomes * 4;
+        BK_CUDA(cudaMemcpyAsync(ctx->h_stats, ctx->d_shard_stats.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        BK_CUDA(cudaMemcpyAsync(ctx->h_stats + 4, ctx->d_shard_stats.p + stride, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    }
+    BK_CUDA(cudaEventRecord(ctx->ev_end, st));
+    BK_CUDA(cudaEventSynchronize(ctx->ev_end));          // blocking wait (BK_SPIN=1 spins): the host thread sleeps while the GPU works
     const Counters& c = *ctx->h_ctr;
     ctx->finished = true;
-    if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "no room left for novel k-mers (table / list / bin table); set bk_params.table_log2 higher");
+    if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "no room left for novel k-mers (list / bin table); set bk_params.table_log2 higher");
     if (c.var_overflow) return ctx->fail(BK_ERR_OVERFLOW, "variant buffer overflow");
     for (int f = 0; f < n_files; f++) {
         if ((size_t)c.f[f].n_counted > ctx->file[f].ckmers.cap) return ctx->fail(BK_ERR_OVERFLOW, "counted k-mer list overflow");
@@ -933,16 +1035,16 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     memset(&r, 0, sizeof r);
     r.best_genome = c.best; r.n_files = n_files;
     for (int f = 0; f < n_files; f++) {
-        if (ctx->shard_n > 1) r.kmc[f] = ctx->shard_kmc[f];      // globally reduced numbers supplied by the host
-        else {
+        if (ctx->shard) {
+            r.kmc[f].total_reads = ctx->h_stats[f * 4]; r.kmc[f].total_kmers = ctx->h_stats[f * 4 + 1];
+            r.kmc[f].unique_kmers = ctx->h_stats[f * 4 + 2]; r.kmc[f].unique_counted = ctx->h_stats[f * 4 + 3];
+        } else {
             r.kmc[f].total_reads = ctx->file[f].total_reads; r.kmc[f].total_kmers = c.f[f].total_kmers;
             r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = c.f[f].n_counted;
         }
     }
-    cudaEventRecord(ctx->ev_end, st);
     if (c.best < 0) {
         if (out) *out = r;
-        cudaEventSynchronize(ctx->ev_end);
         return ctx->fail(BK_ERR_NO_GENOME, "Unable to pick a best genome");
     }
     r.n_variants = c.n_var; r.num_major_variants = c.n_major; r.num_minor_variants = c.n_minor;
@@ -960,25 +1062,22 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out) {
     ctx->variants.resize(c.n_var);
     if (c.n_var) {
         BK_CUDA(cudaMemcpyAsync(ctx->variants.data(), ctx->d_vars.p, (size_t)c.n_var * sizeof(bk_variant), cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(ctx->ev_end, st);
         BK_CUDA(cudaStreamSynchronize(st));
         std::sort(ctx->variants.begin(), ctx->variants.end(), [](const bk_variant& a, const bk_variant& b) {
             if (a.seq != b.seq) return a.seq < b.seq;
             if (a.pos != b.pos) return a.pos < b.pos;
             return a.alt_base < b.alt_base;
         });
-    } else {
-        cudaEventSynchronize(ctx->ev_end);
     }
     bk_stage_times& t = ctx->times;
     memset(&t, 0, sizeof t);
-    float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms};
+    float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms, &t.coll_ms};
     for (size_t i = 0; i < ctx->spans_used; i++) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b) == cudaSuccess) *acc[ctx->spans[i].stage] += ms;
     }
     cudaEventElapsedTime(&t.total_ms, ctx->ev_begin, ctx->ev_end);
-    t.launches = ctx->launches; t.scan_launches = ctx->scan_launches;
+    t.launches = ctx->launches; t.scan_launches = ctx->scan_launches; t.coll_calls = ctx->coll_calls;
     if (out) *out = r;
     return BK_OK;
 }
@@ -991,142 +1090,51 @@ static int check_finish(bk_ctx* ctx, const char* who) {
     return BK_OK;
 }
 
+static int shard_finish(ShardGroup& G, std::vector<bk_ctx*>& ms, bk_sample_result* out);      // bk_shard.inc
+
 int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
     int rc = check_finish(ctx, "bk_sample_finish");
     if (rc) return rc;
-    if (ctx->shard_n > 1) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: context is in sharded mode; drive the bk_shard_* stages");
-    for (int f = 0; f < n_files_used(ctx); f++) {
-        if ((rc = stage_fold(ctx, f))) return rc;
-        if ((rc = stage_compact(ctx, f))) return rc;
+    return guarded(ctx, [&]() -> int {
+    int rc;
+    if (ctx->shard) {
+        if (ctx->shard->local) return ctx->fail(BK_ERR_ARG, "bk_sample_finish: context belongs to an in-process shard group; call bk_shard_finish_local");
+        std::vector<bk_ctx*> me(1, ctx);
+        return shard_finish(*ctx->shard, me, out);
     }
-    if (can_fuse_map(ctx)) { if ((rc = stage_map_fused(ctx))) return rc; }
-    else {
-        if ((rc = stage_map_stats(ctx))) return rc;
-        if ((rc = stage_select_pileup(ctx))) return rc;
-    }
-    return stage_score(ctx, out);
-}
-
-// ---------------------------------------------------------------------------------------------
-// read-sharded deep sample.  Every rank scans its share of the reads of ONE sample;
-// k-mer counts are merged across ranks before the threshold / cap / max-pileup:
-//   bk_shard_begin            per-rank partial counts are folded; novel k-mers are compacted and
-//                             partitioned by owner rank
-//   (host)                    all-reduce(SUM) the dense reference-k-mer counts; all-to-all the novel
-//                             (k-mer, count) pairs to their owners
-//   bk_shard_import_novel     the owner rebuilds its novel table from the merged pairs
-//   bk_shard_map_stats        threshold + cap on the merged counts (each reference k-mer id and each
-//                             novel k-mer is owned by exactly one rank), per-genome tallies
-//   (host)                    all-reduce(SUM) the tallies and the KMC numbers
-//   bk_shard_select_pileup    selection (same on every rank) + this rank's pileup contribution
-//   (host)                    all-reduce(MAX) the two depth arrays, all-reduce(SUM) the two support arrays
-//   bk_shard_score            noise + variants (every rank gets the same result)
-// ---------------------------------------------------------------------------------------------
-int bk_shard_config(bk_ctx* ctx, uint32_t rank, uint32_t n_ranks) {
-    if (!ctx) return BK_ERR_ARG;
-    if (ctx->in_sample && !ctx->finished) return ctx->fail(BK_ERR_ARG, "bk_shard_config: call between samples");
-    if (n_ranks == 0 || rank >= n_ranks || n_ranks > 1024) return ctx->fail(BK_ERR_ARG, "bk_shard_config: bad rank / n_ranks");
-    ctx->shard_rank = rank; ctx->shard_n = n_ranks;
-    return BK_OK;
-}
-
-int bk_shard_begin(bk_ctx* ctx, int file_slot, void** d_ref_counts, uint64_t* n_ref_counts, void** d_novel_kmers,
-                   void** d_novel_counts, uint64_t* part_off) {
-    int rc = check_finish(ctx, "bk_shard_begin");
-    if (rc) return rc;
-    if (file_slot < 0 || file_slot > 1 || !ctx->file[file_slot].used) return ctx->fail(BK_ERR_ARG, "bk_shard_begin: file slot %d has no reads", file_slot);
-    if (!d_ref_counts || !n_ref_counts || !d_novel_kmers || !d_novel_counts || !part_off) return ctx->fail(BK_ERR_ARG, "bk_shard_begin: null argument");
-    FileState& f = ctx->file[file_slot];
-    if ((rc = stage_fold(ctx, file_slot))) return rc;
-    const u32 n_slots = (u32)(1ull << f.gen_log2);
-    const u32 nr = ctx->shard_n;
-    BK_CUDA(ctx->d_part.reserve((size_t)nr * 2));
-    BK_CUDA(cudaMemsetAsync(ctx->d_part.p, 0, (size_t)nr * 2 * 4, ctx->stream));
-    k_novel_partition<0><<<grid_for(ctx, n_slots, 256), 256, nr * 4, ctx->stream>>>(f.gen.p, n_slots, nr, ctx->d_part.p, nullptr, nullptr, nullptr);
-    std::vector<u32> cnt(nr);
-    BK_CUDA(cudaMemcpyAsync(cnt.data(), ctx->d_part.p, nr * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<u32> start(nr);
-    u64 total = 0;
-    for (u32 r = 0; r < nr; r++) { part_off[r] = total; start[r] = (u32)total; total += cnt[r]; }
-    part_off[nr] = total;
-    BK_CUDA(f.xk.reserve(total + 1)); BK_CUDA(f.xc.reserve(total + 1));
-    BK_CUDA(cudaMemsetAsync(ctx->d_part.p, 0, (size_t)nr * 4, ctx->stream));
-    BK_CUDA(cudaMemcpyAsync(ctx->d_part.p + nr, start.data(), nr * 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_novel_partition<1><<<grid_for(ctx, n_slots, 256), 256, nr * 4, ctx->stream>>>(f.gen.p, n_slots, nr, ctx->d_part.p, ctx->d_part.p + nr, f.xk.p, f.xc.p);
-    ctx->launches += 2;
-    BK_CUDA(cudaGetLastError());
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    *d_ref_counts = f.idcnt.p; *n_ref_counts = ctx->I->d.id_kmer.size();
-    *d_novel_kmers = f.xk.p; *d_novel_counts = f.xc.p;
-    return BK_OK;
-}
-
-int bk_shard_import_novel(bk_ctx* ctx, int file_slot, const void* d_kmers, const void* d_counts, uint64_t n) {
-    int rc = check_finish(ctx, "bk_shard_import_novel");
-    if (rc) return rc;
-    if (file_slot < 0 || file_slot > 1 || !ctx->file[file_slot].used) return ctx->fail(BK_ERR_ARG, "bk_shard_import_novel: bad file slot");
-    FileState& f = ctx->file[file_slot];
-    u32 lg = 10;
-    while ((1ull << lg) < 2 * n + 16) lg++;
-    if (lg > 31) return ctx->fail(BK_ERR_OVERFLOW, "too many novel k-mers for one rank");
-    f.gen_log2 = lg;
-    BK_CUDA(f.gen.reserve(1ull << lg));
-    k_gen_init<<<grid_for(ctx, 1ull << lg, 256 * 8), 256, 0, ctx->stream>>>(f.gen.p, 1ull << lg);
-    if (n) k_novel_insert<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(f.gen.p, 64 - lg, (u32)((1ull << lg) - 1), (const u64*)d_kmers, (const u32*)d_counts, n,
-                                                                           &ctx->d_ctr.p->gen_full);
-    ctx->launches += 2;
-    BK_CUDA(cudaGetLastError());
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));     // the caller may free / reuse its buffers now
-    return BK_OK;
-}
-
-int bk_shard_map_stats(bk_ctx* ctx, void** d_tallies0, void** d_tallies1, uint64_t* n_tallies, bk_kmc_stats* partial) {
-    int rc = check_finish(ctx, "bk_shard_map_stats");
-    if (rc) return rc;
     const int n_files = n_files_used(ctx);
-    for (int f = 0; f < n_files; f++) {
-        if (!ctx->file[f].folded) return ctx->fail(BK_ERR_ARG, "bk_shard_map_stats: call bk_shard_begin for file %d first", f);
-        if ((rc = stage_compact(ctx, f))) return rc;
+    const bool fused = can_fuse_map(ctx);
+    for (int f = 0; f < n_files; f++) {                    // the files run side by side until the selection
+        cudaStream_t st = ctx->s_fin[f];
+        ctx->chain(ctx->s_count[f], st);
+        if ((rc = stage_fold(ctx, f, st))) return rc;
+        if ((rc = stage_compact(ctx, f, st))) return rc;
+        if ((rc = fused ? stage_map_fused(ctx, f, st) : stage_map_stats(ctx, f, st))) return rc;
+        ctx->chain(st, ctx->s_score);
     }
-    if ((rc = stage_map_stats(ctx))) return rc;
-    BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_ctr->gen_full) return ctx->fail(BK_ERR_OVERFLOW, "novel k-mer table is full; set bk_params.table_log2 higher");
-    for (int f = 0; f < 2; f++) {
-        bk_kmc_stats z; memset(&z, 0, sizeof z);
-        if (f < n_files) {
-            z.total_reads = ctx->file[f].total_reads; z.total_kmers = ctx->h_ctr->f[f].total_kmers;
-            z.unique_kmers = ctx->h_ctr->f[f].unique; z.unique_counted = ctx->h_ctr->f[f].n_counted;
+    if ((rc = stage_select(ctx, fused, ctx->s_score))) return rc;
+    if (!fused) {
+        for (int f = 0; f < n_files; f++) {
+            ctx->chain(ctx->s_score, ctx->s_fin[f]);
+            if ((rc = stage_map_pileup(ctx, f, ctx->s_fin[f]))) return rc;
         }
-        if (partial) partial[f] = z;
+        for (int f = 0; f < n_files; f++) ctx->chain(ctx->s_fin[f], ctx->s_score);
     }
-    if (d_tallies0) *d_tallies0 = ctx->file[0].gstats.p;
-    if (d_tallies1) *d_tallies1 = n_files > 1 ? ctx->file[1].gstats.p : nullptr;
-    if (n_tallies) *n_tallies = (u64)ctx->I->d.n_genomes * 4;
-    return BK_OK;
+    return stage_score(ctx, out, ctx->s_score);
+    });
 }
 
-int bk_shard_select_pileup(bk_ctx* ctx, const bk_kmc_stats* global_kmc, void** d_pile, uint64_t* n_per_array) {
-    int rc = check_finish(ctx, "bk_shard_select_pileup");
-    if (rc) return rc;
-    if (global_kmc) { ctx->shard_kmc[0] = global_kmc[0]; ctx->shard_kmc[1] = global_kmc[1]; }
-    if ((rc = stage_select_pileup(ctx))) return rc;
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (d_pile) *d_pile = ctx->d_pile.p;
-    if (n_per_array) *n_per_array = (u64)ctx->I->d.max_genome_rows * 4;
-    return BK_OK;
-}
-
-int bk_shard_score(bk_ctx* ctx, bk_sample_result* out) {
-    int rc = check_finish(ctx, "bk_shard_score");
-    if (rc) return rc;
-    return stage_score(ctx, out);
-}
+#include "bk_shard.inc"
 
 int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out) {
     if (!ctx || !out) return BK_ERR_ARG;
     *out = ctx->times;
+    return BK_OK;
+}
+
+int bk_sample_result_get(bk_ctx* ctx, bk_sample_result* out) {
+    if (!ctx || !ctx->finished || !out) return BK_ERR_ARG;
+    *out = ctx->result;
     return BK_OK;
 }
 
@@ -1152,8 +1160,8 @@ int bk_sample_pileup(bk_ctx* ctx, int arr, uint64_t* out, uint64_t cap_rows) {
     const u32 rows = ctx->I->d.genome_row0[best + 1] - ctx->I->d.genome_row0[best];
     if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_pileup: buffer too small (%u rows)", rows);
     std::vector<u32> tmp((size_t)rows * 4);
-    BK_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_pile.p + (size_t)arr * ctx->I->d.max_genome_rows * 4, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_pile.p + (size_t)arr * ctx->I->d.max_genome_rows * 4, tmp.size() * 4, cudaMemcpyDeviceToHost, ctx->s_score));
+    BK_CUDA(cudaStreamSynchronize(ctx->s_score));
     for (size_t i = 0; i < tmp.size(); i++) out[i] = tmp[i];
     return BK_OK;
 }
@@ -1165,8 +1173,8 @@ int bk_sample_noise_max(bk_ctx* ctx, double* out, uint64_t cap_rows) {
     cudaSetDevice(ctx->device);
     const u32 rows = ctx->I->d.genome_row0[best + 1] - ctx->I->d.genome_row0[best];
     if (cap_rows < rows) return ctx->fail(BK_ERR_ARG, "bk_sample_noise_max: buffer too small");
-    BK_CUDA(cudaMemcpyAsync(out, ctx->d_noise.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(out, ctx->d_noise.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, ctx->s_score));
+    BK_CUDA(cudaStreamSynchronize(ctx->s_score));
     return BK_OK;
 }
 
@@ -1180,9 +1188,9 @@ int bk_kmer_counts_get(bk_ctx* ctx, int slot, uint64_t* kmers, uint32_t* counts,
     *n = have;
     if (!have) return BK_OK;
     std::vector<u64> hk(have); std::vector<u32> hc(have);
-    BK_CUDA(cudaMemcpyAsync(hk.data(), ctx->file[slot].ckmers.p, have * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaMemcpyAsync(hc.data(), ctx->file[slot].ccounts.p, have * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BK_CUDA(cudaStreamSynchronize(ctx->stream));
+    BK_CUDA(cudaMemcpyAsync(hk.data(), ctx->file[slot].ckmers.p, have * 8, cudaMemcpyDeviceToHost, ctx->s_score));
+    BK_CUDA(cudaMemcpyAsync(hc.data(), ctx->file[slot].ccounts.p, have * 4, cudaMemcpyDeviceToHost, ctx->s_score));
+    BK_CUDA(cudaStreamSynchronize(ctx->s_score));
     std::vector<u32> order(have);
     for (u64 i = 0; i < have; i++) order[i] = (u32)i;
     std::sort(order.begin(), order.end(), [&](u32 a, u32 b) { return hk[a] < hk[b]; });

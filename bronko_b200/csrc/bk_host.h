@@ -93,6 +93,8 @@ struct DerivedIndex {
     std::vector<BucketSlot> group_centers;   // key = center, off = first bucket, len = present mask
     std::vector<OffLen> group_buckets;
     std::vector<BucketEntry> bucket_entries;
+    u32 max_key_entries = 0;                 // longest entry list of one key (the thread-per-k-mer map kernels count hits per
+                                             // genome in 16-bit fields: usable while max_key_entries * k < 65536)
     // oriented reference store (forward and reverse-complement of every sequence), 2-bit packed,
     // MSB-first, 32 bases per u64; global base index space with REF_PAD_BASES of padding in front
     std::vector<u64> refpk;

@@ -272,13 +272,17 @@ bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIn
     ix.k = k; ix.meta_k = k;
     // one file = one genome (build.rs:145-231): the files are parsed and their (bucket id, entry) pairs generated on
     // several threads, then joined in file order — the order the reference merges its per-file maps in (223-227)
-    struct FileOut { HostGenome g; std::vector<KeyedEntry> pairs; bool ok = true; };
+    struct FileOut { HostGenome g; std::vector<KeyedEntry> pairs; bool ok = true; std::string why; };
     std::vector<FileOut> outs(paths.size());
     parallel_for(paths.size(), [&](size_t file_id) {
         FileOut& o = outs[file_id];
         u64 ids[32];
         std::string txt;
-        if (!slurp_maybe_gz(paths[file_id], txt)) { o.ok = false; return; }
+        if (!slurp_maybe_gz(paths[file_id], txt)) { o.ok = false; o.why = "Failed to open or inflate the file"; return; }
+        // needletail (parse_fastx_file, src/build.rs:156-159) rejects an empty file and a file that does not start with
+        // a record marker; the reference logs "<error> | Failed to parse fasta file: <path>" and exits
+        if (txt.empty()) { o.ok = false; o.why = "Failed to read the first two bytes. Is the file empty?"; return; }
+        if (txt[0] != '>') { o.ok = false; o.why = std::string("Expected '>' at the start of the file but found '") + txt[0] + "'"; return; }
         HostGenome& g = o.g;
         g.name = path_stem(paths[file_id]);
         size_t pos = 0;
@@ -300,6 +304,9 @@ bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIn
         for (HostSeq& q : g.seqs) {
             q.len = q.bases.size();
             const u64 L = q.len;
+            // src/build.rs:191-192: `for i in 0..=seq_len.saturating_sub(k) { &seq[i..i + k] }` panics for a sequence
+            // shorter than k; here the build fails with a message instead
+            if (L < k) { o.ok = false; o.why = "sequence '" + q.name + "' is shorter than k (the reference panics on it)"; return; }
             if (L >= k) {
                 const u64 kmask = (1ull << (2 * k)) - 1;
                 u64 fwd = 0;
@@ -325,7 +332,7 @@ bool index_build_from_fasta(u32 k, const std::vector<std::string>& paths, HostIn
     });
     size_t total = 0;
     for (size_t file_id = 0; file_id < paths.size(); file_id++) {
-        if (!outs[file_id].ok) { err = "Failed to parse fasta file: " + paths[file_id]; return false; }
+        if (!outs[file_id].ok) { err = outs[file_id].why + " | Failed to parse fasta file: " + paths[file_id]; return false; }
         total += outs[file_id].pairs.size();
     }
     std::vector<KeyedEntry> pairs;
@@ -395,6 +402,7 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         d.bucket_entries[i] = be;
     }
     });
+    for (size_t i = 0; i + 1 < ix.entry_off.size(); i++) d.max_key_entries = std::max<u32>(d.max_key_entries, (u32)std::min<u64>(ix.entry_off[i + 1] - ix.entry_off[i], 0xFFFFFFFFull));
     // Re-key: bucket id j of a canonical k-mer is a perfect rank of (j, k-mer without digit j), so the device can probe
     // with that pair directly and skip the id arithmetic.  Every key is verified against its first entry (the
     // reference k-mer at `location`, canonicalised, digit idx zeroed must rank to exactly this key); one failure (an

@@ -15,9 +15,9 @@ namespace bk {
 struct BucketSlotD { u64 key; u32 off; u32 len; };
 struct BucketEntryD { u32 row; unsigned short file_id; u8 idx; u8 canonical; };
 
-struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 nov_n; u64 total_kmers; };
+struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 nov_n; u64 total_kmers; u32 n_desc; u32 pad; };
 struct Counters {
-    u32 n_desc; u32 gen_full; u32 var_overflow; u32 pad0;
+    u32 gen_full; u32 var_overflow; u32 pad0; u32 pad1;
     FileCounters f[2];
     i32 best; u32 n_var; u32 n_major; u32 n_minor;
     u64 pos_covered; u64 total_cov;
@@ -223,13 +223,6 @@ k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
     if (lane == 0 && created) atomicAdd(gen_new, created);
 }
 
-__global__ void k_gen_init(GenSlot* gen, u64 n) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    uint4* p = reinterpret_cast<uint4*>(gen);
-    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = e;
-}
-
 // ------------------------------------------------------------------------------------------------
 // prefix sum of the difference array (u32, wrap-around arithmetic) + fold onto distinct k-mer ids
 // ------------------------------------------------------------------------------------------------
@@ -316,91 +309,6 @@ __global__ void __launch_bounds__(256) k_compact_ids(CompactArgs a, const u32* _
     }
     uniq = warp_sum_u32(uniq); total = warp_sum_u64(total);
     if ((threadIdx.x & 31) == 0 && uniq) { atomicAdd(&a.fc->unique, uniq); atomicAdd((unsigned long long*)&a.fc->total_kmers, (unsigned long long)total); }
-}
-
-// The novel table is big (millions of slots) and most warps hold a kept k-mer, so the output slots are
-// reserved once per CTA round (1024 table slots) instead of once per warp: one hot atomic address
-// would otherwise serialise the whole kernel.
-__global__ void __launch_bounds__(256) k_compact_gen(CompactArgs a, const GenSlot* __restrict__ gen, u32 n_slots) {
-    __shared__ u32 s_base;
-    u32 uniq = 0; u64 total = 0;
-    for (u32 base = blockIdx.x * 1024u; base < n_slots; base += gridDim.x * 1024u) {   // n_slots: power of two >= 1024
-        u64 key[4]; u32 cnt[4]; bool keep[4];
-        u32 mine = 0;
-#pragma unroll
-        for (u32 q = 0; q < 4; q++) {
-            const uint4 sl = __ldg(reinterpret_cast<const uint4*>(gen) + base + q * 256u + threadIdx.x);
-            key[q] = ((u64)sl.y << 32) | sl.x; cnt[q] = sl.z;
-            const bool have = key[q] != BK_EMPTY;
-            if (have) { uniq++; total += cnt[q]; }
-            keep[q] = have && cnt[q] >= a.ci && cnt[q] <= 1000000000u;
-            mine += keep[q] ? 1u : 0u;
-        }
-        u32 tot;
-        u32 o = block_excl_scan_256(mine, &tot);
-        if (threadIdx.x == 0) s_base = tot ? atomicAdd(&a.fc->n_counted, tot) : 0u;
-        __syncthreads();
-        o += s_base;
-#pragma unroll
-        for (u32 q = 0; q < 4; q++)
-            if (keep[q]) { if (o < a.out_cap) { a.out_kmers[o] = key[q]; a.out_counts[o] = min(cnt[q], a.cs); } o++; }
-        __syncthreads();
-    }
-    uniq = warp_sum_u32(uniq); total = warp_sum_u64(total);
-    if ((threadIdx.x & 31) == 0 && uniq) { atomicAdd(&a.fc->unique, uniq); atomicAdd((unsigned long long*)&a.fc->total_kmers, (unsigned long long)total); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// read-sharded mode: novel k-mers grouped by owner rank, and re-insertion of merged (k-mer, count) pairs
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u32 owner_of(u64 kmer, u32 n_ranks) {
-    return (u32)(((kmer ^ (kmer >> 29)) * 0xD6E8FEB86659FD93ull) >> 33) % n_ranks;
-}
-
-// PASS 0: per-owner counts (counts[n_ranks]); PASS 1: scatter to out[start[owner] + cursor[owner]++]
-template <int PASS>
-__global__ void __launch_bounds__(256)
-k_novel_partition(const GenSlot* __restrict__ gen, u32 n_slots, u32 n_ranks, u32* counts, const u32* start, u64* out_k, u32* out_c) {
-    extern __shared__ u32 sh[];
-    if (PASS == 0) {
-        for (u32 i = threadIdx.x; i < n_ranks; i += blockDim.x) sh[i] = 0;
-        __syncthreads();
-    }
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        const uint4 s = __ldg(reinterpret_cast<const uint4*>(gen) + i);
-        const u64 key = ((u64)s.y << 32) | s.x;
-        if (key == BK_EMPTY) continue;
-        const u32 o = owner_of(key, n_ranks);
-        if (PASS == 0) atomicAdd(sh + o, 1u);
-        else {
-            // counts[] was zeroed again by the host after PASS 0 and now serves as the per-owner cursors
-            const u32 pos = start[o] + atomicAdd(counts + o, 1u);
-            out_k[pos] = key; out_c[pos] = s.z;
-        }
-    }
-    if (PASS == 0) {
-        __syncthreads();
-        for (u32 i = threadIdx.x; i < n_ranks; i += blockDim.x) if (sh[i]) atomicAdd(counts + i, sh[i]);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-k_novel_insert(GenSlot* gen, u32 shift, u32 mask, const u64* __restrict__ kmers, const u32* __restrict__ counts, u64 n, u32* full) {
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u64 kmer = kmers[i];
-        const u32 c = counts[i];
-        u32 h = hash_slot(kmer, shift);
-        bool done = false;
-        for (u32 probe = 0; probe <= mask && !done; probe++) {
-            u64 cur = load_key(&gen[h].key);
-            if (cur == BK_EMPTY) cur = cas_u64(&gen[h].key, BK_EMPTY, kmer);
-            if (cur == BK_EMPTY || cur == kmer) { atomicAdd(&gen[h].cnt, c); done = true; }
-            h = (h + 1) & mask;
-        }
-        if (!done) *full = 1;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -136,3 +136,51 @@ def config_reads(config, sample=0, depth=None):
     else:
         raise ValueError(config)
     return simulate_pairs(g, depth if depth is not None else d, SEED0 + sample)
+
+
+# ---- the same recipe on the GPU (torch), for inputs too large to simulate on the host -------------------------------
+def plant_for(genome_ascii, seed, n_snv=10, n_isnv=20):
+    """The planted variants of a sample (drawn once from the sample's seed, as simulate_pairs does): every chunk /
+    rank of a deep sample must carry the same ones."""
+    rng = np.random.default_rng(seed)
+    g = _CODE[np.asarray(genome_ascii, dtype=np.uint8)]
+    pos, afs = plant_variants(len(g), rng, n_snv, n_isnv)
+    alt = (g[pos] + rng.integers(1, 4, size=len(pos), dtype=np.uint8)) & 3
+    return pos, alt, afs
+
+
+def simulate_pairs_torch(genome_ascii, n_pairs, seed, device, plan, read_len=150, frag_len=300, err=0.002, batch=400_000):
+    """n_pairs read pairs of one chunk of a sample, generated on `device` with torch's Philox generator seeded by
+    `seed` (reproducible on the same GPU type and torch version: bench.py's sharded leg regenerates the chunks of
+    other ranks from their seeds instead of moving them).  Returns (r1 bases, r2 bases, offsets): uint8 device tensors of
+    n_pairs * read_len + 64 bytes (64 bytes of '*' slack) and one int32 offsets tensor (n_pairs + 1) valid for both."""
+    import torch
+    pos, alt, afs = plan
+    g = torch.from_numpy(_CODE[np.asarray(genome_ascii, dtype=np.uint8)]).to(device)
+    L = g.numel()
+    fixed = afs >= 1.0
+    h0 = g.clone()
+    h0[torch.from_numpy(pos[fixed]).to(device)] = torch.from_numpy(alt[fixed]).to(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    lut = torch.from_numpy(_ASCII.copy()).to(device)
+    out1 = torch.full((n_pairs * read_len + 64,), ord("*"), dtype=torch.uint8, device=device)
+    out2 = torch.full((n_pairs * read_len + 64,), ord("*"), dtype=torch.uint8, device=device)
+    ar = torch.arange(frag_len, device=device, dtype=torch.int32)
+    for c0 in range(0, n_pairs, batch):
+        n = min(batch, n_pairs - c0)
+        start = torch.randint(0, L - frag_len + 1, (n,), generator=gen, device=device, dtype=torch.int32)
+        frag = h0[(start[:, None] + ar[None, :]).long()]
+        for p, a, af in zip(pos[~fixed].tolist(), alt[~fixed].tolist(), afs[~fixed].tolist()):
+            carry = (start <= p) & (start + frag_len > p) & (torch.rand(n, generator=gen, device=device) < af)
+            rows = carry.nonzero(as_tuple=True)[0]
+            frag[rows, (p - start[rows]).long()] = a
+        strand = torch.rand(n, generator=gen, device=device) < 0.5
+        frag = torch.where(strand[:, None], 3 - frag.flip(1), frag)
+        for out, a in ((out1, frag[:, :read_len]), (out2, (3 - frag.flip(1))[:, :read_len])):
+            e = torch.rand((n, read_len), generator=gen, device=device) < err
+            sub = torch.randint(1, 4, (n, read_len), generator=gen, device=device, dtype=torch.uint8)
+            a = torch.where(e, (a + sub) & 3, a)
+            out[c0 * read_len:(c0 + n) * read_len] = lut[a.long()].reshape(-1)
+    off = (torch.arange(n_pairs + 1, device=device, dtype=torch.int64) * read_len).to(torch.int32)
+    return out1, out2, off

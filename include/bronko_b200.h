@@ -32,7 +32,8 @@ typedef enum {
     BK_ERR_IO = -3,       /* file could not be opened / parsed */
     BK_ERR_NO_GENOME = -4,/* pick_best_genome returned None (src/call.rs:230-233): host must exit(1) */
     BK_ERR_OVERFLOW = -5, /* a device table overflowed its capacity; re-run with a larger table */
-    BK_ERR_NO_DEVICE = -6
+    BK_ERR_NO_DEVICE = -6,
+    BK_ERR_NOMEM = -7     /* host allocation failed */
 } bk_status;
 
 /* #[repr(C)] BucketInfo, src/build.rs:52-60 — 12 bytes including padding. */
@@ -109,15 +110,20 @@ typedef struct {
     float total_ms;     /* bk_sample_begin → end of bk_sample_finish */
     uint32_t launches;  /* kernels launched for this sample          */
     uint32_t scan_launches;
+    float coll_ms;      /* read-sharded sample: collectives (all-reduces, size all-gather, pair all-to-all) */
+    uint32_t coll_calls;
 } bk_stage_times;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int bk_create(bk_ctx** out, int device);
 void bk_destroy(bk_ctx* ctx);
 const char* bk_last_error(bk_ctx* ctx);      /* ctx may be NULL: last bk_create error */
-void* bk_stream(bk_ctx* ctx);                /* cudaStream_t the pushes (counting kernels) are enqueued on: order device
-                                              * buffers handed to bk_reads_push_device against it.  Later stages of a
-                                              * sample run on internal streams of higher priority chained to it by
+void* bk_stream(bk_ctx* ctx);                /* = bk_stream_slot(ctx, 0) */
+void* bk_stream_slot(bk_ctx* ctx, int file_slot);
+                                             /* cudaStream_t the pushes (counting kernels) of one file slot are enqueued on:
+                                              * order device buffers handed to bk_reads_push_device against it.  The two
+                                              * files of a pair run side by side on their own streams; later stages of a
+                                              * sample run on internal streams of higher priority chained to them by
                                               * events; every call that returns results synchronises. */
 const char* bk_version(void);
 
@@ -154,10 +160,14 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params);
 /* get_kmers / count_kmers_kmc (src/call.rs:630-646, 1152-1226): feed decoded reads of one file.
  * file_slot 0 = the -r file or R1, 1 = R2 (counted and thresholded separately, src/call.rs:302-307).
  * bases = concatenated sequence lines (ASCII), read r = bases[read_off[r] .. read_off[r+1]).
- * Host buffers (pinned recommended: bk_host_alloc); may be called repeatedly per file (chunks). */
+ * Host buffers (pinned recommended: bk_host_alloc); may be called repeatedly per file (chunks).  Both buffers have been
+ * copied when the call returns: the caller may overwrite them at once. */
 int bk_reads_push(bk_ctx* ctx, int file_slot, const uint8_t* bases, const uint32_t* read_off,
                   uint64_t n_reads);
-/* Same, buffers already in device memory (16-byte aligned, readable for 16 bytes past n_bases). */
+/* Same, buffers already in device memory: d_bases 16-byte aligned and readable for 64 bytes past n_bases (the scan
+ * loads whole words around a read; bk_fastq_decode chunks carry that slack).  The kernels read the buffers
+ * asynchronously: they must stay valid and unmodified until bk_sample_finish returns (or the context's stream,
+ * bk_stream(), has been synchronised). */
 int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
                          const uint32_t* d_read_off, uint64_t n_reads, uint64_t n_bases,
                          uint32_t max_read_len);
@@ -179,6 +189,7 @@ void bk_reads_free(bk_reads* reads);
  * Returns BK_ERR_NO_GENOME where the reference exits with "Unable to pick a best genome". */
 int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out);
 /* Results of the last finished sample. */
+int bk_sample_result_get(bk_ctx* ctx, bk_sample_result* out);               /* what bk_sample_finish returned */
 int bk_sample_variants(bk_ctx* ctx, bk_variant* out, uint64_t cap);          /* sorted seq,pos,alt */
 int bk_sample_genome_stats(bk_ctx* ctx, int file_slot, bk_genome_stats* out);/* n_genomes entries */
 /* OutputData.counts of the selected genome (src/call.rs:1235-1239), widened to u64:
@@ -198,29 +209,26 @@ int bk_write_pileup(bk_ctx* ctx, const char* out_path);
 uint64_t bk_clean_sample_id(const char* path, char* buf, uint64_t cap);
 
 /* ---- read-sharded deep sample (BASELINE config C3) -----------------------------
- * Every rank scans its share of the reads of ONE sample with bk_reads_push*.  The pileup is a MAX over
- * globally summed, thresholded (>= min_kmers), saturated counts (src/call.rs:1172-1173, 1342-1343), so the
- * k-mer counts are merged across ranks BEFORE the threshold and the pileups combined afterwards.  The
- * library only exposes / re-imports device buffers; the host moves them (NCCL via torch.distributed in
- * bronko_b200/dist.py).  Call order per sample:
- *   bk_shard_config (once, between samples) ; bk_sample_begin ; bk_reads_push* ;
- *   per file: bk_shard_begin → host: all-reduce(SUM) d_ref_counts in place, all-to-all the novel pairs by
- *             part_off → bk_shard_import_novel(merged pairs this rank owns) ;
- *   bk_shard_map_stats → host: all-reduce(SUM) the tallies in place and the partial KMC numbers ;
- *   bk_shard_select_pileup(global KMC numbers) → host: all-reduce(MAX) arrays 0,1 and (SUM) arrays 2,3 ;
- *   bk_shard_score → the same bk_sample_result on every rank. */
-int bk_shard_config(bk_ctx* ctx, uint32_t rank, uint32_t n_ranks);
-/* d_ref_counts: n_ref_counts u32 (one per distinct reference k-mer); novel pairs: u64 k-mers / u32 counts,
- * grouped by owner rank, rank r owns [part_off[r], part_off[r+1]) (part_off: n_ranks+1 entries, host). */
-int bk_shard_begin(bk_ctx* ctx, int file_slot, void** d_ref_counts, uint64_t* n_ref_counts,
-                   void** d_novel_kmers, void** d_novel_counts, uint64_t* part_off);
-int bk_shard_import_novel(bk_ctx* ctx, int file_slot, const void* d_kmers, const void* d_counts, uint64_t n);
-/* d_tallies{0,1}: n_tallies u32 per file ([genome][perfect, variant, unique, present]); partial[2]: this
- * rank's share of the four KMC numbers per file (sum over ranks = the sample's numbers). */
-int bk_shard_map_stats(bk_ctx* ctx, void** d_tallies0, void** d_tallies1, uint64_t* n_tallies, bk_kmc_stats* partial);
-/* d_pile: 4 consecutive u32 arrays of n_per_array elements (fwd depth, rev depth, fwd support, rev support). */
-int bk_shard_select_pileup(bk_ctx* ctx, const bk_kmc_stats* global_kmc, void** d_pile, uint64_t* n_per_array);
-int bk_shard_score(bk_ctx* ctx, bk_sample_result* out);
+ * Every rank scans its share of the reads of ONE sample with bk_reads_push* (every rank must use the same file
+ * slots; a push of zero reads counts).  The pileup is a MAX over globally summed, thresholded (>= min_kmers),
+ * saturated counts (src/call.rs:1172-1173, 1341-1345; R1 / R2 separately, 302-317), so the library merges the k-mer
+ * counts across ranks BEFORE the cut-offs — all-reduce(SUM) of the dense reference-k-mer counts, all-to-all of the
+ * novel (k-mer, partial count) pairs to an owner rank — lets every k-mer be thresholded and mapped by exactly one
+ * rank, and only then combines depth (MAX), support and tallies (SUM).  bk_sample_finish does all of it, collectives
+ * included (NCCL, enqueued on the context's stream), must be called by every rank, and returns the same result on
+ * every rank.  One rank per process and GPU:
+ *   rank 0: bk_shard_unique_id(id) ; the host hands the 128 bytes to every rank (MPI / torch.distributed / a file) ;
+ *   every rank: bk_shard_init(ctx, rank, n_ranks, id), between samples ; n_ranks <= 1 returns to whole samples.
+ * libnccl.so.2 is opened when the first of these is called; a process that never shards does not need it. */
+int bk_shard_unique_id(uint8_t* out128);
+int bk_shard_init(bk_ctx* ctx, uint32_t rank, uint32_t n_ranks, const uint8_t* id128);
+int bk_shard_info(bk_ctx* ctx, uint32_t* rank, uint32_t* n_ranks);
+/* The same sharded path with all ranks in ONE process on ONE device (NCCL refuses two ranks on a device): contexts
+ * ctxs[0..n) sharing one index (bk_index_share) become ranks 0..n-1, every one gets its share of the reads, and
+ * bk_shard_finish_local runs the sharded finish for all of them (collectives are kernels / copies).  The single-GPU
+ * parity tests of the sharded kernels use this; n = 1 dissolves the group. */
+int bk_shard_local(bk_ctx** ctxs, uint32_t n);
+int bk_shard_finish_local(bk_ctx** ctxs, uint32_t n, bk_sample_result* out);
 
 /* ---- pinned host memory helpers ---------------------------------------------------------- */
 void* bk_host_alloc(uint64_t bytes);

@@ -247,19 +247,56 @@ def test_shared_index_between_contexts(ctx_sars):
         c1.close()
 
 
-def test_novel_kmers_in_global_table(sars_paths, oracle, monkeypatch):
-    """BK_NOVEL_TABLE: novel k-mers counted in the global open-addressing table (what the read-sharded mode uses)
-    instead of list → bins → shared-memory tables."""
+def test_chunked_pushes_with_buffer_reuse(ctx_sars):
+    """A file pushed in chunks from ONE pair of pinned host buffers that is overwritten the moment bk_reads_push
+    returns (the contract: "both buffers have been copied when the call returns"), with chunks of very different
+    sizes so that the novel k-mer list of the file has to learn its real fill and grow between pushes."""
+    import ctypes as C
     import bronko_b200
-    monkeypatch.setenv("BK_NOVEL_TABLE", "1")
-    c = bronko_b200.Bronko(0)
+    from bronko_b200 import _lib as L
+    c, oi = ctx_sars
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[1]), 900, sim.SEED0 + 47)
+    lib = L.lib()
+    cuts = [0, 40, 45, 3000, 3100, 20000, len(o1) - 1]             # reads per chunk: 40, 5, 2955, 100, 16900, rest
+    cap_b = max(int(o1[cuts[i + 1]]) - int(o1[cuts[i]]) for i in range(len(cuts) - 1)) + 64
+    cap_o = max(cuts[i + 1] - cuts[i] for i in range(len(cuts) - 1)) + 1
+    hb_p, ho_p = lib.bk_host_alloc(cap_b), lib.bk_host_alloc(cap_o * 4)
+    assert hb_p and ho_p
+    hb = np.ctypeslib.as_array(C.cast(hb_p, C.POINTER(C.c_uint8)), shape=(cap_b,))
+    ho = np.ctypeslib.as_array(C.cast(ho_p, C.POINTER(C.c_uint32)), shape=(cap_o,))
     try:
-        c.build_index(21, sars_paths)
-        oi = oracle.Index.build(21, sars_paths)
-        r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[0]), 400, sim.SEED0 + 47)
-        run_both(c, oi, [(r1, o1), (r2, o2)])
+        c.begin(bronko_b200.CallArgs())
+        for slot, (b, o) in enumerate(((r1, o1), (r2, o2))):
+            for i in range(len(cuts) - 1):
+                lo, hi = cuts[i], cuts[i + 1]
+                b0, b1 = int(o[lo]), int(o[hi])
+                hb[:b1 - b0] = b[b0:b1]
+                hb[b1 - b0:b1 - b0 + 64] = ord("*")
+                ho[:hi - lo + 1] = (o[lo:hi + 1].astype(np.int64) - b0).astype(np.uint32)
+                c.push_ptr(slot, hb_p, ho_p, hi - lo)
+                hb[:] = ord("N")                                   # the caller reuses its buffers at once
+                ho[:] = 0
+        g = c.finish()
+        from util import assert_sample_equal, oracle_sample
+        counts, osample = oracle_sample(oi, [(r1, o1), (r2, o2)], bronko_b200.CallArgs())
+        assert_sample_equal(g, counts, osample)
     finally:
-        c.close()
+        lib.bk_host_free(hb_p); lib.bk_host_free(ho_p)
+
+
+def test_deep_duplication_single_round_bins(ctx_hpv):
+    """The same few thousand novel k-mers repeated until every bin holds far more occurrences than a worst-case round
+    (what a 10^6x sample looks like): bins are counted in ONE optimistic round; and a list with as many DISTINCT
+    novel k-mers, where the optimistic round must give up and fall back to worst-case rounds."""
+    from util import reads_from_strings
+    c, oi = ctx_hpv
+    rng = np.random.default_rng(19)
+    g = "".join(chr(x) for x in sim.load_genome(sim.HPV16))
+    own = [g[i:i + 150] for i in range(0, 7000, 7)] * 4                     # (something to select a genome with)
+    few = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=150)) for _ in range(40)]
+    run_both(c, oi, [reads_from_strings(few * 1500 + own)])                # 7.8 M occurrences of 5,200 k-mers
+    many = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=150)) for _ in range(30000)]
+    run_both(c, oi, [reads_from_strings(many * 3 + own)])                  # 3.9 M distinct k-mers, three times each
 
 
 def test_heavy_hitter_and_fixed_capacity(ctx_hpv):

@@ -8,6 +8,6 @@ mkdir -p variants
 make -s bk_host_index.o bk_io.o
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function \
      -Xptxas -v "$@" -c -o variants/$name.o bk_device.cu 2> variants/$name.ptxas.log || (cat variants/$name.ptxas.log; false)
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so variants/$name.o bk_host_index.o bk_io.o -lz -cudart static
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/$name.so variants/$name.o bk_host_index.o bk_io.o -lz -ldl -cudart static
 rm -f variants/$name.o
 echo "built variants/$name.so"
