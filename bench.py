@@ -657,19 +657,27 @@ def fastq_legs(args, ctxs, files, oi):
             paths = prepare_fastq(files, td, kind, bgzf)
             size = sum(os.path.getsize(p) for p in paths)
 
-            def one(i, paths=paths, kind=kind):
-                c = ctxs[i % len(ctxs)]
+            def one(ci, i, paths=paths, kind=kind):
+                c = ctxs[ci]
                 c.begin(cargs)
                 for slot, p in enumerate(paths):
                     c.push_fastq(slot, p)
                 r = c.finish()
-                r.write_vcf(paths[0], os.path.join(td, "%s_%d.vcf" % (kind, i % len(ctxs))))
+                r.write_vcf(paths[0], os.path.join(td, "%s_%d.vcf" % (kind, ci)))
                 return len(r.variants)
-            one(0)                                                     # warm-up (page cache, allocations)
-            n = 2 * len(ctxs)
+            nv = [one(0, 0)]                                           # warm-up (page cache, allocations)
+            per_ctx = 2
+            n = per_ctx * len(ctxs)
+
+            def worker(ci):                                            # one host thread per context (a context is not thread-safe)
+                for i in range(per_ctx):
+                    one(ci, i)
+            th = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
             t0 = time.perf_counter()
-            with ThreadPoolExecutor(len(ctxs)) as ex:                  # one host thread per context: ctypes drops the GIL
-                nv = list(ex.map(one, range(n)))
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
             dt = time.perf_counter() - t0
             out[kind] = {"samples_per_min": 60.0 * n / dt, "samples": n, "in_flight": len(ctxs), "compressed_bytes_per_sample": size,
                          "n_variants": nv[0], "decode": ctxs[0].decode_info()}

@@ -43,7 +43,11 @@ class SampleResult(C.Structure):
 class StageTimes(C.Structure):
     _fields_ = [("scan_ms", C.c_float), ("leftover_ms", C.c_float), ("finalize_ms", C.c_float), ("map_ms", C.c_float),
                 ("score_ms", C.c_float), ("total_ms", C.c_float), ("launches", u32), ("scan_launches", u32),
-                ("coll_ms", C.c_float), ("coll_calls", u32)]
+                ("coll_ms", C.c_float), ("coll_calls", u32), ("decode_ms", C.c_float)]
+
+
+class DecodeInfo(C.Structure):
+    _fields_ = [("mode", u32), ("segments", u32), ("compressed_bytes", u64), ("text_bytes", u64), ("n_reads", u64), ("n_bases", u64)]
 
 
 VARIANT_DTYPE = np.dtype([("seq", "<u4"), ("pos", "<u4"), ("ref_base", "u1"), ("alt_base", "u1"), ("pad", "u1", 6),
@@ -79,6 +83,8 @@ SIGNATURES = {
     "bk_reads_push": (C.c_int, [P, C.c_int, P, P, u64]),
     "bk_reads_push_device": (C.c_int, [P, C.c_int, P, P, u64, u64, u32]),
     "bk_reads_push_fastq": (C.c_int, [P, C.c_int, C.c_char_p]),
+    "bk_reads_push_fastq_mem": (C.c_int, [P, C.c_int, P, u64]),
+    "bk_decode_info_get": (C.c_int, [P, C.c_int, C.POINTER(DecodeInfo)]),
     "bk_fastq_decode": (C.c_int, [C.c_char_p, C.POINTER(P), C.c_char_p, u64]),
     "bk_reads_n_chunks": (u64, [P]),
     "bk_reads_chunk": (C.c_int, [P, u64, C.POINTER(P), C.POINTER(P), C.POINTER(u64), C.POINTER(u64)]),

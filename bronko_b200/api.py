@@ -198,6 +198,20 @@ class Bronko:
     def push_fastq(self, file_slot, path):
         self._check(self._lib.bk_reads_push_fastq(self.h, file_slot, path.encode()))
 
+    def push_fastq_mem(self, file_slot, data):
+        """The bytes of a FASTQ(.gz) file (bytes / numpy uint8): inflated (BGZF: by the GPU's decompression engine) and
+        parsed on the device."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        self._check(self._lib.bk_reads_push_fastq_mem(self.h, file_slot, L.ptr(a) if len(a) else None, len(a)))
+
+    def decode_info(self, file_slot=0):
+        d = L.DecodeInfo()
+        self._check(self._lib.bk_decode_info_get(self.h, file_slot, C.byref(d)))
+        names = {0: "none", 1: "plain text, parsed on the device", 2: "gzip inflated by zlib on the host, parsed on the device",
+                 3: "BGZF inflated by the GPU decompression engine, parsed on the device"}
+        return {"mode": d.mode, "how": names.get(d.mode, "?"), "segments": d.segments, "compressed_bytes": d.compressed_bytes,
+                "text_bytes": d.text_bytes, "n_reads": d.n_reads, "n_bases": d.n_bases}
+
     def push_decoded(self, file_slot, reads: DecodedReads):
         self._check(self._lib.bk_reads_push_decoded(self.h, file_slot, reads.h))
 

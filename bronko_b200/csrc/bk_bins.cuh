@@ -35,6 +35,9 @@ namespace bk {
 #define BK_BIN_ROUND 2048                    // occurrences one worst-case round may hold (distinct <= occurrences <= half the slots, in expectation)
 #define BK_BIN_FILL 3072                     // distinct k-mers at which an optimistic single round gives up
 #define BK_BIN_SMEM (BK_BIN_SLOTS * 14)       // keys, counts, list of occupied slots
+#ifndef BK_BIN_AGG_MIN
+#define BK_BIN_AGG_MIN (2 * BK_BIN_ROUND)    // bins with more occurrences than this merge equal keys per warp before the shared-memory atomic
+#endif
 #define BK_OWNER_UNITS_LOG2 6                // owner ranks split the hash space in 64 units (a bin never straddles one: P >= 64)
 
 __device__ __forceinline__ u64 bin_hash(u64 x) { return (x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull; }
@@ -135,6 +138,10 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
         if (threadIdx.x == 0) { s_nocc = 0; s_abort = 0; }
         __syncthreads();
         const bool optimistic = rounds == 1 && rounds_safe > 1;                // may give up; a worst-case-sized round never does
+        // a k-mer repeated a million times must not serialise on one shared-memory word: in bins that are far larger
+        // than average (that is where such a k-mer lands) the lanes holding the key of the first taking lane let that
+        // lane add for all of them.  Ordinary bins skip the two ballots and the shuffles: ~45 % of their keys are distinct.
+        const bool merge_equal = (e - s) > BK_BIN_AGG_MIN;
         const u32 n_round = ((e - s + 31) & ~31u);
         for (u32 i0 = 0; i0 < n_round; i0 += 8 * 256) {
             u64 kq[8]; u32 wq[8];
@@ -152,10 +159,8 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                 const u64 h = bin_hash(key);
                 bool take = key != BK_HOLE;
                 if (rounds > 1) take = take && ((u32)((h * 0xD6E8FEB86659FD93ull) >> 40) % rounds) == r;     // (uniform branch: one round is the rule)
-                // a k-mer repeated a million times must not serialise on one shared-memory word: if many lanes hold
-                // the key of the first taking lane, that lane adds for all of them
                 u32 w = wq[j];
-                const u32 tm = __ballot_sync(0xFFFFFFFFu, take);
+                const u32 tm = merge_equal ? __ballot_sync(0xFFFFFFFFu, take) : 0u;
                 if (tm) {
                     const u32 first = (u32)__ffs(tm) - 1;
                     const u64 key0 = __shfl_sync(0xFFFFFFFFu, key, first);       // (every lane: no short-circuit around it)

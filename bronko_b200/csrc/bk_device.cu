@@ -1,6 +1,7 @@
 // bk_device.cu — bk_ctx, device memory, kernel launches and the C ABI of libbronko_b200.so
 // (include/bronko_b200.h).  There is no CPU fallback anywhere in this file: every stage of a sample
 // runs as a CUDA kernel from bk_kernels.cuh, and bk_create fails without an sm_100 device.
+#include <cuda.h>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -16,6 +17,7 @@
 
 #include "bk_host.h"
 #include "bk_shard.cuh"
+#include "bk_fastq.cuh"
 
 using namespace bk;
 
@@ -49,7 +51,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-enum Stage { ST_SCAN = 0, ST_LEFTOVER, ST_FINALIZE, ST_MAP, ST_SCORE, ST_COLL, ST_N };
+enum Stage { ST_SCAN = 0, ST_LEFTOVER, ST_FINALIZE, ST_MAP, ST_SCORE, ST_COLL, ST_DECODE, ST_N };
 
 // Everything one reads file (R1 or R2) owns.  The two files of a pair are independent until the genome is selected
 // (src/call.rs:302-317 counts and maps them one after the other), so each has its own scratch and its own streams.
@@ -110,6 +112,12 @@ struct ShardGroup {
 
 }  // namespace
 
+struct FqState;        // bk_fastq.inc: buffers of the FASTQ decode stage of one file slot
+extern "C" {
+static void fq_destroy(FqState* q);
+static void fq_begin_sample(FqState* q);
+}
+
 struct bk_ctx {
     int device = 0;
     // Streams.  The two files of a sample run concurrently: file f counts (scan / leftover) on s_count[f] and is
@@ -153,6 +161,7 @@ struct bk_ctx {
     cudaEvent_t stage_free[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
     cudaEvent_t off_free = nullptr, off_copied = nullptr;   // d_stage_off: last kernels that read it / its H2D copy
     int stage_next = 0;
+    FqState* fq[2] = {nullptr, nullptr};    // FASTQ decode stage (bk_fastq.inc), created on first use
     // read-sharded deep sample
     std::shared_ptr<ShardGroup> shard;      // null: this context holds whole samples
     u32 shard_rank = 0;
@@ -301,6 +310,7 @@ void bk_destroy(bk_ctx* ctx) {
     }
     ctx->I.reset();                         // the last context sharing an index frees its device copies
     for (FileState& f : ctx->file) f.release();
+    for (FqState*& q : ctx->fq) { fq_destroy(q); q = nullptr; }
     ctx->d_ctr.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();
     ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
@@ -547,6 +557,7 @@ int bk_sample_begin(bk_ctx* ctx, const bk_params* params) {
     ctx->variants.clear();
     memset(&ctx->result, 0, sizeof ctx->result);
     ctx->result.best_genome = -1;
+    for (FqState* q : ctx->fq) fq_begin_sample(q);
     // (every stream of the context is idle here: the previous sample ended with a host wait on its last event)
     cudaStream_t st = ctx->s_count[0];
     cudaEventRecord(ctx->ev_begin, st);
@@ -759,18 +770,6 @@ int bk_reads_push_decoded(bk_ctx* ctx, int slot, const bk_reads* reads) {
     }
     if (!any) return file_prepare(ctx, slot);             // an empty file is still a file of the sample
     return BK_OK;
-}
-
-int bk_reads_push_fastq(bk_ctx* ctx, int slot, const char* path) {
-    int rc = check_push(ctx, slot);
-    if (rc) return rc;
-    if (!path) return ctx->fail(BK_ERR_ARG, "bk_reads_push_fastq: null path");
-    bk_reads* reads = nullptr;
-    char err[512] = "";
-    if (bk_fastq_decode(path, &reads, err, sizeof err) != BK_OK) return ctx->fail(BK_ERR_IO, "%s", err);
-    rc = bk_reads_push_decoded(ctx, slot, reads);
-    bk_reads_free(reads);
-    return rc;
 }
 
 // ---- stages of bk_sample_finish (the read-sharded mode drives the same stages, bk_shard.inc) ---------------
@@ -1071,7 +1070,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     }
     bk_stage_times& t = ctx->times;
     memset(&t, 0, sizeof t);
-    float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms, &t.coll_ms};
+    float* acc[ST_N] = {&t.scan_ms, &t.leftover_ms, &t.finalize_ms, &t.map_ms, &t.score_ms, &t.coll_ms, &t.decode_ms};
     for (size_t i = 0; i < ctx->spans_used; i++) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->spans[i].a, ctx->spans[i].b) == cudaSuccess) *acc[ctx->spans[i].stage] += ms;
@@ -1125,6 +1124,7 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
 }
 
 #include "bk_shard.inc"
+#include "bk_fastq.inc"
 
 int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out) {
     if (!ctx || !out) return BK_ERR_ARG;

@@ -351,6 +351,9 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
     const u32 k = m.k;
     u32* cta = sm;
     u32* hits = sm + m.n_genomes * 4 + wib * m.n_genomes;
+    __shared__ u32 s_wpre[8][33], s_woff[8][32];       // per warp: exclusive prefix of the entry-list lengths (+ sentinel), list starts
+    u32* wpre = s_wpre[wib]; u32* woff = s_woff[wib];
+    if (lane == 0) wpre[32] = 0xFFFFFFFFu;
     i32 best = -1; u32 g_row0 = 0;
     if (PILEUP) {
         best = *best_ptr;
@@ -380,9 +383,9 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
         u64 bucket;
         if (REKEY) bucket = ((u64)lane << 58) | (kb & ~(3ull << sh));
         else { const u64 sum_mu = warp_sum_u64(mu); bucket = sum_mu - mu + val - num_a * cur + 1 + num_a; }
+        u32 off = 0, len = 0;
         if (lane >= m.b0 && lane < m.b1) {
             u32 h = hash_slot(bucket, m.shift);
-            u32 off = 0, len = 0;
             for (;;) {
                 const uint4 s = __ldg(reinterpret_cast<const uint4*>(m.slots) + h);
                 const u64 key = ((u64)s.y << 32) | s.x;
@@ -390,8 +393,30 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
                 if (key == BK_EMPTY) break;
                 h = (h + 1) & m.mask;
             }
-            for (u32 j = 0; j < len; j++) {
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + off + j);
+        }
+        // entry lists: a few entries per bucket (databases of a few genomes) are walked by the lane that probed the
+        // bucket, all lanes in parallel; long lists (a 200-strain database holds ~150 entries per bucket, 2,400 per
+        // exact k-mer) are flattened over the warp: item t of the concatenated lists goes to lane t mod 32, so
+        // consecutive lanes read consecutive entries
+        u32 incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += v; }
+        const u32 total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const bool flat = total > 64;
+        if (flat) { wpre[lane] = incl - len; woff[lane] = off; __syncwarp(); }
+        const u32 n_it = flat ? (total + 31) / 32 : len;
+        for (u32 it = 0; it < n_it; it++) {
+            u32 e_at;
+            if (flat) {
+                const u32 t = it * 32 + lane;
+                if (t >= total) break;
+                u32 lo = 0;                                            // last lane whose exclusive prefix is <= t
+#pragma unroll
+                for (u32 step = 16; step; step >>= 1) if (wpre[lo + step] <= t) lo += step;
+                e_at = woff[lo] + (t - wpre[lo]);
+            } else e_at = off + it;
+            {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(m.entries) + e_at);
                 const u32 row = raw.x, file_id = raw.y & 0xFFFFu, idx = (raw.y >> 16) & 0xFFu, canon = raw.y >> 24;
                 if (row == 0xFFFFFFFFu) continue;
                 if (!PILEUP) {
@@ -406,6 +431,7 @@ k_map(MapView m, const u64* __restrict__ kmers, const u32* __restrict__ counts, 
                 }
             }
         }
+        __syncwarp();
         if (!PILEUP) {
             __syncwarp();
             u32 n_perfect = 0, perfect_g = 0;

@@ -152,7 +152,8 @@ static int run_build(const Args& a) {
     info("Building indexes from fasta files");
     bk::HostIndex ix;
     std::string err;
-    if (!bk::index_build_from_fasta((uint32_t)a.kmer, a.genomes, ix, err)) die(err + " | Reference failed to build");
+    // (a file that does not parse ends the reference inside build_indexes with its own message, src/build.rs:156-159)
+    if (!bk::index_build_from_fasta((uint32_t)a.kmer, a.genomes, ix, err)) die(err.find("Failed to parse fasta file") != std::string::npos ? err : err + " | Reference failed to build");
     const std::string out = a.output + ".bkdb";
     info("Saving index to " + out);
     if (!bk::bkdb_write(out, ix, err)) die(err + " | Unable to save index");
@@ -231,8 +232,18 @@ static void write_counts_txt(bk_ctx* ctx, int slot, uint32_t k, const std::strin
 // while the GPU works on this one: R1 and R2 of a sample concurrently, up to `lookahead` samples ahead (-t bounds it).
 struct DecodedSample {
     bk_reads* r[2] = {nullptr, nullptr};
+    bool on_device[2] = {false, false};      // BGZF: nothing to do on the host — the GPU's decompression engine inflates it (bk_reads_push_fastq)
     std::string err;
 };
+// BGZF = gzip whose first member carries the 'BC' extra subfield (bgzip / htslib)
+static bool looks_bgzf(const std::string& path) {
+    unsigned char h[18];
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    const size_t n = fread(h, 1, sizeof h, f);
+    fclose(f);
+    return n == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+}
 static bk_reads* decode_file(const std::string& path, std::string* err) {
     bk_reads* r = nullptr;
     char msg[512] = "";
@@ -243,17 +254,19 @@ static DecodedSample decode_sample(std::string r1, std::string r2, bool paired) 
     DecodedSample d;
     std::string e2;
     std::future<bk_reads*> second;
-    if (paired) second = std::async(std::launch::async, decode_file, r2, &e2);
-    d.r[0] = decode_file(r1, &d.err);
-    if (paired) { d.r[1] = second.get(); if (d.err.empty()) d.err = e2; }
+    d.on_device[0] = looks_bgzf(r1);
+    d.on_device[1] = paired && looks_bgzf(r2);
+    if (paired && !d.on_device[1]) second = std::async(std::launch::async, decode_file, r2, &e2);
+    if (!d.on_device[0]) d.r[0] = decode_file(r1, &d.err);
+    if (paired && !d.on_device[1]) { d.r[1] = second.get(); if (d.err.empty()) d.err = e2; }
     return d;
 }
 
 static OutputInfo process_sample(bk_ctx* ctx, const Args& a, const bk_params& p, const std::string& r1, const std::string* r2, DecodedSample d) {
     if (!d.err.empty()) die(d.err);
     CK(bk_sample_begin(ctx, &p));
-    CK(bk_reads_push_decoded(ctx, 0, d.r[0]));
-    if (r2) CK(bk_reads_push_decoded(ctx, 1, d.r[1]));
+    if (d.on_device[0]) CK(bk_reads_push_fastq(ctx, 0, r1.c_str())); else CK(bk_reads_push_decoded(ctx, 0, d.r[0]));
+    if (r2) { if (d.on_device[1]) CK(bk_reads_push_fastq(ctx, 1, r2->c_str())); else CK(bk_reads_push_decoded(ctx, 1, d.r[1])); }
     bk_reads_free(d.r[0]); bk_reads_free(d.r[1]);
     bk_sample_result res;
     const int rc = bk_sample_finish(ctx, &res);
@@ -350,7 +363,10 @@ static int run_call(const Args& a) {
         info("Creating bronko index from provided reference genomes");
         std::vector<const char*> ps;
         for (const std::string& g : a.genomes) ps.push_back(g.c_str());
-        if (bk_index_build(ctx, (uint32_t)a.kmer, (uint32_t)ps.size(), ps.data()) != 0) die(std::string(bk_last_error(ctx)) + " | Reference failed to build");
+        if (bk_index_build(ctx, (uint32_t)a.kmer, (uint32_t)ps.size(), ps.data()) != 0) {
+            const std::string err = bk_last_error(ctx);
+            die(err.find("Failed to parse fasta file") != std::string::npos ? err : err + " | Reference failed to build");
+        }
     } else {
         info("Reading in provided bronko index");
         if (bk_index_load_file(ctx, a.db.c_str()) != 0) die(bk_last_error(ctx));

@@ -112,7 +112,15 @@ typedef struct {
     uint32_t scan_launches;
     float coll_ms;      /* read-sharded sample: collectives (all-reduces, size all-gather, pair all-to-all) */
     uint32_t coll_calls;
+    float decode_ms;    /* bk_reads_push_fastq*: H2D of the file, inflate, FASTQ parse (device time)         */
 } bk_stage_times;
+
+/* What the decode stage did with the last file pushed to a slot by bk_reads_push_fastq / _fastq_mem. */
+typedef struct {
+    uint32_t mode;      /* 1 plain text, 2 gzip inflated by zlib on the host, 3 BGZF inflated by the GPU's decompression engine */
+    uint32_t segments;  /* device passes (long files are decoded a segment of text at a time)                */
+    uint64_t compressed_bytes, text_bytes, n_reads, n_bases;
+} bk_decode_info;
 
 /* ---- context ---------------------------------------------------------------------------- */
 int bk_create(bk_ctx** out, int device);
@@ -171,8 +179,14 @@ int bk_reads_push(bk_ctx* ctx, int file_slot, const uint8_t* bases, const uint32
 int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
                          const uint32_t* d_read_off, uint64_t n_reads, uint64_t n_bases,
                          uint32_t max_read_len);
-/* Decode a FASTQ(.gz) file on the host (KMC reader contract) and push it. */
+/* A FASTQ(.gz) file (KMC reader contract) decoded ON THE DEVICE and pushed: the host only moves
+ * bytes.  BGZF files (bgzip / htslib: independent <= 64 KiB gzip members) are inflated by the B200's hardware
+ * decompression engine; other gzip files by zlib on the host (a single deflate stream cannot be split); the text is
+ * parsed by kernels either way.  _mem takes the file's bytes from host memory (pinned: bk_host_alloc — copied
+ * asynchronously; pageable works).  bk_decode_info_get tells which way the last file of a slot went. */
 int bk_reads_push_fastq(bk_ctx* ctx, int file_slot, const char* fastq_path);
+int bk_reads_push_fastq_mem(bk_ctx* ctx, int file_slot, const uint8_t* file_bytes, uint64_t n_bytes);
+int bk_decode_info_get(bk_ctx* ctx, int file_slot, bk_decode_info* out);
 /* The host decode stage on its own — the step in front of the path (KMC's FASTQ reader inside count_kmers_kmc,
  * src/call.rs:1166-1181; contract in SURVEY.md Appendix B: 4-line records, only the sequence line is used, gz detected).
  * Needs no context and no GPU and is thread-safe: decode the files of the next samples on other host threads while

@@ -35,7 +35,14 @@ class FakeBronko:
 
     def stage_times(self):
         return {"scan_ms": 0.2, "leftover_ms": 0.1, "finalize_ms": 0.5, "map_ms": 0.4, "score_ms": 0.5, "total_ms": 1.7,
-                "launches": 33, "scan_launches": 2}
+                "launches": 33, "scan_launches": 2, "coll_ms": 0.0, "coll_calls": 0, "decode_ms": 0.0}
+
+
+class FakeStream:
+    def __init__(self, *a, **k): pass
+    def synchronize(self): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
 
 
 class FakeEvent:
@@ -54,13 +61,16 @@ def test_bench_prints_one_json_line_with_every_contract_key(monkeypatch, capfd):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: s)
     tiny = sim.simulate_pairs(sim.load_genome(sim.HPV16), 20, sim.SEED0)
     monkeypatch.setattr(sim, "simulate_pairs", lambda *a, **k: tiny)
     spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     monkeypatch.setattr(b, "oracle_step", lambda *a, **k: None)
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "8", "--warmup", "3"])
+    # (the FASTQ and sharded legs need the real library: the GPU run covers them)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "8", "--warmup", "3", "--no-fastq", "--no-sharded"])
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     saved = os.dup(1)
@@ -74,7 +84,8 @@ def test_bench_prints_one_json_line_with_every_contract_key(monkeypatch, capfd):
     assert len(lines) == 1
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks",
+                "h2d_ceiling", "roofline_path", "fastq", "sharded"):
         assert key in d, key
     assert d["steps"] == 8 and d["n_gpus"] == 1 and d["gpu_launches"] == 8 * 33
     assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}

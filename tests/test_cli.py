@@ -50,6 +50,12 @@ def test_argument_checks_exit_1(hpv_fasta, tmp_path):
     assert run(["call", "-d", "x.bkdb", "-r", "a.fq", "--noise-multiplier", "0.5"]).returncode == 1
     assert run(["call", "-d", "x.bkdb", "-r", "a.fq", "--min-af", "1.5"]).returncode == 1
     assert run(["build"]).returncode == 2 and run([]).returncode == 2            # arg_required_else_help
+    # what needletail rejects (src/build.rs:156-159 logs "<error> | Failed to parse fasta file: <path>" and exits 1)
+    empty, junk, short = tmp_path / "empty.fa", tmp_path / "junk.fa", tmp_path / "short.fa"
+    empty.write_text(""); junk.write_text("ACGT\n>x\nACGT\n"); short.write_text(">s\nACGTACGT\n")
+    for bad in (empty, junk, short):
+        r = run(["build", "-g", str(bad), "-o", str(tmp_path / "bad")])
+        assert r.returncode == 1 and "Failed to parse fasta file: " + str(bad) in r.stderr, r.stderr
 
 
 @pytest.mark.gpu
@@ -100,3 +106,38 @@ def test_call_end_to_end(oracle, sars_paths, tmp_path):
     assert not (out / "ON765678.1.mfa").exists()                     # only one sample picked that genome
     # k mismatch between -k and the db → exit 1 (src/call.rs:193-197)
     assert run(["call", "-d", db + ".bkdb", "-r", singles[0], "-k", "19", "-o", str(out)]).returncode == 1
+
+
+@pytest.mark.gpu
+def test_call_with_genomes_and_bgzf_reads(oracle, sars_paths, tmp_path):
+    """`bronko call -g <fasta>...` builds the index on the fly (src/call.rs:170-178) and must give what `call -d` gives
+    on the db `bronko build` wrote; R1 comes as BGZF (inflated by the GPU's decompression engine), R2 as plain text."""
+    import zlib
+    from util import oracle_sample
+    import bronko_b200
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[3]), 400, sim.SEED0 + 58)
+    f1_plain, f2 = str(tmp_path / "g_R1.fastq"), str(tmp_path / "g_R2.fastq")
+    sim.write_fastq(f1_plain, r1, o1, "g", 1)
+    sim.write_fastq(f2, r2, o2, "g", 2)
+    text = open(f1_plain, "rb").read()
+    f1 = str(tmp_path / "g_R1.fastq.gz")
+    with open(f1, "wb") as f:
+        for i in range(0, len(text), 65280):
+            chunk = text[i:i + 65280]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            body = co.compress(chunk) + co.flush()
+            f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + (len(body) + 25).to_bytes(2, "little") + body +
+                    (zlib.crc32(chunk) & 0xFFFFFFFF).to_bytes(4, "little") + len(chunk).to_bytes(4, "little"))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    out_g, out_d = tmp_path / "out_g", tmp_path / "out_d"
+    r = run(["call", "-g"] + sars_paths + ["-1", f1, "-2", f2, "-o", str(out_g), "--pileup", "-t", "2"])
+    assert r.returncode == 0, r.stderr
+    db = str(tmp_path / "sars4")
+    assert run(["build", "-g"] + sars_paths + ["-o", db]).returncode == 0
+    r = run(["call", "-d", db + ".bkdb", "-1", f1, "-2", f2, "-o", str(out_d), "--pileup", "-t", "2"])
+    assert r.returncode == 0, r.stderr
+    for name in ("g_R1.vcf", "g_R1.tsv", "bronko_overview.tsv"):
+        assert (out_g / name).read_bytes() == (out_d / name).read_bytes(), name
+    osample = oracle_sample(oracle.Index.build(21, sars_paths), [(r1, o1), (r2, o2)], bronko_b200.CallArgs())[1]
+    assert (out_g / "g_R1.vcf").read_text() == osample.vcf_text(f1)
+    assert (out_g / "g_R1.tsv").read_text() == osample.pileup_text()

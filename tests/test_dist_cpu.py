@@ -50,7 +50,8 @@ class OracleShardEngine:
 
     @staticmethod
     def owner(kmers, world):
-        return ((kmers ^ (kmers >> np.uint64(29))) * np.uint64(0xD6E8FEB86659FD93) >> np.uint64(33)) % np.uint64(world)
+        from bronko_b200.dist import owner_of            # the library's owner function (bk_bins.cuh: hash units)
+        return owner_of(kmers, world)
 
     def begin(self, f):
         b, off = self.files[f]

@@ -71,6 +71,20 @@ def test_tau_table_matches_oracle(oracle):
     assert (t[:3] == 0).all()
 
 
+def test_product_tau_table_against_scipy():
+    """The product's own Student-t / Thompson-tau table (bk_io.cpp: tau_table, uploaded to the device as c_tau) against an
+    INDEPENDENT implementation — scipy's t.ppf — to 1e-12 relative.  (The comparison with the oracle above cannot
+    catch an error the two restatements share; this one can.)"""
+    import math
+    stats = pytest.importorskip("scipy.stats")
+    t = np.zeros(301)
+    emul_lib().emul_tau_table(ptr(t))                     # tests/emul links the product's bk_io.cpp: the same function the library calls
+    for n in range(3, 301):
+        q = stats.t.ppf(1 - 0.001 / n, n - 2)
+        want = q * (n - 1) / (math.sqrt(n) * math.sqrt(n - 2 + q * q))
+        assert abs(t[n] - want) < 1e-12 * want, n
+
+
 def test_clean_sample_id_matches_oracle(oracle):
     buf = C.create_string_buffer(512)
     for p in ["a/b/rep1_R1.fastq.gz", "x.fq", "x.fq.gz", "s.fastq.fastq", "weird.fna.gz", "reads.txt", "noext",

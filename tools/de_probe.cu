@@ -26,7 +26,7 @@ static std::vector<unsigned char> raw_deflate(const unsigned char* p, size_t n, 
     return out;
 }
 
-int main() {
+int main(int argc, char**) {
     CK(cuInit(0));
     CUdevice dev; CK(cuDeviceGet(&dev, 0));
     CUcontext cx; CK(cuDevicePrimaryCtxRetain(&cx, dev)); CK(cuCtxSetCurrent(cx));
@@ -47,6 +47,37 @@ int main() {
         txt.append(150, 'I');
         txt += "\n";
     }
+    // alignment: BGZF payloads start 18 bytes into a member and members follow each other without padding; text
+    // destinations follow each other at arbitrary offsets
+    for (int mis : {0, 1, 2, 7}) {
+        const size_t block = 65280, nb = 512;
+        std::vector<std::vector<unsigned char>> comp(nb);
+        size_t ctot = 0;
+        for (size_t b = 0; b < nb; b++) { comp[b] = raw_deflate((const unsigned char*)txt.data() + b * block, block, 1); ctot += comp[b].size() + 26; }
+        CUdeviceptr dsrc, ddst, dact;
+        CK(cuMemAlloc(&dsrc, ctot + 64)); CK(cuMemAlloc(&ddst, nb * block + 64)); CK(cuMemAlloc(&dact, nb * 4));
+        std::vector<unsigned char> flat(ctot + 64);
+        std::vector<CUmemDecompressParams> ps(nb);
+        size_t off = mis;
+        for (size_t b = 0; b < nb; b++) {
+            memcpy(flat.data() + off, comp[b].data(), comp[b].size());
+            memset(&ps[b], 0, sizeof ps[b]);
+            ps[b].srcNumBytes = comp[b].size(); ps[b].dstNumBytes = block; ps[b].dstActBytes = (cuuint32_t*)(dact + b * 4);
+            ps[b].src = (const void*)(dsrc + off); ps[b].dst = (void*)(ddst + mis + b * block); ps[b].algo = CU_MEM_DECOMPRESS_ALGORITHM_DEFLATE;
+            off += comp[b].size() + 26 - (b % 3);          // arbitrary, unaligned strides
+        }
+        CK(cuMemcpyHtoD(dsrc, flat.data(), ctot + 32));
+        CUstream st; CK(cuStreamCreate(&st, CU_STREAM_NON_BLOCKING));
+        size_t erridx = 0;
+        CUresult r = cuMemBatchDecompressAsync(ps.data(), nb, 0, &erridx, st);
+        CUresult r2 = r == CUDA_SUCCESS ? cuStreamSynchronize(st) : r;
+        std::vector<unsigned char> back(nb * block);
+        bool ok = false;
+        if (r2 == CUDA_SUCCESS) { CK(cuMemcpyDtoH(back.data(), ddst + mis, nb * block)); ok = memcmp(back.data(), txt.data(), nb * block) == 0; }
+        printf("misaligned by %d (src and dst): submit %d, sync %d, output %s\n", mis, (int)r, (int)r2, ok ? "identical" : "DIFFERS");
+        cuMemFree(dsrc); cuMemFree(ddst); cuMemFree(dact);
+    }
+    if (argc > 1) return 0;                      // any argument: alignment test only
     for (size_t block : {size_t(64) << 10, size_t(1) << 20, size_t(4) << 20}) {
         if ((size_t)maxlen && block > (size_t)maxlen) { printf("block %zu > maximum length, skipped\n", block); continue; }
         const size_t nb = txt.size() / block;
