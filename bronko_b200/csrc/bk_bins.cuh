@@ -53,6 +53,10 @@ struct BinView {
     const ExactSlotD* exact; u32 exact_shift, exact_mask;   // reference k-mer → representative raw slot
     const u32* slot2id; u32* idcnt;                          // raw slot → distinct reference k-mer id → its count
     u64* pair_k; u32* pair_c; u32* dcount;               // MODE 1: pairs of bin b at [cnt[b * G], + dcount[b])
+    // mismatch lines (bk_dense.cuh; null = off): (j << 58 | k-mer without digit j) → id of the reference k-mer that equals
+    // the k-mer everywhere but at digit j; a distinct k-mer of the list that is the string of an unambiguous cell joins it
+    const ExactSlotD* nb; u32 nb_shift, nb_mask; u32 k;
+    const u32* id_amb; const u32* id_rep; u32* dense; u8* dense_flag;
 };
 
 __device__ __forceinline__ void bin_chunk(const BinView& b, u32* lo, u32* hi) {
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(BK_BIN_G_THREADS) k_bin_scatter(BinView b) {
 // thread that claims an empty slot also appends it to the list of occupied slots); then, over that dense list:
 // look the distinct k-mers up in the reference table (first probes of four k-mers together; a reference k-mer adds
 // its count to idcnt and drops out) and compact what is left to the output of the MODE.
-template <int MODE>
+template <int MODE, bool W>
 __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, u32* full) {
     extern __shared__ __align__(16) u8 bsm[];
     __shared__ u32 s_base, s_nocc, s_abort, s_out;
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
             for (u32 j = 0; j < 8; j++) {
                 const u32 i = i0 + j * 256 + threadIdx.x;
                 kq[j] = (s + i < e) ? __ldg(b.sorted + s + i) : BK_HOLE;
-                wq[j] = (MODE == 2 && s + i < e) ? __ldg(b.sorted_w + s + i) : 1u;
+                wq[j] = (W && s + i < e) ? __ldg(b.sorted_w + s + i) : 1u;
             }
 #pragma unroll
             for (u32 j = 0; j < 8; j++) {
@@ -217,23 +221,67 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                     }
                 }
             }
+            bool is_ref[4];
 #pragma unroll
             for (u32 j = 0; j < 4; j++) {
+                is_ref[j] = false;
                 if (kk[j] == BK_HOLE) continue;
-                bool is_ref = false;
                 if (MODE != 2) {                         // (MODE 2: the senders already took the reference k-mers out)
                     u32 h = hh[j];
                     ExactSlotD sl = e0[j];
                     for (;;) {                           // same probe sequence as bk_core.cuh: exact_lookup
-                        if (sl.key == kk[j]) { atomicAdd(b.idcnt + __ldg(b.slot2id + sl.gidx), cc[j]); is_ref = true; break; }
+                        if (sl.key == kk[j]) { atomicAdd(b.idcnt + __ldg(b.slot2id + sl.gidx), cc[j]); is_ref[j] = true; break; }
                         if (sl.key == BK_EMPTY) break;
                         h = (h + 1) & b.exact_mask;
                         sl = load_exact(b.exact + h);
                     }
                 }
-                bool keep = !is_ref;
+            }
+            if (MODE == 0 && b.nb) {
+                // Is the k-mer the string of an unambiguous mismatch-line cell (bk_dense.cuh)?  k candidate cells — digit jj
+                // replaced — probed seven at a time: the loads of a batch are independent, a thread waits for three or four
+                // memory round trips per k-mer instead of k.
+#pragma unroll 1
+                for (u32 j = 0; j < 4; j++) {
+                    if (kk[j] == BK_HOLE || is_ref[j]) continue;
+                    const u64 K = kk[j];
+                    bool done = false;
+#pragma unroll 1
+                    for (u32 j0 = 0; j0 < b.k && !done; j0 += 7) {
+                        u64 key[7]; u32 hs[7]; ExactSlotD sl[7];
+#pragma unroll
+                        for (u32 t = 0; t < 7; t++) {
+                            const u32 jj = min(j0 + t, b.k - 1);
+                            key[t] = ((u64)jj << 58) | (K & ~(3ull << (2 * (b.k - 1 - jj))));
+                            hs[t] = hash_slot(key[t], b.nb_shift);
+                            sl[t] = load_exact(b.nb + hs[t]);
+                        }
+#pragma unroll
+                        for (u32 t = 0; t < 7; t++) {
+                            const u32 jj = j0 + t;
+                            if (jj >= b.k || done) continue;
+                            u32 h = hs[t];
+                            ExactSlotD s1 = sl[t];
+                            while (s1.key != key[t] && s1.key != BK_EMPTY) { h = (h + 1) & b.nb_mask; s1 = load_exact(b.nb + h); }
+                            if (s1.key != key[t]) continue;
+                            done = true;                                       // a neighbour: if it is ambiguous every neighbour is, the k-mer stays here
+                            const u32 id = s1.gidx;
+                            if (((__ldg(b.id_amb + id) >> jj) & 1u) == 0) {
+                                const u32 line = (__ldg(b.id_rep + id) + jj) * 4u + (u32)((K >> (2 * (b.k - 1 - jj))) & 3);
+                                atomicAdd(b.dense + (size_t)line * (b.k + 1) + jj, cc[j]);
+                                b.dense_flag[line] = 1;
+                                is_ref[j] = true;                              // leaves the bins: counted with its cell
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (u32 j = 0; j < 4; j++) {
+                if (kk[j] == BK_HOLE) continue;
+                bool keep = !is_ref[j];
                 if (MODE != 1) {
-                    if (!is_ref) { uniq++; total += cc[j]; }
+                    if (!is_ref[j]) { uniq++; total += cc[j]; }
                     keep = keep && cc[j] >= a.ci && cc[j] <= 1000000000u;
                 }
                 if (keep) mine++; else kk[j] = BK_HOLE;

@@ -167,7 +167,15 @@ struct CountView {
     u32* gen_full;                   // set to 1 if the novel table / list ran out of room
     u64* nov; u32 nov_cap; u32* nov_n;   // list mode (nov != null): novel k-mer occurrences are appended here instead of
                                          // being counted in `gen`; bk_bins.cuh counts the list afterwards
+    u32* nov_w;                          // weights of the list entries (null: every entry counts once)
     uint2* desc; u32 desc_cap; u32* n_desc;
+    // Mismatch lines (null = off): k-mers with exactly ONE mismatch against the diagonal their read follows are not
+    // listed one by one.  A mismatch of read base e (reference base index r = g0 + e) to base b is seen by the k-mers
+    // starting at read bases e - j, j = 0 .. k-1 (j = where the mismatch sits inside the k-mer); those that hold no other
+    // bad base form a range jlo .. jhi and are counted with two atomics on line (r, b): dense[(r * 4 + b) * (k + 1) + jlo]
+    // += 1, [.. + jhi + 1] -= 1 — a difference array along j, like `diff` along the diagonal.  Cell (line, j) after the
+    // prefix sum = occurrences of the k-mer "reference k-mer at raw slot r - j with digit j replaced by b".
+    u32* dense; u8* dense_flag;          // lines x (k + 1) counters; one byte per line: touched
 };
 
 #if defined(__CUDACC__)
@@ -207,7 +215,7 @@ BK_HD u32 count_one(const CountView& v, u64 kmer) {
     }
     if (v.nov) {                                         // list mode, rare paths only (one atomic per k-mer)
         const u32 pos = fetch_add_u32(v.nov_n, 1u);
-        if (pos < v.nov_cap) v.nov[pos] = kmer; else *v.gen_full = 1;
+        if (pos < v.nov_cap) { v.nov[pos] = kmer; if (v.nov_w) v.nov_w[pos] = 1u; } else *v.gen_full = 1;
         return 0;
     }
     u32 h = hash_slot(kmer, v.gen_shift);
@@ -262,6 +270,21 @@ BK_HD u32 emit_leftover(const CountView& v, const Ld& ld, u32 o0, u32 a, u32 cnt
 BK_HD void emit_run(const CountView& v, i32 g0, u32 a, u32 cnt) {
     add_u32(v.diff + (u32)(g0 + (i32)a), 1u);
     add_u32(v.diff + (u32)(g0 + (i32)a) + cnt, 0xFFFFFFFFu);
+}
+
+// one read byte → 2-bit code (A0 C1 G2 T3, either case); false if it is not one of ACGTacgt
+template <class Ld>
+BK_HD bool base_code(const Ld& ld, u32 byte_off, u32* code) {
+    const u32 up = ((ld(byte_off >> 2) >> (8 * (byte_off & 3))) & 0xFFu) & 0xDFu;
+    *code = ((up >> 1) ^ (up >> 2)) & 3u;
+    return up == 'A' || up == 'C' || up == 'G' || up == 'T';
+}
+BK_HD void emit_dense(const CountView& v, u32 refpos, u32 alt, u32 jlo, u32 jhi) {
+    const u32 line = refpos * 4u + alt;
+    u32* row = v.dense + (size_t)line * (v.k + 1);
+    add_u32(row + jlo, 1u);
+    add_u32(row + jhi + 1, 0xFFFFFFFFu);
+    v.dense_flag[line] = 1;
 }
 
 #ifndef BK_MAX_SEEDS
@@ -380,6 +403,10 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
     i32 c = 0;
     i32 seed_from = 0;
     bool active = has;                           // still looking for / following a diagonal
+    // mismatch lines: the last bad base of the current diagonal whose one-mismatch k-mers are not classified yet
+    // (-1: none) and the first k-mer start that may hold it alone
+    const bool dense_on = v.dense != nullptr && len < 32768u;
+    i32 pe = -1, pe_lo = 0;
     const i32 cmax = (i32)v.ref_chunks - 1;
     for (u32 diag = 0; diag < BK_MAX_DIAGS; diag++) {
         if (!BK_ANY(active)) break;
@@ -409,14 +436,30 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
             w_end = (i_hi + 31) >> 5;
         }
         bool bailed = false;
-#define BK_EVENT(e_)                                                                        \
+        pe = -1;                                 // (a mismatch left pending by a diagonal that was given up stays a leftover)
+        // A bad base at e (real_: a mismatch / non-ACGT byte inside the overlap; else the end of the overlap).  First the
+        // pending mismatch pe is settled: the k-mers that hold pe and no other bad base start in [pe_lo, min(pe, e - k)];
+        // if pe is a clean substitution they go to its mismatch line, and what was pending before them to a leftover
+        // stretch.  K-mers holding two bad bases, a non-ACGT byte or bases outside the overlap stay leftovers.
+#define BK_EVENT(e_, real_)                                                                 \
     do {                                                                                    \
         const i32 e__ = (e_);                                                               \
+        if (pe >= 0) {                                                                      \
+            const i32 hi__ = (e__ - (i32)k) < pe ? (e__ - (i32)k) : pe;                     \
+            u32 code__;                                                                     \
+            if (pe_lo <= hi__ && base_code(ld, o0 + (u32)pe, &code__)) {                    \
+                if (c < pe_lo) created += emit_leftover(v, ld, o0, (u32)c, (u32)(pe_lo - c), gofs, pend); \
+                emit_dense(v, (u32)(g0 + pe), code__, (u32)(pe - hi__), (u32)(pe - pe_lo)); \
+                c = hi__ + 1;                                                               \
+            }                                                                               \
+            pe = -1;                                                                        \
+        }                                                                                   \
         if (e__ - ms >= (i32)k) {                                                           \
             if (c < ms) created += emit_leftover(v, ld, o0, (u32)c, (u32)(ms - c), gofs, pend); \
             emit_run(v, g0, (u32)ms, (u32)(e__ - (i32)k + 1 - ms));                         \
             c = e__ - (i32)k + 1;                                                           \
         }                                                                                   \
+        if (dense_on && (real_)) { pe = e__; pe_lo = (e__ - (i32)k + 1) > ms ? (e__ - (i32)k + 1) : ms; } \
         ms = e__ + 1;                                                                       \
     } while (0)
         for (;;) {                               // segments of up to 32 words
@@ -467,7 +510,7 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
                     u32 t = word_mask(ld, o0 + (u32)b0, ex8, i_lo - b0, i_hi - b0);
                     if (BK_POPC(t) >= BK_BAIL_MISMATCHES) {            // wrong diagonal from here on: close, re-seed
                         const i32 e = b0 + (i32)BK_FFS0(t);
-                        BK_EVENT(e);
+                        BK_EVENT(e, false);                            // (wrong diagonal: nothing around e is a one-mismatch k-mer of it)
                         seed_from = e + 1;
                         bailed = true;
                         wm = 0;
@@ -475,14 +518,14 @@ BK_HD u32 scan_read(const CountView& v, const Ld& ld, const LdRef4& ldr4, u32 o0
                         while (t) {
                             const u32 j = BK_FFS0(t);
                             t &= t - 1;
-                            BK_EVENT(b0 + (i32)j);
+                            BK_EVENT(b0 + (i32)j, true);
                         }
                     }
                 }
                 BK_SYNCWARP();
             }
         }
-        if (active && !bailed) { BK_EVENT(i_hi); active = false; }
+        if (active && !bailed) { BK_EVENT(i_hi, false); active = false; }
 #undef BK_EVENT
     }
     if (has && (i32)nk > c) created += emit_leftover(v, ld, o0, (u32)c, nk - (u32)c, gofs, pend);

@@ -63,9 +63,12 @@ struct FileState {
     DevBuf<u32> bsum;                          // prefix-sum scratch
     DevBuf<u64> nov, sorted;                   // novel k-mer occurrences of the file, and the same grouped by bin (bk_bins.cuh)
     DevBuf<u32> bin_cnt;
+    DevBuf<u32> dense; DevBuf<u8> dflag;       // mismatch lines (bk_dense.cuh): all zero between samples
+    bool dense_dirty = true;                   // not known to be all zero (fresh allocation, or a sample that did not finish)
     // read-sharded mode: pair counts next to nov / sorted, per-bin pair counts, pairs received from the other ranks
     DevBuf<u32> wa, wb, dcount, own_off;
     DevBuf<u64> rk, rsk; DevBuf<u32> rc, rsw;
+    size_t ck_cap = 0;                         // capacity the counted list of this sample was given (its back end holds the mismatch-line k-mers)
     u64 nov_ub = 0;                            // upper bound of list entries the pushes so far were given room for
     u64 nov_limit = 0;                         // entries the kernels may use (the allocation can be larger: it is reused)
     u32 bin_log2p = 8;
@@ -73,7 +76,7 @@ struct FileState {
     u64 total_reads = 0, total_bases = 0;
     void release() {
         diff.release(); idcnt.release(); ckmers.release(); ccounts.release(); gstats.release(); desc.release(); bsum.release();
-        nov.release(); sorted.release(); bin_cnt.release(); wa.release(); wb.release(); dcount.release(); own_off.release();
+        nov.release(); sorted.release(); bin_cnt.release(); dense.release(); dflag.release(); wa.release(); wb.release(); dcount.release(); own_off.release();
         rk.release(); rsk.release(); rc.release(); rsw.release();
     }
 };
@@ -90,6 +93,9 @@ struct IndexDev {
     DevBuf<u32> d_refnib; DevBuf<u32> d_oseq_start, d_oseq_len;
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
+    DevBuf<u32> d_slot2rep, d_id_amb, d_id_rep; DevBuf<ExactSlotD> d_nb;       // mismatch lines (bk_dense.cuh); empty when !d.dense_ok
+    DevBuf<u32> d_line_amb, d_line_fold;
+    DevBuf<uint2> d_id_bucket;                                                   // map shortcut (bk_host.h); empty when !d.map_shortcut_ok
     DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
     u32 max_seqs_per_genome = 1;
     ~IndexDev() {
@@ -97,6 +103,7 @@ struct IndexDev {
         d_bucket_slots.release(); d_bucket_entries.release(); d_group_slots.release(); d_group_centers.release(); d_group_buckets.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
         d_exact.release(); d_slot2id.release(); d_id_kmer.release(); d_genome_row0.release(); d_genome_seq_off.release();
         d_seq_row0.release(); d_genome_len.release(); d_ref_code.release();
+        d_slot2rep.release(); d_id_amb.release(); d_id_rep.release(); d_nb.release(); d_id_bucket.release(); d_line_amb.release(); d_line_fold.release();
     }
 };
 
@@ -285,9 +292,11 @@ int bk_create(bk_ctx** out, int device) {
                  cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_bin_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
                  cudaFuncSetAttribute(k_bin_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_bin_count<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_bin_count<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
-                 cudaFuncSetAttribute(k_bin_count<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess;
+                 cudaFuncSetAttribute(k_bin_count<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess &&
+                 cudaFuncSetAttribute(k_bin_count<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_BIN_SMEM) == cudaSuccess;
     if (!ok) { g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()); delete ctx; return BK_ERR_CUDA; }
     memset(&ctx->times, 0, sizeof ctx->times);
     memset(&ctx->result, 0, sizeof ctx->result);
@@ -391,6 +400,20 @@ static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
     BK_CUDA(ctx->I->d_oseq_len.upload(d.oseq_len, st));
     BK_CUDA(ctx->I->d_slot2id.upload(d.slot2id, st));
     BK_CUDA(ctx->I->d_id_kmer.upload(d.id_kmer, st));
+    if (d.dense_ok) {
+        BK_CUDA(ctx->I->d_slot2rep.upload(d.slot2rep, st));
+        BK_CUDA(ctx->I->d_id_amb.upload(d.id_amb, st));
+        BK_CUDA(ctx->I->d_id_rep.upload(d.id_rep, st));
+        BK_CUDA(ctx->I->d_line_amb.upload(d.line_amb, st));
+        BK_CUDA(ctx->I->d_line_fold.upload(d.line_fold, st));
+        BK_CUDA(ctx->I->d_nb.reserve(d.nb_slots.size()));
+        BK_CUDA(cudaMemcpyAsync(ctx->I->d_nb.p, d.nb_slots.data(), d.nb_slots.size() * 16, cudaMemcpyHostToDevice, st));
+        if (d.map_shortcut_ok) {
+            static_assert(sizeof(OffLen) == sizeof(uint2), "layout");
+            BK_CUDA(ctx->I->d_id_bucket.reserve(d.id_bucket.size()));
+            BK_CUDA(cudaMemcpyAsync(ctx->I->d_id_bucket.p, d.id_bucket.data(), d.id_bucket.size() * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
     BK_CUDA(ctx->I->d_genome_row0.upload(d.genome_row0, st));
     BK_CUDA(ctx->I->d_genome_seq_off.upload(d.genome_seq_off, st));
     BK_CUDA(ctx->I->d_seq_row0.upload(d.seq_row0, st));
@@ -431,6 +454,11 @@ static int size_for_index(bk_ctx* ctx) {
         BK_CUDA(f.idcnt.reserve(d.id_kmer.size()));
         BK_CUDA(f.gstats.reserve((size_t)d.n_genomes * 4));
         BK_CUDA(f.bsum.reserve(std::max<size_t>((size_t)d.n_raw + 2, (size_t)16384 * ctx->sm_count * BK_BIN_G_PER_SM) / BK_PS_BLOCK + 2));
+        if (d.dense_ok) {
+            BK_CUDA(f.dense.reserve((size_t)d.n_raw * 4 * (d.k + 1)));
+            BK_CUDA(f.dflag.reserve((size_t)d.n_raw * 4));
+        }
+        f.dense_dirty = true;
     }
     ctx->in_sample = false; ctx->finished = false;
     return BK_OK;
@@ -581,6 +609,9 @@ static CountView make_count_view(bk_ctx* ctx, int slot) {
     v.gen_full = &ctx->d_ctr.p->gen_full;
     v.nov = f.nov.p; v.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
     v.nov_n = &ctx->d_ctr.p->f[slot].nov_n;
+    const bool dense = ctx->I->d.dense_ok;
+    v.nov_w = dense ? f.wa.p : nullptr;                    // (with mismatch lines the list is weighted: ambiguous cells join it)
+    v.dense = dense ? f.dense.p : nullptr; v.dense_flag = dense ? f.dflag.p : nullptr;
     v.desc = f.desc.p; v.desc_cap = (u32)std::min<size_t>(f.desc.cap, 0xFFFFFFFFu); v.n_desc = &ctx->d_ctr.p->f[slot].n_desc;
     return v;
 }
@@ -607,6 +638,13 @@ static int file_prepare(bk_ctx* ctx, int slot) {
     cudaStream_t st = ctx->s_count[slot];
     BK_CUDA(cudaMemsetAsync(f.diff.p, 0, ((size_t)ctx->I->d.n_raw + 2) * 4, st));
     BK_CUDA(cudaMemsetAsync(f.idcnt.p, 0, std::max<size_t>(ctx->I->d.id_kmer.size(), 1) * 4, st));
+    if (ctx->I->d.dense_ok) {
+        if (f.dense_dirty) {                               // (normally the finish leaves the lines all zero)
+            BK_CUDA(cudaMemsetAsync(f.dense.p, 0, f.dense.cap * 4, st));
+            BK_CUDA(cudaMemsetAsync(f.dflag.p, 0, f.dflag.cap, st));
+        }
+        f.dense_dirty = true;
+    }
     f.used = true;
     return BK_OK;
 }
@@ -621,7 +659,7 @@ static int novel_room(bk_ctx* ctx, int slot, u64 n_bases) {
     const u64 LIMIT = 0xFFFFFFF0ull;
     if (ctx->params.table_log2) {
         const u64 need = 1ull << ctx->params.table_log2;
-        if (f.nov_ub == 0) BK_CUDA(f.nov.reserve(need));
+        if (f.nov_ub == 0) { BK_CUDA(f.nov.reserve(need)); if (ctx->I->d.dense_ok) BK_CUDA(f.wa.reserve(need)); }
         f.nov_ub = need; f.nov_limit = need;
         return BK_OK;
     }
@@ -643,7 +681,15 @@ static int novel_room(bk_ctx* ctx, int slot, u64 n_bases) {
             BK_CUDA(cudaStreamSynchronize(st));
             f.nov.release();
             f.nov = bigger;
-        } else BK_CUDA(f.nov.reserve(want));
+            if (ctx->I->d.dense_ok) {
+                DevBuf<u32> bw;
+                BK_CUDA(bw.reserve(want));
+                BK_CUDA(cudaMemcpyAsync(bw.p, f.wa.p, f.nov_ub * 4, cudaMemcpyDeviceToDevice, st));
+                BK_CUDA(cudaStreamSynchronize(st));
+                f.wa.release();
+                f.wa = bw;
+            }
+        } else { BK_CUDA(f.nov.reserve(want)); if (ctx->I->d.dense_ok) BK_CUDA(f.wa.reserve(want)); }
     }
     f.nov_ub = need; f.nov_limit = need;
     return BK_OK;
@@ -790,6 +836,7 @@ static int stage_fold(bk_ctx* ctx, int slot, cudaStream_t st) {
     const u32 n = d.n_raw;
     const u32 nb = (n + BK_PS_BLOCK - 1) / BK_PS_BLOCK;
     int sp = ctx->span_begin(ST_FINALIZE, st);
+    BK_CUDA(cudaMemsetAsync(f.gstats.p, 0, (size_t)d.n_genomes * 16, st));      // (tallies: the mismatch-line cells add theirs before the map kernel does)
     k_diff_blocksum<<<nb, BK_PS_THREADS, 0, st>>>(f.diff.p, n, f.bsum.p);
     k_diff_scan_bsum<<<1, BK_PS_THREADS, 0, st>>>(f.bsum.p, nb);
     k_diff_apply<<<nb, BK_PS_THREADS, 0, st>>>(f.diff.p, n, f.bsum.p, ctx->I->d_slot2id.p, f.idcnt.p);
@@ -811,9 +858,12 @@ static CompactArgs make_compact_args(bk_ctx* ctx, int slot, size_t out_cap) {
 
 // the list of `ub` (an upper bound) entries → bins: P = 2^lp bins sized so that a worst-case round of a bin is ~1/32 of
 // the bound at 3 % of it novel; histogram, prefix, scatter.  W: entries carry weights.
-static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted, cudaStream_t st) {
+static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted, cudaStream_t st, bool weighted_pairs = false) {
     FileState& f = ctx->file[slot];
     const DerivedIndex& d = ctx->I->d;
+    // (with mismatch lines the list holds ~1/20 of what it held: fewer, fuller bins; a list that is large all the same —
+    // foreign reads — is walked in rounds)
+    if (d.dense_ok && !weighted_pairs) ub /= 16;
     u32 lp = 6;
     while (lp < 14 && ((u64)BK_BIN_ROUND << lp) < ub / 32) lp++;
     f.bin_log2p = lp;
@@ -822,12 +872,61 @@ static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted,
     b.cnt = f.bin_cnt.p; b.log2p = lp; b.G = G;
     b.exact = ctx->I->d_exact.p; b.exact_shift = 64 - d.exact_log2; b.exact_mask = (1u << d.exact_log2) - 1;
     b.slot2id = ctx->I->d_slot2id.p; b.idcnt = f.idcnt.p;
+    b.k = d.k;
+    if (d.dense_ok) {
+        b.nb = ctx->I->d_nb.p; b.nb_shift = 64 - d.nb_log2; b.nb_mask = (1u << d.nb_log2) - 1;
+        b.id_amb = ctx->I->d_id_amb.p; b.id_rep = ctx->I->d_id_rep.p; b.dense = f.dense.p; b.dense_flag = f.dflag.p;
+    }
     k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
     launch_prefix(ctx, f.bin_cnt.p, PG, f.bsum.p, st);
     if (weighted) k_bin_scatter<true><<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
     else k_bin_scatter<false><<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
     ctx->launches += 2;
     BK_CUDA(cudaGetLastError());
+    return BK_OK;
+}
+
+static MapView make_map_view(bk_ctx* ctx);
+static bool dense_maps(const bk_ctx* ctx) { return ctx->I->d.dense_ok && ctx->I->d.map_shortcut_ok && can_fuse_map(ctx) && !ctx->shard; }
+static DenseView make_dense_view(bk_ctx* ctx, int slot) {
+    FileState& f = ctx->file[slot];
+    const DerivedIndex& d = ctx->I->d;
+    DenseView dv; memset(&dv, 0, sizeof dv);
+    if (!d.dense_ok) return dv;
+    dv.dense = f.dense.p; dv.flag = f.dflag.p; dv.n_lines = d.n_raw * 4; dv.k = d.k;
+    dv.slot2rep = ctx->I->d_slot2rep.p; dv.slot2id = ctx->I->d_slot2id.p; dv.id_kmer = ctx->I->d_id_kmer.p; dv.id_amb = ctx->I->d_id_amb.p;
+    dv.line_amb = ctx->I->d_line_amb.p; dv.line_fold = ctx->I->d_line_fold.p;
+    dv.nov = f.nov.p; dv.nov_w = f.wa.p; dv.nov_n = &ctx->d_ctr.p->f[slot].nov_n; dv.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
+    dv.full = &ctx->d_ctr.p->gen_full;
+    if (dense_maps(ctx)) {
+        dv.id_bucket = ctx->I->d_id_bucket.p; dv.m = make_map_view(ctx); dv.gstats = f.gstats.p;
+        dv.pile = ctx->d_pile_all.p; dv.pile_stride = d.max_genome_rows * 4;
+    }
+    return dv;
+}
+
+// mismatch-line cells that join the list (the ambiguous ones; all of them on a read-sharded rank) need room behind the
+// occurrences the pushes were given room for: at most one entry per cell, and no more cells than k-mers
+static u64 dense_cells_max(const bk_ctx* ctx, const FileState& f) {
+    const DerivedIndex& d = ctx->I->d;
+    return d.dense_ok ? std::min<u64>((u64)d.n_raw * 4 * d.k, f.total_bases) : 0;
+}
+static int dense_list_room(bk_ctx* ctx, int slot, cudaStream_t st) {
+    FileState& f = ctx->file[slot];
+    if (!ctx->I->d.dense_ok || ctx->params.table_log2) return BK_OK;      // (a caller-fixed capacity is what it is: overflow is reported)
+    const u64 need = std::min<u64>(f.nov_ub + dense_cells_max(ctx, f) + 64, 0xFFFFFFF0ull);
+    if (need > f.nov.cap) {
+        DevBuf<u64> bk_; DevBuf<u32> bw;
+        BK_CUDA(bk_.reserve(need)); BK_CUDA(bw.reserve(need));
+        if (f.nov.p && f.nov_ub) {
+            BK_CUDA(cudaMemcpyAsync(bk_.p, f.nov.p, std::min<u64>(f.nov_ub, f.nov.cap) * 8, cudaMemcpyDeviceToDevice, st));
+            BK_CUDA(cudaMemcpyAsync(bw.p, f.wa.p, std::min<u64>(f.nov_ub, f.wa.cap) * 4, cudaMemcpyDeviceToDevice, st));
+            BK_CUDA(cudaStreamSynchronize(st));
+        }
+        f.nov.release(); f.wa.release();
+        f.nov = bk_; f.wa = bw;
+    }
+    f.nov_ub = need; f.nov_limit = need;
     return BK_OK;
 }
 
@@ -838,21 +937,43 @@ static int stage_compact(bk_ctx* ctx, int slot, cudaStream_t st) {
     if (f.finalized) return BK_OK;
     const DerivedIndex& d = ctx->I->d;
     const u32 n_ids = (u32)d.id_kmer.size();
-    // the novel part of the list: a kept k-mer stands for >= ci occurrences
+    // the novel part of the list: a kept k-mer stands for >= ci occurrences; mismatch-line cells (kept where they are, or
+    // through the list if ambiguous): at most one k-mer each
     const size_t novel_cap = std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)) / std::max<u32>(ctx->params.min_kmers, 1) + 1;
-    const size_t out_cap = (size_t)n_ids + novel_cap;
+    const size_t out_cap = (size_t)n_ids + novel_cap + dense_cells_max(ctx, f);
+    { int rc = dense_list_room(ctx, slot, st); if (rc) return rc; }
     BK_CUDA(f.ckmers.reserve(out_cap)); BK_CUDA(f.ccounts.reserve(out_cap));
+    f.ck_cap = out_cap;
     BK_CUDA(f.sorted.reserve(std::max<size_t>(std::min<u64>(f.nov.cap, std::max<u64>(f.nov_ub, 1)), 1)));
     int sp = ctx->span_begin(ST_FINALIZE, st);
     const CompactArgs a = make_compact_args(ctx, slot, out_cap);
+    const bool dense = d.dense_ok;
+    DenseView dv = make_dense_view(ctx, slot);
+    const int dgrid = dense ? grid_for(ctx, (u64)dv.n_lines, 256, 4) : 0;
+    if (dense) {                                           // mismatch lines: counts per cell, one cell per string, ambiguous ones to the list
+        BK_CUDA(f.wb.reserve(f.sorted.cap));
+        k_dense_prefix<<<dgrid, 256, 0, st>>>(dv);
+        k_dense_fold<<<dgrid, 256, 0, st>>>(dv);
+        k_dense_emit<0, false><<<dgrid, 256, 0, st>>>(dv, a);
+        ctx->launches += 3;
+    }
     BinView b; memset(&b, 0, sizeof b);
     b.nov = f.nov.p; b.nov_n = &ctx->d_ctr.p->f[slot].nov_n; b.nov_cap = (u32)std::min<u64>(f.nov.cap, f.nov_limit);
     b.sorted = f.sorted.p;
+    if (dense) { b.nov_w = f.wa.p; b.sorted_w = f.wb.p; }
     if (!ablated("bins")) {
-        int rc = launch_bins(ctx, slot, b, f.nov_ub, false, st);
+        int rc = launch_bins(ctx, slot, b, f.nov_ub, dense, st);
         if (rc) return rc;
-        if (!ablated("bincount")) k_bin_count<0><<<1u << b.log2p, 256, BK_BIN_SMEM, st>>>(b, a, &ctx->d_ctr.p->gen_full);
+        if (ablated("bincount")) {}
+        else if (dense) k_bin_count<0, true><<<1u << b.log2p, 256, BK_BIN_SMEM, st>>>(b, a, &ctx->d_ctr.p->gen_full);
+        else k_bin_count<0, false><<<1u << b.log2p, 256, BK_BIN_SMEM, st>>>(b, a, &ctx->d_ctr.p->gen_full);
         ctx->launches++;
+    }
+    if (dense) {                                           // what is left on the lines is final: cut-offs, counted list, lines back to zero
+        if (dense_maps(ctx)) k_dense_emit<1, true><<<dgrid, 256, 0, st>>>(dv, a);       // ... and mapped on the spot: tallies + all-genome pileups
+        else k_dense_emit<1, false><<<dgrid, 256, 0, st>>>(dv, a);
+        ctx->launches++;
+        f.dense_dirty = false;
     }
     k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, st>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
     ctx->launches++;
@@ -896,7 +1017,6 @@ static int stage_map_fused(bk_ctx* ctx, int f, cudaStream_t st) {
     Counters* dc = ctx->d_ctr.p;
     FileState& fs = ctx->file[f];
     int sp = ctx->span_begin(ST_MAP, st);
-    BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
     const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
     if (ablated("map")) {}
     else if (m.gslots) k_map_grp<2><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, ctx->d_pile_all.p, pile_stride);
@@ -930,7 +1050,6 @@ static int stage_map_stats(bk_ctx* ctx, int f, cudaStream_t st) {
     Counters* dc = ctx->d_ctr.p;
     FileState& fs = ctx->file[f];
     int sp = ctx->span_begin(ST_MAP, st);
-    BK_CUDA(cudaMemsetAsync(fs.gstats.p, 0, (size_t)d.n_genomes * 16, st));
     const u32 ccap = (u32)std::min<size_t>(fs.ckmers.cap, 0xFFFFFFFFu);
     if (small && m.gslots) k_map_grp<0><<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
     else if (small) (d.rekeyed ? k_map_small<0, 1> : k_map_small<0, 0>)<<<ctx->sm_count * BK_STRIDE_WAVES, 256, 0, st>>>(m, fs.ckmers.p, fs.ccounts.p, &dc->f[f].n_counted, ccap, fs.gstats.p, nullptr, nullptr, 0);
@@ -1023,7 +1142,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "no room left for novel k-mers (list / bin table); set bk_params.table_log2 higher");
     if (c.var_overflow) return ctx->fail(BK_ERR_OVERFLOW, "variant buffer overflow");
     for (int f = 0; f < n_files; f++) {
-        if ((size_t)c.f[f].n_counted > ctx->file[f].ckmers.cap) return ctx->fail(BK_ERR_OVERFLOW, "counted k-mer list overflow");
+        if ((size_t)c.f[f].n_counted + c.f[f].n_dense > ctx->file[f].ckmers.cap) return ctx->fail(BK_ERR_OVERFLOW, "counted k-mer list overflow");
         ctx->gstats[f].assign(d.n_genomes, bk_genome_stats());
         for (u32 g = 0; g < d.n_genomes; g++) {
             bk_genome_stats& s = ctx->gstats[f][g];
@@ -1039,7 +1158,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
             r.kmc[f].unique_kmers = ctx->h_stats[f * 4 + 2]; r.kmc[f].unique_counted = ctx->h_stats[f * 4 + 3];
         } else {
             r.kmc[f].total_reads = ctx->file[f].total_reads; r.kmc[f].total_kmers = c.f[f].total_kmers;
-            r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = c.f[f].n_counted;
+            r.kmc[f].unique_kmers = c.f[f].unique; r.kmc[f].unique_counted = (u64)c.f[f].n_counted + c.f[f].n_dense;
         }
     }
     if (c.best < 0) {
@@ -1188,8 +1307,17 @@ int bk_kmer_counts_get(bk_ctx* ctx, int slot, uint64_t* kmers, uint32_t* counts,
     *n = have;
     if (!have) return BK_OK;
     std::vector<u64> hk(have); std::vector<u32> hc(have);
-    BK_CUDA(cudaMemcpyAsync(hk.data(), ctx->file[slot].ckmers.p, have * 8, cudaMemcpyDeviceToHost, ctx->s_score));
-    BK_CUDA(cudaMemcpyAsync(hc.data(), ctx->file[slot].ccounts.p, have * 4, cudaMemcpyDeviceToHost, ctx->s_score));
+    // the list has a front (k-mers the map kernel handled) and a back (mismatch-line cells mapped where they were counted)
+    const u64 n_back = ctx->shard ? 0 : ctx->h_ctr->f[slot].n_dense, n_front = have - n_back;
+    const size_t cap = ctx->file[slot].ck_cap;
+    if (n_front) {
+        BK_CUDA(cudaMemcpyAsync(hk.data(), ctx->file[slot].ckmers.p, n_front * 8, cudaMemcpyDeviceToHost, ctx->s_score));
+        BK_CUDA(cudaMemcpyAsync(hc.data(), ctx->file[slot].ccounts.p, n_front * 4, cudaMemcpyDeviceToHost, ctx->s_score));
+    }
+    if (n_back) {
+        BK_CUDA(cudaMemcpyAsync(hk.data() + n_front, ctx->file[slot].ckmers.p + (cap - n_back), n_back * 8, cudaMemcpyDeviceToHost, ctx->s_score));
+        BK_CUDA(cudaMemcpyAsync(hc.data() + n_front, ctx->file[slot].ccounts.p + (cap - n_back), n_back * 4, cudaMemcpyDeviceToHost, ctx->s_score));
+    }
     BK_CUDA(cudaStreamSynchronize(ctx->s_score));
     std::vector<u32> order(have);
     for (u64 i = 0; i < have; i++) order[i] = (u32)i;

@@ -107,6 +107,27 @@ struct DerivedIndex {
     // raw slot → id of the distinct k-mer string (0xFFFFFFFF for invalid slots); id → k-mer
     std::vector<u32> slot2id;
     std::vector<u64> id_kmer;
+    // Mismatch lines (bk_core.cuh: emit_dense; bk_dense.cuh).  A k-mer with exactly one mismatch against the diagonal of
+    // its read is counted in cell (raw slot, j, b).  Cells are folded onto the representative raw slot of the reference
+    // k-mer (slot2rep), and a cell's k-mer string "id's k-mer with digit j replaced by b" is unique to the cell unless
+    // another reference k-mer lies within Hamming distance 2 of id's and differs from it at digit j (then two cells —
+    // or a cell and a reference k-mer — can spell the same string): bit j of id_amb[id] marks those, they are
+    // counted through the exact bins instead.  nb_slots: (j << 58 | k-mer without digit j) → id, for every id and j:
+    // a k-mer that reaches the bins another way (two mismatches on its own diagonal, foreign diagonal, ...) finds the
+    // cell it belongs to.  dense_ok = false (k > 29, large databases): everything goes through the bins as before.
+    bool dense_ok = false;
+    std::vector<u32> slot2rep;               // raw slot → representative raw slot of its k-mer (0xFFFFFFFF: invalid slot)
+    std::vector<u32> id_rep;                 // id → its representative raw slot
+    std::vector<u32> line_amb, line_fold;    // per reference base r: bit j = cell (slot r - j, j) is ambiguous / sits on a non-representative slot
+    std::vector<u32> id_amb;                 // per id: bit j set = cells (id, j, *) are ambiguous
+    u32 nb_log2 = 0;
+    std::vector<ExactSlot> nb_slots;         // key, gidx = id (oseq unused); key == ~0 → empty
+    // Map shortcut (rekeyed tables only).  The k-mer of an unambiguous cell (id, j, b) is within one digit of exactly one
+    // reference k-mer — id's — so map_kmers can hit one bucket at most: index j of id's canonical form, and only if
+    // replacing the digit does not flip which strand of the k-mer is canonical (bit 31 of id_amb[id]: id's k-mer is
+    // the reverse complement of its canonical form).  id_bucket[id * k + j] = {off, len} of that bucket's entries.
+    bool map_shortcut_ok = false;
+    std::vector<OffLen> id_bucket;
 };
 
 static const u32 REF_PAD_BASES = 64;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -549,6 +550,98 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
         u64 h = hash_slot_host(occ[i].kmer, 64 - d.exact_log2);
         while (d.exact_slots[h].key != ~0ull) h = (h + 1) & emask;
         d.exact_slots[h] = ExactSlot{occ[i].kmer, occ[i].gidx, occ[i].oseq};
+    }
+
+    // ---- mismatch lines (bk_host.h) ----
+    const size_t n_ids = d.id_kmer.size();
+    d.dense_ok = k <= 29 && n_ids > 0 && n_ids <= 400000 && (u64)d.n_raw * 4 * (k + 1) * 4 <= (512ull << 20) && getenv("BK_NO_DENSE") == nullptr;
+    if (!d.dense_ok) return;
+    {
+        d.id_rep.assign(n_ids, 0);
+        for (size_t i = 0; i < occ.size(); i++) if (i == 0 || occ[i].kmer != occ[i - 1].kmer) d.id_rep[d.slot2id[occ[i].gidx]] = occ[i].gidx;
+        d.slot2rep.assign(d.n_raw, 0xFFFFFFFFu);
+        for (u32 sl = 0; sl < d.n_raw; sl++) if (d.slot2id[sl] != 0xFFFFFFFFu) d.slot2rep[sl] = d.id_rep[d.slot2id[sl]];
+    }
+    // pairs of reference k-mers within Hamming distance 2 share at least one third of their digits exactly: group the
+    // ids by each third in turn and compare inside the groups
+    d.id_amb.assign(n_ids, 0);
+    {
+        const u32 cut[4] = {0, k / 3, 2 * k / 3, k};
+        std::vector<std::pair<u64, u32>> byp(n_ids);
+        for (u32 part = 0; part < 3; part++) {
+            const u32 d0 = cut[part], d1 = cut[part + 1];                        // digits [d0, d1), digit 0 = most significant
+            const u32 sh = 2 * (k - d1);
+            const u64 mask = ((1ull << (2 * (d1 - d0))) - 1);
+            for (size_t i = 0; i < n_ids; i++) byp[i] = std::make_pair((d.id_kmer[i] >> sh) & mask, (u32)i);
+            std::sort(byp.begin(), byp.end());
+            for (size_t a = 0; a < n_ids;) {
+                size_t b = a;
+                while (b < n_ids && byp[b].first == byp[a].first) b++;
+                if (b - a > 4096) {                                              // low complexity: do not compare 10^7 pairs, give up on the group
+                    for (size_t x = a; x < b; x++) d.id_amb[byp[x].second] = (1u << k) - 1u;
+                } else {
+                    for (size_t x = a; x < b; x++)
+                        for (size_t y = x + 1; y < b; y++) {
+                            const u64 df = d.id_kmer[byp[x].second] ^ d.id_kmer[byp[y].second];
+                            u64 nz = (df | (df >> 1)) & 0x5555555555555555ull;
+                            const int cnt = __builtin_popcountll(nz);
+                            if (cnt < 1 || cnt > 2) continue;
+                            while (nz) {
+                                const u32 bit = (u32)__builtin_ctzll(nz);
+                                nz &= nz - 1;
+                                const u32 j = k - 1 - bit / 2;
+                                d.id_amb[byp[x].second] |= 1u << j;
+                                d.id_amb[byp[y].second] |= 1u << j;
+                            }
+                        }
+                }
+                a = b;
+            }
+        }
+    }
+    d.nb_log2 = log2_cap(n_ids * k);
+    d.nb_slots.assign(1ull << d.nb_log2, ExactSlot{~0ull, 0, 0});
+    const u64 nmask = (1ull << d.nb_log2) - 1;
+    for (size_t i = 0; i < n_ids; i++)
+        for (u32 j = 0; j < k; j++) {
+            const u64 key = ((u64)j << 58) | (d.id_kmer[i] & ~(3ull << (2 * (k - 1 - j))));
+            u64 h = hash_slot_host(key, 64 - d.nb_log2);
+            while (d.nb_slots[h].key != ~0ull && d.nb_slots[h].key != key) h = (h + 1) & nmask;
+            if (d.nb_slots[h].key == ~0ull) d.nb_slots[h] = ExactSlot{key, (u32)i, 0};      // (a second id with this key: both are flagged at j)
+        }
+    // per line: which cells are ambiguous / must be folded (most lines: none — the kernels skip them without reading the row)
+    d.line_amb.assign(d.n_raw, 0); d.line_fold.assign(d.n_raw, 0);
+    for (u32 r = 0; r < d.n_raw; r++)
+        for (u32 j = 0; j < k && j <= r; j++) {
+            const u32 sl = r - j;
+            if (d.slot2id[sl] == 0xFFFFFFFFu) continue;
+            if ((d.id_amb[d.slot2id[sl]] >> j) & 1u) d.line_amb[r] |= 1u << j;
+            if (d.slot2rep[sl] != sl) d.line_fold[r] |= 1u << j;
+        }
+    // map shortcut
+    d.map_shortcut_ok = d.rekeyed && getenv("BK_NO_MAP_SHORTCUT") == nullptr;
+    if (d.map_shortcut_ok) {
+        d.id_bucket.assign(n_ids * k, OffLen{0, 0});
+        const u64 bmask2 = (1ull << d.bucket_log2) - 1;
+        parallel_for((n_ids + 4095) / 4096, [&](size_t c) {
+            for (size_t i = c * 4096, i_end = std::min(n_ids, (c + 1) * 4096); i < i_end; i++) {
+                const u64 S = d.id_kmer[i], R = revcomp_host(S, (int)k);
+                const bool rcS = !(S < R);                                          // src/lcb.rs:87-95
+                const u64 kb = rcS ? R : S;
+                d.id_amb[i] = (d.id_amb[i] & 0x7FFFFFFFu) | (rcS ? 0x80000000u : 0u);
+                for (u32 j = 0; j < k; j++) {
+                    const u32 jc = rcS ? k - 1 - j : j;
+                    const u64 key = ((u64)jc << 58) | (kb & ~(3ull << (2 * (k - 1 - jc))));
+                    u64 h = hash_slot_host(key, 64 - d.bucket_log2);
+                    for (;;) {
+                        const BucketSlot& sl = d.bucket_slots[h];
+                        if (sl.key == key) { d.id_bucket[i * k + j] = OffLen{sl.off, sl.len}; break; }
+                        if (sl.key == ~0ull) break;
+                        h = (h + 1) & bmask2;
+                    }
+                }
+            }
+        });
     }
 }
 

@@ -15,7 +15,8 @@ namespace bk {
 struct BucketSlotD { u64 key; u32 off; u32 len; };
 struct BucketEntryD { u32 row; unsigned short file_id; u8 idx; u8 canonical; };
 
-struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 nov_n; u64 total_kmers; u32 n_desc; u32 pad; };
+struct FileCounters { u32 n_counted; u32 gen_new; u32 unique; u32 nov_n; u64 total_kmers; u32 n_desc;
+                      u32 n_dense; };   // n_dense: counted k-mers kept at the END of the counted list (mapped where they were counted, bk_dense.cuh)
 struct Counters {
     u32 gen_full; u32 var_overflow; u32 pad0; u32 pad1;
     FileCounters f[2];
@@ -205,7 +206,7 @@ k_leftover(CountView v, const u8* __restrict__ bases, u32* gen_new) {
                 if (LIST) {
                     if (b + 1 >= k) {                        // k-mer number b + 1 - k of the stretch ends at this byte
                         const u32 pos = base + (b + 1 - k);                // reference k-mers among them are
-                        if (pos < v.nov_cap) v.nov[pos] = run >= k ? km : BK_HOLE;   // recognised when the bins are counted
+                        if (pos < v.nov_cap) { v.nov[pos] = run >= k ? km : BK_HOLE; if (v.nov_w) v.nov_w[pos] = 1u; }   // recognised when the bins are counted
                         else *v.gen_full = 1;
                     }
                 } else if (run >= k) created += count_one(v, km);
@@ -873,3 +874,4 @@ k_call(ScoreView sv, CallParams p, const double* __restrict__ noise_max, bk_vari
 }  // namespace bk
 
 #include "bk_bins.cuh"
+#include "bk_dense.cuh"

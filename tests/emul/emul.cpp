@@ -119,9 +119,11 @@ u64 emul_clean_sample_id(const char* path, char* buf, u64 cap) {
 // Counting stage on the CPU with the device logic: scan every read, drain the leftover queue, prefix
 // sum + fold, compaction.  stats4 = total_reads, total_kmers, unique_kmers, unique_counted.
 // dbg3 = number of leftover descriptors, leftover k-mers, novel keys.
-u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_log2, u32 desc_cap,
+u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_log2_flags, u32 desc_cap,
                u32 ci, u32 cs, u64* stats4, u64* dbg3) {
     Emul* e = (Emul*)h;
+    const bool use_dense = (gen_log2_flags >> 31) != 0;
+    const u32 gen_log2 = gen_log2_flags & 0xFFu;
     const DerivedIndex& d = e->d;
     const u64 n_bases = off[n_reads];
     std::vector<u32> words((n_bases + 64) / 4 + 4, 0x2A2A2A2Au);   // padding bytes are '*' (invalid)
@@ -140,6 +142,10 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     v.gen_full = &gen_full;
     v.nov = nullptr; v.nov_cap = 0; v.nov_n = nullptr;
     v.desc = desc.data(); v.desc_cap = desc_cap; v.n_desc = &n_desc;
+    // mismatch lines (bk_core.cuh: emit_dense), switched on by bit 31 of gen_log2's caller-side flag word
+    std::vector<u32> dense; std::vector<u8> dflag;
+    v.dense = nullptr; v.dense_flag = nullptr;
+    if (use_dense) { dense.assign((size_t)d.n_raw * 4 * (d.k + 1), 0); dflag.assign((size_t)d.n_raw * 4, 0); v.dense = dense.data(); v.dense_flag = dflag.data(); }
     auto ld = [&](u32 i) { return words[i]; };
     auto ldr4 = [&](u32 i4) { W4 r; r.x = d.refnib[4 * i4]; r.y = d.refnib[4 * i4 + 1]; r.z = d.refnib[4 * i4 + 2]; r.w = d.refnib[4 * i4 + 3]; return r; };
     u64 novel = 0, left_kmers = 0;
@@ -156,6 +162,41 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     }
     const u32 nd = std::min(n_desc, desc_cap);
     for (u32 i = 0; i < nd; i++) { left_kmers += desc[i].y; novel += count_stretch(v, ld, desc[i].x, desc[i].y, 0, 1); }
+    // mismatch lines: prefix sum along j; cell (line, j) = occurrences of the reference k-mer at raw slot r - j with digit j
+    // replaced by b.  Here every such k-mer simply joins the other counts (exact reference k-mer → its slot, else the novel
+    // table): the device's shortcuts for unambiguous cells (bk_dense.cuh) must give the same totals.
+    u64 dense_cells = 0, dense_kmers = 0;
+    if (use_dense) {
+        const u32 k = d.k;
+        for (size_t line = 0; line < dflag.size(); line++) {
+            if (!dflag[line]) continue;
+            const u32 refpos = (u32)(line >> 2), alt = (u32)(line & 3);
+            u32 run = 0;
+            for (u32 j = 0; j <= k; j++) {
+                run += dense[line * (k + 1) + j];
+                if (j == k) { if (run != 0) return ~0ull - 3; break; }             // a line must sum to zero
+                if (!run) continue;
+                if (refpos < j) return ~0ull - 4;
+                const u32 slot = refpos - j;
+                if (slot >= d.n_raw || d.slot2id[slot] == 0xFFFFFFFFu) return ~0ull - 5;      // cell on an invalid slot: logic error
+                const u64 ref = d.id_kmer[d.slot2id[slot]];
+                const u32 sh = 2 * (k - 1 - j);
+                if (((ref >> sh) & 3) == alt) return ~0ull - 6;                     // not a mismatch: logic error
+                const u64 km = (ref & ~(3ull << sh)) | ((u64)alt << sh);
+                dense_cells++; dense_kmers += run;
+                u32 gidx, oseq;
+                if (exact_lookup(v, km, &gidx, &oseq)) { diff[gidx] += run; diff[gidx + 1] -= run; }
+                else {
+                    u32 hh = hash_slot(km, v.gen_shift);
+                    for (;;) {
+                        if (gen[hh].key == BK_EMPTY) { gen[hh].key = km; gen[hh].cnt = run; novel++; break; }
+                        if (gen[hh].key == km) { gen[hh].cnt += run; break; }
+                        hh = (hh + 1) & v.gen_mask;
+                    }
+                }
+            }
+        }
+    }
     if (gen_full) return ~0ull;
     // prefix sum + fold
     std::vector<u32> idcnt(d.id_kmer.size(), 0);
@@ -186,7 +227,7 @@ u64 emul_count(void* h, const u8* bases, const u32* off, u64 n_reads, u32 gen_lo
     e->out_kmers.clear(); e->out_counts.clear();
     for (auto& kv : kept) { e->out_kmers.push_back(kv.first); e->out_counts.push_back(kv.second); }
     stats4[0] = n_reads; stats4[1] = total; stats4[2] = uniq; stats4[3] = kept.size();
-    if (dbg3) { dbg3[0] = n_desc; dbg3[1] = left_kmers; dbg3[2] = novel; }
+    if (dbg3) { dbg3[0] = n_desc; dbg3[1] = left_kmers; dbg3[2] = use_dense ? dense_kmers : novel; }
     return kept.size();
 }
 void emul_count_get(void* h, u64* kmers, u32* counts) {

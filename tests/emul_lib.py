@@ -73,13 +73,13 @@ class Emul:
     def save(self, path):
         assert lib().emul_save(self.h, path.encode()) == 0
 
-    def count(self, bases, off, ci=3, cs=1000000, gen_log2=20, desc_cap=None):
+    def count(self, bases, off, ci=3, cs=1000000, gen_log2=20, desc_cap=None, dense=False):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n_reads = len(off) - 1
         st, dbg = np.zeros(4, dtype=np.uint64), np.zeros(3, dtype=np.uint64)
         cap = desc_cap if desc_cap is not None else 2 * n_reads + 64
-        n = lib().emul_count(self.h, ptr(bases), ptr(off), n_reads, gen_log2, cap, ci, cs, ptr(st), ptr(dbg))
+        n = lib().emul_count(self.h, ptr(bases), ptr(off), n_reads, gen_log2 | (0x80000000 if dense else 0), cap, ci, cs, ptr(st), ptr(dbg))
         assert n < 2 ** 63, "emulation reported a logic error (code %d)" % (2 ** 64 - 1 - n)
         km, ct = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint32)
         lib().emul_count_get(self.h, ptr(km), ptr(ct))

@@ -183,12 +183,24 @@ def test_simulated_sample_all_containers_match_oracle(sars_paths, oracle, tmp_pa
         c.close()
 
 
-def test_corrupt_bgzf_is_reported(ctx):
-    import bronko_b200
+def test_corrupt_bgzf_is_reported(tmp_path, sars_paths):
+    """A BGZF block whose deflate payload is damaged: the decompression engine faults on it, which costs the process its
+    CUDA context — so this runs in a process of its own (the CLI, like a user would): the run must end with an error
+    message and exit code 1, not hang and not produce a VCF.  (BK_NO_DECOMP_ENGINE=1 sends BGZF through zlib, which
+    reports the damage without losing the context.)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bronko = os.path.join(root, "bronko_b200", "csrc", "bronko")
+    subprocess.check_call(["make", "-C", os.path.join(root, "bronko_b200", "csrc"), "-s", "bronko"])
     text = fastq_of([b"ACGTACGTACGTAGCTAGCTAGCATCGATCGAT" * 3] * 50)
     data = bytearray(bgzf(text, 997))
     data[40] ^= 0x55                                     # inside the first member's deflate payload
-    ctx.begin(bronko_b200.CallArgs())
-    with pytest.raises(bronko_b200.BkError):
-        ctx.push_fastq_mem(0, bytes(data))
-        ctx.finish()
+    bad = tmp_path / "bad.fastq.gz"
+    bad.write_bytes(bytes(data))
+    for env_extra in ({}, {"BK_NO_DECOMP_ENGINE": "1"}):
+        out = tmp_path / ("out%d" % len(env_extra))
+        r = subprocess.run([bronko, "call", "-g"] + sars_paths + ["-r", str(bad), "-o", str(out)], capture_output=True, text=True,
+                           timeout=120, env=dict(os.environ, **env_extra))
+        assert r.returncode == 1, (r.returncode, r.stderr[-400:])
+        assert "ERROR" in r.stderr
+        assert not (out / "bad.vcf").exists()

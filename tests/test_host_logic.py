@@ -93,16 +93,21 @@ def test_clean_sample_id_matches_oracle(oracle):
         assert buf.value.decode() == oracle.clean_sample_id(p), p
 
 
+@pytest.mark.parametrize("dense", [False, True])
 @pytest.mark.parametrize("strain,depth", [(0, 200), (1, 200), (3, 120)])
-def test_counting_logic_matches_oracle(oracle, sars_emul, strain, depth):
+def test_counting_logic_matches_oracle(oracle, sars_emul, strain, depth, dense):
+    """dense: k-mers with exactly one mismatch against their read's diagonal are counted on mismatch lines (two atomics
+    per sequencing error) instead of being listed one by one — same counts, and most of the leftover volume is gone."""
     r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[strain]), depth, 100 + strain)
     for b, o in ((r1, o1), (r2, o2)):
         want = oracle.Counts.count(21, b, o.astype(np.uint64), 3, 1000000, 2)
-        km, ct, st, dbg = sars_emul.count(b, o)
+        km, ct, st, dbg = sars_emul.count(b, o, dense=dense)
         wk, wc = want.get()
         assert st == want.stats()
         assert len(km) == len(wk) and (km == wk).all() and (ct.astype(np.uint64) == wc).all()
         assert dbg[1] < 0.2 * st[1]                     # most k-mers ride on runs, not the leftover path
+        if dense:
+            assert dbg[1] < 0.02 * st[1] and dbg[2] > 5 * dbg[1]       # ... and most of the rest on mismatch lines
 
 
 def test_counting_edge_cases(oracle, hpv_emul):
@@ -114,22 +119,36 @@ def test_counting_edge_cases(oracle, hpv_emul):
             g[1500:1560] + "ACGT" + g[1560:1700], "TTTTTTTTTT" + g[0:140], g[-140:] + "GGGGGGGGGG", rcg[0:150],
             "CCCCC" + rcg[-100:] + "AAAAA", g[3000:3800], g, g[2000:2021], g[2001:2022],
             "".join("ACGT"[i] for i in rng.integers(0, 4, size=300))]
+    # substitutions everywhere: next to the read ends, next to each other, runs of them, on both strands, as lower case / N
+    def sub(s, at, to=None):
+        s = list(s)
+        for p in at:
+            s[p] = to if to else "ACGT"[("ACGT".index(s[p].upper()) + 1) % 4]
+        return "".join(s)
+    r = g[4000:4150]
+    seqs += [sub(r, [0]), sub(r, [149]), sub(r, [20]), sub(r, [21]), sub(r, [129]), sub(r, [128]), sub(r, [70]), sub(r, [70, 71]),
+             sub(r, [70, 90]), sub(r, [70, 91]), sub(r, [70, 92]), sub(r, [10, 75, 140]), sub(r, [5, 6, 7, 8]), sub(r, [70], "n"),
+             sub(r, [70], "t" if r[70] != "T" else "a"), sub(r, [30, 60, 61, 100, 121]), sub(r, range(40, 49)),
+             sub(rcg[500:650], [0, 75, 149]), sub(g[0:150], [3, 30]), sub(g[-150:], [120, 147]), sub(g[5000:5040], [19]),
+             sub(g[5000:5041], [20]), sub(g[5000:5042], [0, 41])]
     for ci in (1, 2):
-        b, off = reads_from_strings(seqs * 2)
-        want = oracle.Counts.count(21, b, off.astype(np.uint64), ci, 1000000, 1)
-        km, ct, st, _ = hpv_emul.count(b, off, ci=ci)
-        wk, wc = want.get()
-        assert st == want.stats()
-        assert (km == wk).all() and (ct.astype(np.uint64) == wc).all()
+        for dense in (False, True):
+            b, off = reads_from_strings(seqs * 2)
+            want = oracle.Counts.count(21, b, off.astype(np.uint64), ci, 1000000, 1)
+            km, ct, st, _ = hpv_emul.count(b, off, ci=ci, dense=dense)
+            wk, wc = want.get()
+            assert st == want.stats()
+            assert (km == wk).all() and (ct.astype(np.uint64) == wc).all()
 
 
 def test_counting_with_full_leftover_queue(oracle, hpv_emul):
     """Queue overflow falls back to in-place counting: still exact."""
     r1, o1, _, _, _ = sim.simulate_pairs(sim.load_genome(sim.HPV16), 60, 7)
     want = oracle.Counts.count(21, r1, o1.astype(np.uint64), 3, 1000000, 1)
-    km, ct, st, _ = hpv_emul.count(r1, o1, desc_cap=8)
-    wk, wc = want.get()
-    assert st == want.stats() and (km == wk).all() and (ct.astype(np.uint64) == wc).all()
+    for dense in (False, True):
+        km, ct, st, _ = hpv_emul.count(r1, o1, desc_cap=8, dense=dense)
+        wk, wc = want.get()
+        assert st == want.stats() and (km == wk).all() and (ct.astype(np.uint64) == wc).all()
 
 
 def test_c_abi_exports_every_declared_symbol():
