@@ -324,15 +324,16 @@ def sharded_leg(args, rank, world, local_rank, owner_ctx, dist, torch):
             whole = bronko_b200.Bronko(local_rank)
             whole.share_index(owner_ctx)
             t0 = time.perf_counter()
-            whole.begin(cargs)
-            for c in range(n_chunks):
-                ch = chunks[c] if c in chunks else sim.simulate_pairs_torch(genome, chunk_pairs, seed_of(c), dev, plan)
-                push_chunk(whole, ch)
-                if c not in chunks:
-                    _sync_ctx(whole)               # the scan of this chunk is done: its buffers may go back to the allocator
-                    del ch
-            ref = whole.finish()
+            # every chunk of the sample resident on this GPU (the other ranks' chunks regenerated from their seeds)
+            allc = {c: (chunks[c] if c in chunks else sim.simulate_pairs_torch(genome, chunk_pairs, seed_of(c), dev, plan)) for c in range(n_chunks)}
+            torch.cuda.synchronize()               # the chunks are complete before the library's streams read them
+            for _ in range(2):                     # (the first run allocates)
+                whole.begin(cargs)
+                for c in range(n_chunks):
+                    push_chunk(whole, allc[c])
+                ref = whole.finish()
             unsharded_ms = whole.stage_times()["total_ms"]
+            del allc
             checks = {
                 "variants": ref.variants.tobytes() == res.variants.tobytes(),
                 "pileup": bool((ref.pileup() == res.pileup()).all()),
@@ -410,7 +411,9 @@ def main():
         import torch.distributed as dist_mod
         dist = dist_mod
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # (a rank that dies must not leave the others waiting for ever in a collective)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
     torch.cuda.set_device(local_rank)
 
     # S contexts per GPU keep S samples in flight: a sample's sequential tail (the exact noise chains run on

@@ -18,6 +18,7 @@
 
 #if defined(__CUDACC__)
 #define BK_HD __device__ __forceinline__
+#define BK_COLD __device__ __noinline__          /* rare paths: kept out of line so the hot loops stay small */
 #define BK_CLZLL(x) __clzll((long long)(x))
 #define BK_POPCLL(x) __popcll((unsigned long long)(x))
 #define BK_POPC(x) __popc((unsigned)(x))
@@ -29,6 +30,7 @@
 #define BK_PRMT(x, y, sel) __byte_perm((x), (y), (sel))
 #else
 #define BK_HD static inline
+#define BK_COLD static
 #define BK_CLZLL(x) __builtin_clzll((unsigned long long)(x))
 #define BK_POPCLL(x) __builtin_popcountll((unsigned long long)(x))
 #define BK_POPC(x) __builtin_popcount((unsigned)(x))
@@ -236,7 +238,7 @@ BK_HD u32 count_one(const CountView& v, u64 kmer) {
 // (k-mers that contain a non-ACGT byte are not counted: KMC splits reads there).  step/first let a
 // warp interleave lanes.  Returns the number of new novel keys.
 template <class Ld>
-BK_HD u32 count_stretch(const CountView& v, const Ld& ld, u32 byte_off, u32 cnt, u32 first, u32 step) {
+BK_COLD u32 count_stretch(const CountView& v, const Ld& ld, u32 byte_off, u32 cnt, u32 first, u32 step) {
     u32 created = 0;
     for (u32 j = first; j < cnt; j += step) {
         u64 km;

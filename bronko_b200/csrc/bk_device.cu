@@ -1139,6 +1139,10 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     BK_CUDA(cudaEventSynchronize(ctx->ev_end));          // blocking wait (BK_SPIN=1 spins): the host thread sleeps while the GPU works
     const Counters& c = *ctx->h_ctr;
     ctx->finished = true;
+    if (getenv("BK_DEBUG_COUNTS"))
+        for (int f = 0; f < n_files; f++)
+            fprintf(stderr, "[counts] file %d: reads %llu, leftover stretches (last push) %u, list entries %u, counted front %u + back %u, distinct %u, total k-mers %llu\n", f,
+                    (unsigned long long)ctx->file[f].total_reads, c.f[f].n_desc, c.f[f].nov_n, c.f[f].n_counted, c.f[f].n_dense, c.f[f].unique, (unsigned long long)c.f[f].total_kmers);
     if (c.gen_full) return ctx->fail(BK_ERR_OVERFLOW, "no room left for novel k-mers (list / bin table); set bk_params.table_log2 higher");
     if (c.var_overflow) return ctx->fail(BK_ERR_OVERFLOW, "variant buffer overflow");
     for (int f = 0; f < n_files; f++) {

@@ -38,7 +38,15 @@ typedef long long i64;
 #define BK_NOISE_TABLE 10
 #define BK_NZ_CHUNK 128          // iterations per speculative table chunk
 #define BK_NZ_WARM 256           // warm-up iterations in front of a chunk
-#define BK_NZ_ROUND 256          // iterations per chain round (= threads of the chain block)
+#ifndef BK_NZ_IPT
+#define BK_NZ_IPT 1              // iterations per thread and chain round
+#endif
+#define BK_NZ_OPT (6 * BK_NZ_IPT) // operations per thread and round
+#ifndef BK_NZ_SEQ_THREADS
+#define BK_NZ_SEQ_THREADS 256     // threads of a chain block (512: measured no faster — the round is bound by instruction issue, not latency)
+#endif
+#define BK_NZ_WARPS (BK_NZ_SEQ_THREADS / 32)
+#define BK_NZ_ROUND (BK_NZ_SEQ_THREADS * BK_NZ_IPT)   // iterations per chain round
 #define BK_NZ_TILE 1024          // iterations of fractions staged per shared-memory tile of a chain block
 #ifndef BK_NZ_SERIAL
 #define BK_NZ_SERIAL 8           // iterations executed serially per batch (after a stop, and for as long as the exponent keeps moving)
@@ -56,6 +64,7 @@ BK_HD double nz_mul(double a, double b) { return __dmul_rn(a, b); }
 BK_HD double nz_div(double a, double b) { return __ddiv_rn(a, b); }
 BK_HD double nz_sqrt(double a) { return __dsqrt_rn(a); }
 BK_HD double nz_abs(double a) { return fabs(a); }
+BK_HD long long nz_floor_ll(double a) { return __double2ll_rd(a); }
 #else
 }  // namespace bk
 #include <cmath>
@@ -69,6 +78,7 @@ BK_HD double nz_mul(double a, double b) { return a * b; }
 BK_HD double nz_div(double a, double b) { return a / b; }
 BK_HD double nz_sqrt(double a) { return std::sqrt(a); }
 BK_HD double nz_abs(double a) { return std::fabs(a); }
+BK_HD long long nz_floor_ll(double a) { return (long long)std::floor(a); }
 #endif
 
 // ---- fractions: src/call.rs:829-842.  counts sorted descending, "minor" = ranks 2..4 ------------------------
@@ -172,6 +182,112 @@ BK_HD void nz_compose(i64 g0, i64 g1, i64 f0, i64 f1, i64* h0, i64* h1) {
 }
 BK_HD bool nz_inside(i64 T) { return T > (1ll << 52) && T < (1ll << 53); }
 BK_HD double nz_value(u32 ef, i64 T) { return nz_d(((u64)ef << 52) | ((u64)T & BK_NZ_MASK52)); }
+
+// ---- chains across binade borders: three-zone rounds -------------------------------------------------------------
+// A sum that hovers at a power of two crosses it again and again (thin coverage: in nearly every iteration for tens to
+// hundreds of iterations), an iSNV entering the window doubles it — and a round that only knows one binade stops at
+// every crossing.  Three adjacent binades are therefore handled together, in units of the LOWEST one's ulp u: zone g
+// (g = 0, 1, 2) holds the multiples of G = 2^g in [2^(52+g), 2^(53+g)).  With X = x/u = A + f (A = floor, 0 <= f < 1,
+// both exact) and v = S + A, the IEEE result of S + x is v rounded to a multiple of G, G the zone v falls in:
+//     low = v mod G, w = v - low;   up  = low + f > G/2;   tie = low + f = G/2
+//     result = w + G * [up or (tie and w/G odd)]           (round to nearest, ties to even)
+// i.e. S + A + r with |r| <= 2, r depending on S only through S mod 8 — once the zone of the operation is known.  The
+// zone follows from the integer prefix sum of the A's: the roundings move the true S by at most two units per
+// operation, so S0 + (A's so far) decides unless it is within that drift of a zone border (then the operation ends the
+// accepted prefix and is executed in real FP64, like an operation that leaves the three zones).  Every operation is thus
+// a map "S mod 8 -> r", those maps compose associatively, and a round is two block-wide scans: the A's, then the maps.
+#define BK_NZ_ZONES 3
+#define BK_NZ_CLASSES 8
+struct NzZ2 { u32 el; double scale, xmax; };              // el = exponent field of the lowest zone
+BK_HD bool nz2_zones(u64 sb, NzZ2* z) {                    // false: s is zero / tiny / non-finite / negative → serial
+    const u32 ef = (u32)(sb >> 52);
+    if (ef < 66u || ef >= 0x7FCu) return false;
+    z->el = ef - 1;                                       // one binade of room below, one above
+    z->scale = nz_d((u64)(2098u - z->el) << 52);          // 1 / ulp(lowest zone)
+    z->xmax = nz_d((u64)(z->el + BK_NZ_ZONES) << 52);     // operands beyond the top of the zones cannot leave the sum inside them
+    return true;
+}
+BK_HD i64 nz2_start(const NzZ2& z, u64 sb) {
+    const i64 m = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
+    return m << ((u32)(sb >> 52) - z.el);
+}
+BK_HD bool nz2_split(const NzZ2& z, double x, i64* A, u32* fc) {
+    if (!(nz_abs(x) < z.xmax)) { *A = 0; *fc = 0; return false; }
+    const double X = nz_mul(x, z.scale);                  // exact: a power of two; |X| < 2^55
+    const i64 a = nz_floor_ll(X);
+    const double f = nz_sub(X, (double)a);                // exact, in [0, 1) (zero once |X| >= 2^52)
+    *A = a;
+    *fc = f == 0.0 ? 0u : (f < 0.5 ? 1u : (f == 0.5 ? 2u : 3u));
+    return true;
+}
+// r = result - (S + A) for S mod 8 = m before the operation, the operation's result in zone g: a function of
+// v = (S + A) mod 8 only, tabulated per (zone, fraction class) as eight signed bytes (nz2_round_slow is the formula the
+// table is generated from; tests/emul checks one against the other for all 96 cases).
+BK_HD i32 nz2_round_slow(u32 g, u32 fc, u32 v) {
+    if (g == 0) return (fc == 3u || (fc == 2u && (v & 1u))) ? 1 : 0;
+    const u32 G = 1u << g, low = v & (G - 1u), half = G >> 1;
+    const bool up = low > half || (low == half && fc != 0u);
+    const bool tie = low == half && fc == 0u;
+    const bool odd = ((v - low) >> g) & 1u;
+    return (i32)((up || (tie && odd)) ? G : 0u) - (i32)low;
+}
+BK_HD u64 nz2_round_table(u32 g, u32 fc) {                 // byte v = r for (S + A) mod 8 = v
+    if (g == 0) return fc == 3u ? 0x0101010101010101ull : (fc == 2u ? 0x0100010001000100ull : 0ull);
+    if (g == 1) return fc == 0u ? 0x0100FF000100FF00ull : 0x0100010001000100ull;
+    return fc == 0u ? 0x0102FF0001FEFF00ull : 0x0102FF000102FF00ull;
+}
+BK_HD bool nz2_inside(i64 T) { return T > (1ll << 52) && T < (1ll << (52 + BK_NZ_ZONES)); }
+BK_HD double nz2_value(const NzZ2& z, i64 T) {
+    const u32 g = T >= (1ll << 54) ? 2u : (T >= (1ll << 53) ? 1u : 0u);
+    return nz_d(((u64)(z.el + g) << 52) | (((u64)T >> g) & BK_NZ_MASK52));
+}
+// Eight classes side by side: a "class vector" holds one byte per start class m (two words: classes 0-3, 4-7).  Table
+// look-ups for all classes are byte permutes (PRMT: four look-ups into an eight-byte table per instruction).
+struct NzVec { u32 lo, hi; };
+BK_HD NzVec nzvec_identity() { NzVec v; v.lo = 0x03020100u; v.hi = 0x07060504u; return v; }
+BK_HD u32 nz_sel(u32 v) { const u32 t = v | (v >> 4); return (t & 0xFFu) | ((t >> 8) & 0xFF00u); }      // four bytes (each 0..7) → four selector nibbles
+BK_HD u32 nz_vadd4(u32 a, u32 b) { return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u); }   // byte-wise a + b
+BK_HD NzVec nzvec_lookup(u32 tlo, u32 thi, const NzVec& idx) {    // byte m = table[idx byte m]
+    NzVec r; r.lo = BK_PRMT(tlo, thi, nz_sel(idx.lo)); r.hi = BK_PRMT(tlo, thi, nz_sel(idx.hi)); return r;
+}
+BK_HD u32 nzvec_get(const NzVec& v, u32 m) { return ((m < 4 ? v.lo : v.hi) >> (8 * (m & 3u))) & 0xFFu; }
+BK_HD NzVec nzvec_compose(const NzVec& g, const NzVec& f) {       // transition maps: g first, then f
+    return nzvec_lookup(f.lo, f.hi, g);
+}
+// one thread's operations (BK_NZ_OPT: six per iteration) for all eight start classes at once: pr[q] = roundings up to and
+// including operation q (a signed byte per class), next = the class after them, and which operations cannot be decided
+// (bad = first such operation, BK_NZ_OPT = none).  s_est = S0 + (A's of the round before this thread), first_idx = operations
+// of the round before this thread.
+struct NzThread { NzVec pr[BK_NZ_OPT]; i64 a_pre[BK_NZ_OPT]; NzVec next; u32 bad; };
+BK_HD void nz2_thread(const i64* A, const u32* fc, const bool* ok, i64 s_est, u32 first_idx, NzThread* t) {
+    i64 run = 0;
+    NzVec cur = nzvec_identity(), tot; tot.lo = 0; tot.hi = 0;
+    t->bad = BK_NZ_OPT;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (u32 q = 0; q < BK_NZ_OPT; q++) {
+        const i64 v = s_est + run + A[q];                   // S + A without the roundings so far: off by at most `drift`
+        const i64 drift = 2ll * (i64)(first_idx + q);         // (|r| <= 2 per operation)
+        u32 g = 0; bool sure = true;
+        for (u32 b = 1; b < BK_NZ_ZONES; b++) {
+            const i64 E = v - (1ll << (52 + b));
+            if (E >= drift) g = b; else if (!(E < -drift)) sure = false;
+        }
+        if ((!sure || !ok[q]) && t->bad == BK_NZ_OPT) t->bad = q;
+        run += A[q];
+        t->a_pre[q] = run;
+        const u64 tab = nz2_round_table(g, fc[q]);
+        const u32 arep = ((u32)(u64)A[q] & 7u) * 0x01010101u;
+        NzVec vv; vv.lo = (cur.lo + arep) & 0x07070707u; vv.hi = (cur.hi + arep) & 0x07070707u;     // (S + A) mod 8 per class
+        const NzVec r = nzvec_lookup((u32)tab, (u32)(tab >> 32), vv);
+        tot.lo = nz_vadd4(tot.lo, r.lo); tot.hi = nz_vadd4(tot.hi, r.hi);
+        t->pr[q] = tot;
+        cur.lo = nz_vadd4(vv.lo, r.lo) & 0x07070707u; cur.hi = nz_vadd4(vv.hi, r.hi) & 0x07070707u;
+    }
+    t->next = cur;
+}
+BK_HD i32 nz2_pr(const NzVec& v, u32 m) { return (i32)(signed char)(unsigned char)nzvec_get(v, m); }
 
 // operation q (0..5) of iteration i: - old_j, + new_j for j = 0..2 (src/call.rs:845-895); M(p, j) = fraction j of position p
 template <bool SQUARE, class LdM>
@@ -309,7 +425,6 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
 }
 
 // ---- chain block: 256 threads, one iteration per thread and round ---------------------------------------------
-#define BK_NZ_SEQ_THREADS 256
 #define BK_NZ_CHAIN_SMEM ((BK_NZ_TILE + BK_NOISE_WINDOW) * 3 * 8)
 #define BK_NZ_TABLE_POS (BK_NOISE_WINDOW + BK_NZ_WARM + BK_NZ_CHUNK)          // positions a chunk lane touches
 #define BK_NZ_TABLE_WARPS 8                                                   // chunk lanes per table block
@@ -330,10 +445,18 @@ __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
 #define BK_NZ_PH_STORE do {} while (0)
 #endif
 
+__device__ __forceinline__ NzVec nzvec_shfl_up(const NzVec& f, int o) {
+    NzVec g;
+    g.lo = __shfl_up_sync(0xFFFFFFFFu, f.lo, o); g.hi = __shfl_up_sync(0xFFFFFFFFu, f.hi, o);
+    return g;
+}
+
 template <bool SQUARE>
 __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* mt) {
-    __shared__ i64 wt0[2][8], wt1[2][8];
-    __shared__ u32 wbad[2][8];
+    __shared__ i64 wsumA[2][BK_NZ_WARPS];
+    __shared__ u32 wnextL[2][BK_NZ_WARPS], wnextH[2][BK_NZ_WARPS];               // per warp: class transition of the whole warp
+    __shared__ i32 wsumR[2][BK_NZ_WARPS];                              // per warp: roundings of the whole warp
+    __shared__ u32 wbad[2][BK_NZ_WARPS];
     __shared__ double sstate[2];
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double* mafp = nv.maf + (size_t)(sq.mbase - BK_NZ_PAD_LO) * 3;       // position -100
@@ -361,89 +484,143 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         auto M = [mt, tl](i32 p, u32 j) { return mt[(u32)(p + BK_NOISE_WINDOW - (i32)tl) * 3 + j]; };
         const u32 n_it = min(width, tile_hi - i0);
         const u64 sb = nz_b(s);
-        const u32 ef = (u32)(sb >> 52);
-        if (ef < 64u || ef >= 0x7FFu || serial_left) {
-            // s is zero / subnormal / negative / non-finite, or rounds stopped making progress: like the reference
-            // A serial iteration costs ~1/30 of a round, and a sum that hovers at a binade border crosses it in
-            // nearly every iteration for tens to hundreds of iterations: stay serial for as long as the exponent
-            // keeps moving (a round would be stopped by its first operations again).
+        NzZ2 z;
+        if (sb == 0) {
+            // s is exactly zero (sparse coverage: the last positive fraction has left the window): every iteration whose six
+            // operands are zero leaves it there — find the first one that does not, all iterations of the round at once
+            u32 first = n_it;
+#pragma unroll
+            for (u32 j = 0; j < BK_NZ_IPT; j++) {
+                const u32 it = tid * BK_NZ_IPT + j;
+                if (it < n_it && first == n_it) {
+                    bool any = false;
+#pragma unroll
+                    for (u32 q = 0; q < 6; q++) any = any || nz_operand<SQUARE>(M, (i32)(i0 + it), q) != 0.0;
+                    if (any) first = it;
+                }
+            }
+            first = __reduce_min_sync(0xFFFFFFFFu, first);
+            const u32 zbuf = round & 1;
+            round++;
+            if (lane == 0) wbad[zbuf][wid] = first;
+            __syncthreads();
+#pragma unroll
+            for (u32 w = 0; w < BK_NZ_WARPS; w++) first = min(first, wbad[zbuf][w]);
+#pragma unroll
+            for (u32 j = 0; j < BK_NZ_IPT; j++) if (tid * BK_NZ_IPT + j < first) snap[i0 + tid * BK_NZ_IPT + j] = 0.0;
+            i0 += first;
+            if (first < n_it) {                              // the iteration that brings the sum back: like the reference
+#pragma unroll
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)i0, q));
+                if (tid == 0) snap[i0] = s;
+                i0++; st_serial++;
+            }
+            BK_NZ_PH(7);
+            continue;
+        }
+        if (!nz2_zones(sb, &z) || serial_left) {
+            // s is tiny / negative / non-finite, or the last round accepted next to nothing (operands as large as the sum
+            // one after the other): a few iterations like the reference, then rounds again
             const u32 n_ser = min(tile_hi - i0, (u32)BK_NZ_SERIAL);
-            bool moved = false;
             for (u32 it = 0; it < n_ser; it++) {
 #pragma unroll
-                for (u32 q = 0; q < 6; q++) { s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q)); moved = moved || (u32)(nz_b(s) >> 52) != ef; }
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
                 if (tid == 0) snap[i0 + it] = s;
             }
             i0 += n_ser; st_serial += n_ser;
-            serial_left = moved ? 1u : 0u;
+            serial_left = 0;
             BK_NZ_PH(7);
             continue;
         }
         const u32 buf = round & 1;
         round++; st_rounds++;
-        const NzBinade bin = nz_binade(ef);
-        const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
-        const bool active = tid < n_it;
-        i64 pre0[6], pre1[6];
-        i64 x0 = 0, x1 = 0;                                                      // exclusive prefix inside the warp
-        u32 bad = 6;
-        if (wid * 32 < n_it) {                                                   // warps without an iteration skip the work
-            i64 run0 = 0, run1 = 0;
+        const i64 S0 = nz2_start(z, sb);
+        const u32 it0 = tid * BK_NZ_IPT;                                         // this thread's first iteration of the round
+        i64 A[BK_NZ_OPT]; u32 fc[BK_NZ_OPT]; bool ok[BK_NZ_OPT];
+        i64 PA = 0, incl = 0;
+        const bool warp_on = wid * 32 * BK_NZ_IPT < n_it;                        // warps without an iteration skip the work
+        if (warp_on) {
 #pragma unroll
-            for (u32 q = 0; q < 6; q++) {
-                const double x = active ? nz_operand<SQUARE>(M, (i32)(i0 + tid), q) : 0.0;
-                i64 ie, io;
-                const bool ok = nz_incs(bin, x, &ie, &io);
-                run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
-                pre0[q] = run0; pre1[q] = run1;
-                if (!ok && bad == 6) bad = q;
+            for (u32 q = 0; q < BK_NZ_OPT; q++) {
+                const u32 it = it0 + q / 6;
+                const double x = it < n_it ? nz_operand<SQUARE>(M, (i32)(i0 + it), q % 6) : 0.0;
+                ok[q] = nz2_split(z, x, &A[q], &fc[q]);
+                PA += A[q];
             }
             BK_NZ_PH(1);
-            // inclusive scan of the parity maps over the warp
-            i64 f0 = run0, f1 = run1;
+            incl = PA;                                                           // scan 1: the A's
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const i64 g0 = __shfl_up_sync(0xFFFFFFFFu, f0, o), g1 = __shfl_up_sync(0xFFFFFFFFu, f1, o);
-                if (lane >= (u32)o) { i64 h0, h1; nz_compose(g0, g1, f0, f1, &h0, &h1); f0 = h0; f1 = h1; }
-            }
-            if (lane == 31) { wt0[buf][wid] = f0; wt1[buf][wid] = f1; }
-            x0 = __shfl_up_sync(0xFFFFFFFFu, f0, 1); x1 = __shfl_up_sync(0xFFFFFFFFu, f1, 1);
-            if (lane == 0) { x0 = 0; x1 = 0; }
+            for (int o = 1; o < 32; o <<= 1) { const i64 g = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += g; }
         } else {
 #pragma unroll
-            for (u32 q = 0; q < 6; q++) { pre0[q] = 0; pre1[q] = 0; }
-            if (lane == 31) { wt0[buf][wid] = 0; wt1[buf][wid] = 0; }
+            for (u32 q = 0; q < BK_NZ_OPT; q++) { A[q] = 0; fc[q] = 0; ok[q] = true; }
         }
+        if (lane == 31) wsumA[buf][wid] = incl;
         BK_NZ_PH(2);
         __syncthreads();
-        i64 base = S0;
-        for (u32 w = 0; w < wid; w++) base += (base & 1) ? wt1[buf][w] : wt0[buf][w];
-        base += (base & 1) ? x1 : x0;
-        BK_NZ_PH(3);
-        const bool odd = (base & 1) != 0;
-        i64 T[6];
+        i64 Pex = incl - PA;
 #pragma unroll
-        for (u32 q = 0; q < 6; q++) {
-            T[q] = base + (odd ? pre1[q] : pre0[q]);
-            if (!nz_inside(T[q]) && bad > q) bad = q;
+        for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { const i64 v = wsumA[buf][w]; if (w < wid) Pex += v; }      // (unrolled: the loads issue together)
+        NzThread T;
+        NzVec f = nzvec_identity();
+        NzVec ex = f;
+        if (warp_on) {
+            nz2_thread(A, fc, ok, S0 + Pex, tid * BK_NZ_OPT, &T);
+            f = T.next;                                                          // scan 2: the class transitions
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const NzVec g = nzvec_shfl_up(f, o); if (lane >= (u32)o) f = nzvec_compose(g, f); }
+            ex = nzvec_shfl_up(f, 1);
+            if (lane == 0) ex = nzvec_identity();
+        } else {
+            T.bad = BK_NZ_OPT;
+#pragma unroll
+            for (u32 q = 0; q < BK_NZ_OPT; q++) { T.pr[q].lo = 0; T.pr[q].hi = 0; T.a_pre[q] = 0; }
+        }
+        if (lane == 31) { wnextL[buf][wid] = f.lo; wnextH[buf][wid] = f.hi; }
+        BK_NZ_PH(3);
+        __syncthreads();
+        // the class in front of this thread: the transitions of the warps before it and of the lanes before it, applied
+        // to the start class one after the other
+        u32 cs = (u32)(u64)S0 & 7u;                                              // S mod 8
+#pragma unroll
+        for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { NzVec g; g.lo = wnextL[buf][w]; g.hi = wnextH[buf][w]; if (w < wid) cs = nzvec_get(g, cs); }
+        cs = nzvec_get(ex, cs);
+        // scan 3: the roundings, now that every thread knows the class it starts from
+        const i32 rt = nz2_pr(T.pr[BK_NZ_OPT - 1], cs);
+        i32 rincl = rt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const i32 g = __shfl_up_sync(0xFFFFFFFFu, rincl, o); if (lane >= (u32)o) rincl += g; }
+        if (lane == 31) wsumR[buf][wid] = rincl;
+        __syncthreads();
+        i32 Rex = rincl - rt;
+#pragma unroll
+        for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { const i32 v = wsumR[buf][w]; if (w < wid) Rex += v; }
+        i64 Tq[BK_NZ_OPT];
+        u32 bad = T.bad;
+#pragma unroll
+        for (u32 q = 0; q < BK_NZ_OPT; q++) {
+            Tq[q] = S0 + Pex + T.a_pre[q] + (i64)Rex + (i64)nz2_pr(T.pr[q], cs);
+            if (!nz2_inside(Tq[q]) && bad > q) bad = q;
         }
         const u32 total_ops = n_it * 6;
-        u32 mine = (active && bad < 6) ? tid * 6 + bad : total_ops;
+        u32 mine = bad < BK_NZ_OPT ? min(tid * BK_NZ_OPT + bad, total_ops) : total_ops;     // (operations past the round's end are zeros)
         mine = __reduce_min_sync(0xFFFFFFFFu, mine);
         if (lane == 0) wbad[buf][wid] = mine;
         __syncthreads();
         BK_NZ_PH(4);
         u32 n_ok = total_ops;
 #pragma unroll
-        for (u32 w = 0; w < 8; w++) n_ok = min(n_ok, wbad[buf][w]);
-        if (active && tid * 6 + 5 < n_ok) snap[i0 + tid] = nz_value(ef, T[5]);
-        if (n_ok > 0) {
-            const u32 owner = (n_ok - 1) / 6, oq = (n_ok - 1) - owner * 6;
-            if (tid == owner) {
-                i64 Tl = T[0];
+        for (u32 w = 0; w < BK_NZ_WARPS; w++) n_ok = min(n_ok, wbad[buf][w]);
 #pragma unroll
-                for (u32 q = 1; q < 6; q++) if (q == oq) Tl = T[q];
-                sstate[buf] = nz_value(ef, Tl);
+        for (u32 j = 0; j < BK_NZ_IPT; j++)                                      // iterations whose six operations were all accepted
+            if (it0 + j < n_it && (it0 + j) * 6 + 5 < n_ok) snap[i0 + it0 + j] = nz2_value(z, Tq[j * 6 + 5]);
+        if (n_ok > 0) {
+            const u32 owner = (n_ok - 1) / BK_NZ_OPT, oq = (n_ok - 1) - owner * BK_NZ_OPT;
+            if (tid == owner) {
+                i64 Tl = Tq[0];
+#pragma unroll
+                for (u32 q = 1; q < BK_NZ_OPT; q++) if (q == oq) Tl = Tq[q];
+                sstate[buf] = nz2_value(z, Tl);
             }
         }
         __syncthreads();
@@ -456,7 +633,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         if (tid == 0) snap[i0 + ib] = s;
         i0 += ib + 1;
-        serial_left = 1;                               // stops come in bursts (the sum hovers at a binade border)
+        serial_left = ib < 24 ? 1u : 0u;               // (a round costs about as much as 25 serial iterations)
         BK_NZ_PH(6);
     }
     BK_NZ_PH_STORE;

@@ -2,6 +2,8 @@
 // CUDA kernels are built from) on the CPU, single-threaded, so that seed/extend/run/leftover/fold
 // logic can be checked against the oracle in the `-m "not gpu"` suite.  Not part of libbronko_b200.so.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -245,62 +247,88 @@ void emul_count_get(void* h, u64* kmers, u32* counts) {
 }  // extern "C"
 template <bool SQUARE, class LdM>
 static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
+    // the two-zone rounds of bk_noise.cuh: nz_chain_block, stepped in thread order (the block-wide scans of the device are
+    // replaced by sequential sums / compositions of the same primitives: both are associative)
     double s = 0.0;
     u32 i0 = 0, serial_left = 0;
     const u32 width = BK_NZ_ROUND;
     while (i0 < iters) {
         const u32 n_it = std::min<u32>(width, iters - i0);
         const u64 sb = nz_b(s);
-        const u32 ef = (u32)(sb >> 52);
-        if (ef < 64u || ef >= 0x7FFu || serial_left) {
+        NzZ2 z;
+        if (sb == 0) {                                       // the zero skip of nz_chain_block
+            u32 first = n_it;
+            for (u32 t = 0; t < n_it && first == n_it; t++)
+                for (u32 q = 0; q < 6; q++) if (nz_operand<SQUARE>(M, (i32)(i0 + t), q) != 0.0) { first = t; break; }
+            for (u32 t = 0; t < first; t++) snap[i0 + t] = 0.0;
+            i0 += first;
+            if (first < n_it) {
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)i0, q));
+                snap[i0] = s;
+                i0++; stats[4]++;
+            }
+            continue;
+        }
+        if (!nz2_zones(sb, &z) || serial_left) {
             const u32 n_ser = std::min<u32>(iters - i0, BK_NZ_SERIAL);
-            bool moved = false;
             for (u32 it = 0; it < n_ser; it++) {
-                for (u32 q = 0; q < 6; q++) { s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q)); moved = moved || (u32)(nz_b(s) >> 52) != ef; }
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
                 snap[i0 + it] = s;
             }
-            i0 += n_ser; stats[4] += n_ser; serial_left = moved ? 1 : 0;
+            i0 += n_ser; stats[4] += n_ser; serial_left = 0;
             continue;
         }
         stats[2]++;
-        const NzBinade bin = nz_binade(ef);
-        const i64 S0 = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
-        std::vector<i64> pre0(n_it * 6), pre1(n_it * 6), f0(n_it), f1(n_it);
-        std::vector<u32> bad(n_it, 6);
-        for (u32 t = 0; t < n_it; t++) {
-            i64 run0 = 0, run1 = 0;
-            for (u32 q = 0; q < 6; q++) {
-                i64 ie, io;
-                const bool ok = nz_incs(bin, nz_operand<SQUARE>(M, (i32)(i0 + t), q), &ie, &io);
-                run0 = nz_apply(ie, io, run0, 0); run1 = nz_apply(ie, io, run1, 1);
-                pre0[t * 6 + q] = run0; pre1[t * 6 + q] = run1;
-                if (!ok && bad[t] == 6) bad[t] = q;
+        const i64 S0 = nz2_start(z, sb);
+        const u32 n_thr = (n_it + BK_NZ_IPT - 1) / BK_NZ_IPT;    // threads with an iteration (thread t: iterations t * IPT ..)
+        std::vector<NzThread> T(n_thr);
+        std::vector<i64> Pex(n_thr);
+        i64 run = 0;
+        for (u32 t = 0; t < n_thr; t++) {                    // scan 1 + the thread maps
+            i64 A[BK_NZ_OPT]; u32 fc[BK_NZ_OPT]; bool ok[BK_NZ_OPT]; i64 PA = 0;
+            for (u32 q = 0; q < BK_NZ_OPT; q++) {
+                const u32 it = t * BK_NZ_IPT + q / 6;
+                const double x = it < n_it ? nz_operand<SQUARE>(M, (i32)(i0 + it), q % 6) : 0.0;
+                ok[q] = nz2_split(z, x, &A[q], &fc[q]); PA += A[q];
             }
-            f0[t] = run0; f1[t] = run1;
+            Pex[t] = run;
+            nz2_thread(A, fc, ok, S0 + run, t * BK_NZ_OPT, &T[t]);
+            run += PA;
         }
-        // exclusive composition in thread order (what the warp scan + warp totals compute)
-        i64 g0 = 0, g1 = 0;
+        for (u32 g = 0; g < 3; g++) for (u32 fcc = 0; fcc < 4; fcc++) for (u32 v = 0; v < 8; v++)      // the table against its formula
+            if ((i32)(signed char)(unsigned char)(nz2_round_table(g, fcc) >> (8 * v)) != nz2_round_slow(g, fcc, v)) { stats[0] = 0xBAD; return; }
+        u32 cs = (u32)(u64)S0 & 7u;                          // scans 2 + 3 in thread order: class and roundings in front of every thread
+        i64 Rex = 0;
+        NzVec composed = nzvec_identity();                   // (and the composition of the transitions, as the device's warp scan builds it)
         u32 n_ok = n_it * 6;
-        std::vector<i64> T(n_it * 6);
-        for (u32 t = 0; t < n_it; t++) {
-            i64 base = S0 + ((S0 & 1) ? g1 : g0);
-            const bool odd = (base & 1) != 0;
-            for (u32 q = 0; q < 6; q++) {
-                T[t * 6 + q] = base + (odd ? pre1[t * 6 + q] : pre0[t * 6 + q]);
-                if (!nz_inside(T[t * 6 + q]) && bad[t] > q) bad[t] = q;
+        std::vector<i64> Tq((size_t)n_thr * BK_NZ_OPT);
+        for (u32 t = 0; t < n_thr; t++) {
+            if (nzvec_get(composed, (u32)(u64)S0 & 7u) != cs) { stats[0] = 0xBAD; return; }
+            u32 bad = T[t].bad;
+            for (u32 q = 0; q < BK_NZ_OPT; q++) {
+                Tq[t * BK_NZ_OPT + q] = S0 + Pex[t] + T[t].a_pre[q] + Rex + (i64)nz2_pr(T[t].pr[q], cs);
+                if (!nz2_inside(Tq[t * BK_NZ_OPT + q]) && bad > q) bad = q;
             }
-            if (bad[t] < 6) n_ok = std::min(n_ok, t * 6 + bad[t]);
-            i64 h0, h1; nz_compose(g0, g1, f0[t], f1[t], &h0, &h1); g0 = h0; g1 = h1;
+            if (bad < BK_NZ_OPT) n_ok = std::min(n_ok, t * BK_NZ_OPT + bad);
+            Rex += nz2_pr(T[t].pr[BK_NZ_OPT - 1], cs);
+            cs = nzvec_get(T[t].next, cs);
+            composed = nzvec_compose(composed, T[t].next);
         }
-        for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz_value(ef, T[t * 6 + 5]);
-        if (n_ok > 0) s = nz_value(ef, T[n_ok - 1]);
+        for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz2_value(z, Tq[t * 6 + 5]);
+        if (n_ok > 0) s = nz2_value(z, Tq[n_ok - 1]);
         if (n_ok == n_it * 6) { i0 += n_it; continue; }
         stats[3]++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
+        if (getenv("EMUL_DEBUG")) {
+            const double x = nz_operand<SQUARE>(M, (i32)(i0 + ib), qb);
+            i64 A; u32 fc; const bool ok = nz2_split(z, x, &A, &fc);
+            fprintf(stderr, "[stop] sq=%d i=%u op=%u accepted=%u s=%.6g x=%.6g ok=%d el=%u T=%lld (2^53=%lld) threadbad=%u\n", (int)SQUARE, i0 + ib, qb, n_ok, s, x, (int)ok, z.el,
+                    (long long)Tq[n_ok], (long long)(1ll << 53), T[ib].bad);
+        }
         for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
         snap[i0 + ib] = s;
         i0 += ib + 1;
-        serial_left = 1;
+        serial_left = ib < 24 ? 1 : 0;
     }
 }
 
