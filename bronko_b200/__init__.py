@@ -4,7 +4,7 @@ The product is bronko_b200/csrc (CUDA kernels + C ABI, include/bronko_b200.h); t
 Python mirror of the reference's seam on top of that ABI.  There is no CPU path: importing works
 anywhere, creating a context requires the compiled library and a B200.
 """
-from .api import Bronko, CallArgs, DecodedReads, Sample, clean_sample_id  # noqa: F401
+from .api import Bronko, CallArgs, DecodedReads, Sample, clean_sample_id, pack_reads  # noqa: F401
 from ._lib import BkError  # noqa: F401
 
 __version__ = "0.1.0"

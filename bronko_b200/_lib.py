@@ -82,6 +82,8 @@ SIGNATURES = {
     "bk_sample_begin": (C.c_int, [P, C.POINTER(Params)]),
     "bk_reads_push": (C.c_int, [P, C.c_int, P, P, u64]),
     "bk_reads_push_device": (C.c_int, [P, C.c_int, P, P, u64, u64, u32]),
+    "bk_reads_push_packed": (C.c_int, [P, C.c_int, P, P, u64]),
+    "bk_reads_pack": (C.c_int, [P, P, u64, P, P, P, P, P, P]),
     "bk_reads_push_fastq": (C.c_int, [P, C.c_int, C.c_char_p]),
     "bk_reads_push_fastq_mem": (C.c_int, [P, C.c_int, P, u64]),
     "bk_decode_info_get": (C.c_int, [P, C.c_int, C.POINTER(DecodeInfo)]),

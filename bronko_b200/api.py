@@ -53,6 +53,24 @@ class CallArgs:
         return p
 
 
+def pack_reads(bases, read_off):
+    """bk_reads_pack: (packed u32 words, packed offsets u32, rest bases u8, rest offsets u32) — the packable reads of a
+    chunk as 2-bit words and the others as ASCII (for Bronko.push_packed_ptr / push)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint32)
+    n = len(read_off) - 1
+    nb = int(read_off[-1]) if n else 0
+    packed = np.zeros(nb // 16 + 2, dtype=np.uint32)
+    poff = np.zeros(n + 1, dtype=np.uint32)
+    rest = np.full(nb + 64, ord("*"), dtype=np.uint8)
+    roff = np.zeros(n + 1, dtype=np.uint32)
+    npk, nrs = C.c_uint64(), C.c_uint64()
+    rc = L.lib().bk_reads_pack(L.ptr(bases), L.ptr(read_off), n, L.ptr(packed), L.ptr(poff), C.byref(npk), L.ptr(rest), L.ptr(roff), C.byref(nrs))
+    if rc != 0:
+        raise BkError(rc, "bk_reads_pack")
+    return packed, poff[:npk.value + 1].copy(), rest, roff[:nrs.value + 1].copy()
+
+
 def clean_sample_id(path):
     buf = C.create_string_buffer(4096)
     L.lib().bk_clean_sample_id(path.encode(), buf, 4096)
@@ -197,6 +215,9 @@ class Bronko:
 
     def push_fastq(self, file_slot, path):
         self._check(self._lib.bk_reads_push_fastq(self.h, file_slot, path.encode()))
+
+    def push_packed_ptr(self, file_slot, packed_ptr, off_ptr, n_reads):
+        self._check(self._lib.bk_reads_push_packed(self.h, file_slot, packed_ptr, off_ptr, n_reads))
 
     def push_fastq_mem(self, file_slot, data):
         """The bytes of a FASTQ(.gz) file (bytes / numpy uint8): inflated (BGZF: by the GPU's decompression engine) and

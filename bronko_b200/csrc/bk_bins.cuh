@@ -56,6 +56,7 @@ struct BinView {
     // mismatch lines (bk_dense.cuh; null = off): (j << 58 | k-mer without digit j) → id of the reference k-mer that equals
     // the k-mer everywhere but at digit j; a distinct k-mer of the list that is the string of an unambiguous cell joins it
     const ExactSlotD* nb; u32 nb_shift, nb_mask; u32 k;
+    const u32* nb_bloom; u32 nb_bloom_shift;             // one bit per key of nb (a 2 MB bit set that stays in L2): most k-mers of the list have no neighbour at all
     const u32* id_amb; const u32* id_rep; u32* dense; u8* dense_flag;
 };
 
@@ -248,20 +249,20 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                     bool done = false;
 #pragma unroll 1
                     for (u32 j0 = 0; j0 < b.k && !done; j0 += 7) {
-                        u64 key[7]; u32 hs[7]; ExactSlotD sl[7];
+                        u64 key[7]; u32 bw[7]; u32 bb[7];
 #pragma unroll
-                        for (u32 t = 0; t < 7; t++) {
+                        for (u32 t = 0; t < 7; t++) {                          // the bit set first: seven independent loads that hit L2
                             const u32 jj = min(j0 + t, b.k - 1);
                             key[t] = ((u64)jj << 58) | (K & ~(3ull << (2 * (b.k - 1 - jj))));
-                            hs[t] = hash_slot(key[t], b.nb_shift);
-                            sl[t] = load_exact(b.nb + hs[t]);
+                            bb[t] = hash_slot(key[t], b.nb_bloom_shift);
+                            bw[t] = __ldg(b.nb_bloom + (bb[t] >> 5));
                         }
 #pragma unroll
                         for (u32 t = 0; t < 7; t++) {
                             const u32 jj = j0 + t;
-                            if (jj >= b.k || done) continue;
-                            u32 h = hs[t];
-                            ExactSlotD s1 = sl[t];
+                            if (jj >= b.k || done || !((bw[t] >> (bb[t] & 31u)) & 1u)) continue;
+                            u32 h = hash_slot(key[t], b.nb_shift);
+                            ExactSlotD s1 = load_exact(b.nb + h);
                             while (s1.key != key[t] && s1.key != BK_EMPTY) { h = (h + 1) & b.nb_mask; s1 = load_exact(b.nb + h); }
                             if (s1.key != key[t]) continue;
                             done = true;                                       // a neighbour: if it is ambiguous every neighbour is, the k-mer stays here

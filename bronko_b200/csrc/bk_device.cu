@@ -94,7 +94,7 @@ struct IndexDev {
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
     DevBuf<u32> d_slot2rep, d_id_amb, d_id_rep; DevBuf<ExactSlotD> d_nb;       // mismatch lines (bk_dense.cuh); empty when !d.dense_ok
-    DevBuf<u32> d_line_amb, d_line_fold;
+    DevBuf<u32> d_line_amb, d_line_fold, d_nb_bloom;
     DevBuf<uint2> d_id_bucket;                                                   // map shortcut (bk_host.h); empty when !d.map_shortcut_ok
     DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
     u32 max_seqs_per_genome = 1;
@@ -103,7 +103,7 @@ struct IndexDev {
         d_bucket_slots.release(); d_bucket_entries.release(); d_group_slots.release(); d_group_centers.release(); d_group_buckets.release(); d_refnib.release(); d_oseq_start.release(); d_oseq_len.release();
         d_exact.release(); d_slot2id.release(); d_id_kmer.release(); d_genome_row0.release(); d_genome_seq_off.release();
         d_seq_row0.release(); d_genome_len.release(); d_ref_code.release();
-        d_slot2rep.release(); d_id_amb.release(); d_id_rep.release(); d_nb.release(); d_id_bucket.release(); d_line_amb.release(); d_line_fold.release();
+        d_slot2rep.release(); d_id_amb.release(); d_id_rep.release(); d_nb.release(); d_id_bucket.release(); d_line_amb.release(); d_line_fold.release(); d_nb_bloom.release();
     }
 };
 
@@ -406,6 +406,7 @@ static int upload_index(bk_ctx* ctx, std::shared_ptr<IndexDev> fresh) {
         BK_CUDA(ctx->I->d_id_rep.upload(d.id_rep, st));
         BK_CUDA(ctx->I->d_line_amb.upload(d.line_amb, st));
         BK_CUDA(ctx->I->d_line_fold.upload(d.line_fold, st));
+        BK_CUDA(ctx->I->d_nb_bloom.upload(d.nb_bloom, st));
         BK_CUDA(ctx->I->d_nb.reserve(d.nb_slots.size()));
         BK_CUDA(cudaMemcpyAsync(ctx->I->d_nb.p, d.nb_slots.data(), d.nb_slots.size() * 16, cudaMemcpyHostToDevice, st));
         if (d.map_shortcut_ok) {
@@ -875,6 +876,7 @@ static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted,
     b.k = d.k;
     if (d.dense_ok) {
         b.nb = ctx->I->d_nb.p; b.nb_shift = 64 - d.nb_log2; b.nb_mask = (1u << d.nb_log2) - 1;
+        b.nb_bloom = ctx->I->d_nb_bloom.p; b.nb_bloom_shift = 64 - d.nb_bloom_log2;
         b.id_amb = ctx->I->d_id_amb.p; b.id_rep = ctx->I->d_id_rep.p; b.dense = f.dense.p; b.dense_flag = f.dflag.p;
     }
     k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);

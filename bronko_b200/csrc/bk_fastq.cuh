@@ -119,6 +119,23 @@ __global__ void __launch_bounds__(256) k_fq_gather(const u8* __restrict__ txt, c
 // followed by an empty read).
 __global__ void k_fq_terminate(u8* txt, u32 n) { txt[n] = (n == 0 || txt[n - 1] == '\n') ? (u8)'@' : (u8)'\n'; }
 
+// 2-bit packed reads (bk_reads_push_packed) → the ASCII bytes the scan kernel streams: one thread per packed word
+// (16 bases), one 16-byte store.  Base i of the push sits at bits 2 * (i % 16) of word i / 16, code A0 C1 G2 T3.
+__global__ void __launch_bounds__(256) k_unpack2(const u32* __restrict__ packed, u64 n_words, u8* __restrict__ bases) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const u32 w = __ldg(packed + i);
+        u32 o[4];
+#pragma unroll
+        for (u32 j = 0; j < 4; j++) {
+            const u32 x = (w >> (8 * j)) & 0xFFu;                                  // four codes
+            const u32 sel = (x & 3u) | ((x & 0xCu) << 2) | ((x & 0x30u) << 4) | ((x & 0xC0u) << 6);
+            o[j] = __byte_perm(0x54474341u, 0u, sel);                             // "ACGT"[code]
+        }
+        reinterpret_cast<uint4*>(bases)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // after a batch of engine inflates: every member must have produced the size its trailer announced
 __global__ void __launch_bounds__(256) k_fq_check_sizes(const u32* __restrict__ got, const u32* __restrict__ want, u32 n, u32* bad) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (got[i] != want[i]) atomicAdd(bad, 1u);

@@ -122,6 +122,8 @@ struct DerivedIndex {
     std::vector<u32> id_amb;                 // per id: bit j set = cells (id, j, *) are ambiguous
     u32 nb_log2 = 0;
     std::vector<ExactSlot> nb_slots;         // key, gidx = id (oseq unused); key == ~0 → empty
+    u32 nb_bloom_log2 = 0;
+    std::vector<u32> nb_bloom;               // one bit per hash_slot(key, 64 - nb_bloom_log2) of a key present in nb_slots: ~8 bits per key, stays in L2
     // Map shortcut (rekeyed tables only).  The k-mer of an unambiguous cell (id, j, b) is within one digit of exactly one
     // reference k-mer — id's — so map_kmers can hit one bucket at most: index j of id's canonical form, and only if
     // replacing the digit does not flip which strand of the k-mer is canonical (bit 31 of id_amb[id]: id's k-mer is

@@ -179,6 +179,17 @@ int bk_reads_push(bk_ctx* ctx, int file_slot, const uint8_t* bases, const uint32
 int bk_reads_push_device(bk_ctx* ctx, int file_slot, const uint8_t* d_bases,
                          const uint32_t* d_read_off, uint64_t n_reads, uint64_t n_bases,
                          uint32_t max_read_len);
+/* 2-bit packed reads — a quarter of the bytes across PCIe, which is what bounds a sample pushed from host memory (the
+ * GPU path runs ~6x faster than 16 PCIe Gen5 lanes deliver ASCII).  packed: 16 bases per u32, base i of the push at
+ * bits 2 * (i % 16) of word i / 16, codes A0 C1 G2 T3; reads contiguous in base space, read r = bases
+ * [read_off[r], read_off[r + 1]).  Only reads made of ACGT / acgt can be packed (KMC counts lower case like upper case
+ * and splits reads at any other byte): bk_reads_pack — a host helper of the decode stage — splits a chunk into its
+ * packable reads and the rest, which goes through bk_reads_push as ASCII.  Counting does not depend on the order of the
+ * reads, so the two pushes together equal the ASCII push of the chunk.  Buffers of bk_reads_pack are the caller's:
+ * packed >= n_bases / 16 + 2 words, packed_off and rest_off >= n_reads + 1 entries, rest_bases >= n_bases + 64 bytes. */
+int bk_reads_push_packed(bk_ctx* ctx, int file_slot, const uint32_t* packed, const uint32_t* read_off, uint64_t n_reads);
+int bk_reads_pack(const uint8_t* bases, const uint32_t* read_off, uint64_t n_reads, uint32_t* packed, uint32_t* packed_off,
+                  uint64_t* n_packed, uint8_t* rest_bases, uint32_t* rest_off, uint64_t* n_rest);
 /* A FASTQ(.gz) file (KMC reader contract) decoded ON THE DEVICE and pushed: the host only moves
  * bytes.  BGZF files (bgzip / htslib: independent <= 64 KiB gzip members) are inflated by the B200's hardware
  * decompression engine; other gzip files by zlib on the host (a single deflate stream cannot be split); the text is

@@ -27,6 +27,7 @@ class FakeBronko:
     def begin(self, args=None): pass
     def push_device(self, *a): pass
     def push_ptr(self, *a): pass
+    def push_packed_ptr(self, *a): pass
     def close(self): pass
 
     def finish(self):

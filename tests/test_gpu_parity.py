@@ -462,3 +462,30 @@ def test_decoded_fastq_push_matches_host_push(ctx_sars, tmp_path):
     c.push_fastq(0, f1)
     c.push_fastq(1, f2)
     assert_snapshots_equal(base, snapshot(c.finish(), 2))
+
+
+def test_packed_push_equals_ascii_push(ctx_sars):
+    """bk_reads_push_packed + the ASCII push of the reads that cannot be packed = the ASCII push of everything: a sample
+    with N / junk / lower-case reads mixed in, R1 packed in two chunks, R2 as ASCII."""
+    import bronko_b200
+    from bronko_b200 import _lib as L
+    from util import assert_sample_equal, oracle_sample
+    c, oi = ctx_sars
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[2]), 500, sim.SEED0 + 49)
+    r1 = r1.copy()
+    rng = np.random.default_rng(3)
+    for r in rng.integers(0, len(o1) - 1, size=300):                 # N's, junk and lower case into ~300 reads
+        p = int(o1[r]) + int(rng.integers(0, 150))
+        r1[p] = [ord("N"), ord("*"), r1[p] | 0x20][int(rng.integers(0, 3))]
+    args = bronko_b200.CallArgs()
+    counts, osample = oracle_sample(oi, [(r1, o1), (r2, o2)], args)
+    half = (len(o1) - 1) // 2
+    c.begin(args)
+    for lo, hi in ((0, half), (half, len(o1) - 1)):
+        b0, b1 = int(o1[lo]), int(o1[hi])
+        packed, poff, rest, roff = bronko_b200.pack_reads(r1[b0:b1], (o1[lo:hi + 1].astype(np.int64) - b0).astype(np.uint32))
+        assert len(roff) - 1 > 0 and len(poff) - 1 > 0
+        c.push_packed_ptr(0, L.ptr(packed), L.ptr(poff), len(poff) - 1)
+        c.push(0, rest, roff)
+    c.push(1, r2, o2)
+    assert_sample_equal(c.finish(), counts, osample)

@@ -247,3 +247,27 @@ def test_multi_genome_db_roundtrip_through_bkdb(oracle, sars_emul, sars_paths, t
     assert (perm[0] == want[0]).all() and perm[2].tobytes() != want[2].tobytes()
     want_perm = oracle.Index.build(21, sars_paths[::-1]).export()
     assert (perm[1] == want_perm[1]).all() and perm[2].tobytes() == want_perm[2].tobytes()
+
+
+def test_reads_pack_splits_clean_and_dirty_reads():
+    """bk_reads_pack (host helper of the decode stage): reads of ACGT / acgt only become one continuous 2-bit stream
+    (16 bases per u32, base i at bits 2 * (i % 16)), every other read is passed on as ASCII, order kept on both sides."""
+    import bronko_b200
+    from util import reads_from_strings
+    rng = np.random.default_rng(11)
+    seqs = ["".join("ACGT"[i] for i in rng.integers(0, 4, size=int(n))) for n in rng.integers(0, 200, size=60)]
+    seqs[3] = seqs[3][:10] + "N" + seqs[3][10:]
+    seqs[7] = seqs[7].lower()
+    seqs[11] = "ACGT*ACGT"
+    seqs[12] = ""
+    seqs[40] = seqs[40][:5] + "n" + seqs[40][5:]
+    b, off = reads_from_strings(seqs)
+    packed, poff, rest, roff = bronko_b200.pack_reads(b, off)
+    dirty = [s_ for s_ in seqs if set(s_) - set("ACGTacgt")]
+    clean = [s_ for s_ in seqs if not (set(s_) - set("ACGTacgt"))]
+    assert len(poff) - 1 == len(clean) and len(roff) - 1 == len(dirty)
+    assert [rest[roff[i]:roff[i + 1]].tobytes().decode() for i in range(len(dirty))] == dirty
+    total = int(poff[-1])
+    codes = np.array([(int(packed[i // 16]) >> (2 * (i % 16))) & 3 for i in range(total)], dtype=np.uint8)
+    got = ["".join("ACGT"[c] for c in codes[poff[i]:poff[i + 1]]) for i in range(len(clean))]
+    assert got == [s_.upper() for s_ in clean]
