@@ -41,6 +41,10 @@ namespace bk {
 #define BK_OWNER_UNITS_LOG2 6                // owner ranks split the hash space in 64 units (a bin never straddles one: P >= 64)
 
 __device__ __forceinline__ u64 bin_hash(u64 x) { return (x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull; }
+__device__ __forceinline__ u64 bloom_mask_dev(u64 h, u32 log2w) {            // bk_host.h: bloom_mask
+    const u64 r = h >> (64 - log2w - 18);
+    return (1ull << (r & 63)) | (1ull << ((r >> 6) & 63)) | (1ull << ((r >> 12) & 63));
+}
 // first hash unit (of 64) owned by rank r of n: r owns units [unit_lo(r), unit_lo(r + 1))
 __host__ __device__ __forceinline__ u32 owner_unit_lo(u32 r, u32 n) { return (r * (1u << BK_OWNER_UNITS_LOG2) + n - 1) / n; }
 
@@ -56,7 +60,7 @@ struct BinView {
     // mismatch lines (bk_dense.cuh; null = off): (j << 58 | k-mer without digit j) → id of the reference k-mer that equals
     // the k-mer everywhere but at digit j; a distinct k-mer of the list that is the string of an unambiguous cell joins it
     const ExactSlotD* nb; u32 nb_shift, nb_mask; u32 k;
-    const u32* nb_bloom; u32 nb_bloom_shift;             // one bit per key of nb (a 2 MB bit set that stays in L2): most k-mers of the list have no neighbour at all
+    const u64* nb_bloom; u32 nb_bloom_log2;              // blocked bit set over the keys of nb (bk_host.h: bloom_mask; 16 MB that stay in L2): most k-mers of the list have no neighbour at all
     const u32* id_amb; const u32* id_rep; u32* dense; u8* dense_flag;
 };
 
@@ -246,34 +250,38 @@ __global__ void __launch_bounds__(256, 3) k_bin_count(BinView b, CompactArgs a, 
                 for (u32 j = 0; j < 4; j++) {
                     if (kk[j] == BK_HOLE || is_ref[j]) continue;
                     const u64 K = kk[j];
-                    bool done = false;
+                    u32 cand = 0;                                              // bit jj: the bit set does not rule cell jj out
 #pragma unroll 1
-                    for (u32 j0 = 0; j0 < b.k && !done; j0 += 7) {
-                        u64 key[7]; u32 bw[7]; u32 bb[7];
+                    for (u32 j0 = 0; j0 < b.k; j0 += 7) {
+                        u64 bw[7], bm[7];
 #pragma unroll
-                        for (u32 t = 0; t < 7; t++) {                          // the bit set first: seven independent loads that hit L2
+                        for (u32 t = 0; t < 7; t++) {                          // seven independent loads that hit L2
                             const u32 jj = min(j0 + t, b.k - 1);
-                            key[t] = ((u64)jj << 58) | (K & ~(3ull << (2 * (b.k - 1 - jj))));
-                            bb[t] = hash_slot(key[t], b.nb_bloom_shift);
-                            bw[t] = __ldg(b.nb_bloom + (bb[t] >> 5));
+                            const u64 hb = bin_hash(((u64)jj << 58) | (K & ~(3ull << (2 * (b.k - 1 - jj)))));
+                            bm[t] = bloom_mask_dev(hb, b.nb_bloom_log2);
+                            bw[t] = __ldg(b.nb_bloom + (hb >> (64 - b.nb_bloom_log2)));
                         }
 #pragma unroll
-                        for (u32 t = 0; t < 7; t++) {
-                            const u32 jj = j0 + t;
-                            if (jj >= b.k || done || !((bw[t] >> (bb[t] & 31u)) & 1u)) continue;
-                            u32 h = hash_slot(key[t], b.nb_shift);
-                            ExactSlotD s1 = load_exact(b.nb + h);
-                            while (s1.key != key[t] && s1.key != BK_EMPTY) { h = (h + 1) & b.nb_mask; s1 = load_exact(b.nb + h); }
-                            if (s1.key != key[t]) continue;
-                            done = true;                                       // a neighbour: if it is ambiguous every neighbour is, the k-mer stays here
-                            const u32 id = s1.gidx;
-                            if (((__ldg(b.id_amb + id) >> jj) & 1u) == 0) {
-                                const u32 line = (__ldg(b.id_rep + id) + jj) * 4u + (u32)((K >> (2 * (b.k - 1 - jj))) & 3);
-                                atomicAdd(b.dense + (size_t)line * (b.k + 1) + jj, cc[j]);
-                                b.dense_flag[line] = 1;
-                                is_ref[j] = true;                              // leaves the bins: counted with its cell
-                            }
+                        for (u32 t = 0; t < 7; t++) if (j0 + t < b.k && (bw[t] & bm[t]) == bm[t]) cand |= 1u << (j0 + t);
+                    }
+                    // (one k-mer in ~250 gets here without being a neighbour: a warp no longer walks the big table for
+                    // every cell because one of its lanes might have to)
+                    for (; cand; cand &= cand - 1) {
+                        const u32 jj = (u32)__ffs((int)cand) - 1u;
+                        const u64 key = ((u64)jj << 58) | (K & ~(3ull << (2 * (b.k - 1 - jj))));
+                        u32 h = hash_slot(key, b.nb_shift);
+                        ExactSlotD s1 = load_exact(b.nb + h);
+                        while (s1.key != key && s1.key != BK_EMPTY) { h = (h + 1) & b.nb_mask; s1 = load_exact(b.nb + h); }
+                        if (s1.key != key) continue;
+                        // a neighbour: if it is ambiguous every neighbour is, the k-mer stays here
+                        const u32 id = s1.gidx;
+                        if (((__ldg(b.id_amb + id) >> jj) & 1u) == 0) {
+                            const u32 line = (__ldg(b.id_rep + id) + jj) * 4u + (u32)((K >> (2 * (b.k - 1 - jj))) & 3);
+                            atomicAdd(b.dense + (size_t)line * (b.k + 1) + jj, cc[j]);
+                            b.dense_flag[line] = 1;
+                            is_ref[j] = true;                                  // leaves the bins: counted with its cell
                         }
+                        break;
                     }
                 }
             }

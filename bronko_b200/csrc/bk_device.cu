@@ -94,7 +94,7 @@ struct IndexDev {
     DevBuf<ExactSlotD> d_exact;
     DevBuf<u32> d_slot2id; DevBuf<u64> d_id_kmer;
     DevBuf<u32> d_slot2rep, d_id_amb, d_id_rep; DevBuf<ExactSlotD> d_nb;       // mismatch lines (bk_dense.cuh); empty when !d.dense_ok
-    DevBuf<u32> d_line_amb, d_line_fold, d_nb_bloom;
+    DevBuf<u32> d_line_amb, d_line_fold; DevBuf<u64> d_nb_bloom;
     DevBuf<uint2> d_id_bucket;                                                   // map shortcut (bk_host.h); empty when !d.map_shortcut_ok
     DevBuf<u32> d_genome_row0, d_genome_seq_off, d_seq_row0; DevBuf<u64> d_genome_len; DevBuf<u8> d_ref_code;
     u32 max_seqs_per_genome = 1;
@@ -876,7 +876,7 @@ static int launch_bins(bk_ctx* ctx, int slot, BinView& b, u64 ub, bool weighted,
     b.k = d.k;
     if (d.dense_ok) {
         b.nb = ctx->I->d_nb.p; b.nb_shift = 64 - d.nb_log2; b.nb_mask = (1u << d.nb_log2) - 1;
-        b.nb_bloom = ctx->I->d_nb_bloom.p; b.nb_bloom_shift = 64 - d.nb_bloom_log2;
+        b.nb_bloom = ctx->I->d_nb_bloom.p; b.nb_bloom_log2 = d.nb_bloom_log2;
         b.id_amb = ctx->I->d_id_amb.p; b.id_rep = ctx->I->d_id_rep.p; b.dense = f.dense.p; b.dense_flag = f.dflag.p;
     }
     k_bin_hist<<<G, BK_BIN_G_THREADS, P * 4, st>>>(b);
@@ -977,7 +977,9 @@ static int stage_compact(bk_ctx* ctx, int slot, cudaStream_t st) {
         ctx->launches++;
         f.dense_dirty = false;
     }
-    k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, st>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
+    if (dense && dense_maps(ctx) && !getenv("BK_NO_ID_MAP"))       // the reference k-mers: compacted and mapped in one go
+        k_compact_ids_map<<<std::max(1u, std::min((n_ids + BK_IDMAP_IDS - 1) / BK_IDMAP_IDS, (u32)ctx->sm_count * 16u)), 256, 0, st>>>(dv, a, f.idcnt.p, n_ids);
+    else k_compact_ids<<<grid_for(ctx, n_ids, 256), 256, 0, st>>>(a, f.idcnt.p, ctx->I->d_id_kmer.p, n_ids);
     ctx->launches++;
     ctx->span_end(sp);
     BK_CUDA(cudaGetLastError());

@@ -123,7 +123,8 @@ struct DerivedIndex {
     u32 nb_log2 = 0;
     std::vector<ExactSlot> nb_slots;         // key, gidx = id (oseq unused); key == ~0 → empty
     u32 nb_bloom_log2 = 0;
-    std::vector<u32> nb_bloom;               // one bit per hash_slot(key, 64 - nb_bloom_log2) of a key present in nb_slots: ~8 bits per key, stays in L2
+    std::vector<u64> nb_bloom;               // blocked bit set over the keys of nb_slots: word = top nb_bloom_log2 bits of the hash, three bits of it
+                                             // from the next 18 (bloom_mask) — >= 32 bits per key, one miss in ~5,000 look-ups, 16 MB that stay in L2
     // Map shortcut (rekeyed tables only).  The k-mer of an unambiguous cell (id, j, b) is within one digit of exactly one
     // reference k-mer — id's — so map_kmers can hit one bucket at most: index j of id's canonical form, and only if
     // replacing the digit does not flip which strand of the k-mer is canonical (bit 31 of id_amb[id]: id's k-mer is
@@ -138,6 +139,13 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey = true)
 
 // must match bk::hash_slot in bk_core.cuh (the device probes with the same function)
 inline u32 hash_slot_host(u64 x, u32 shift) { return (u32)(((x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull) >> shift); }
+// the neighbour bit set (nb_bloom; bk_bins.cuh: bloom_mask_dev is the same function): the word is the top `log2w` bits
+// of hash64, its three bits are the next 3 x 6 bits
+inline u64 hash64_host(u64 x) { return (x ^ (x >> 31)) * 0x9E3779B97F4A7C15ull; }
+inline u64 bloom_mask(u64 h, u32 log2w) {
+    const u64 r = h >> (64 - log2w - 18);
+    return (1ull << (r & 63)) | (1ull << ((r >> 6) & 63)) | (1ull << ((r >> 12) & 63));
+}
 
 // ---- Student-t / Thompson tau table (call.rs:922-929) --------------------------------------
 void tau_table(double* tab301);   // tab[n] for n in 3..300 (others 0)

@@ -601,8 +601,8 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
     }
     d.nb_log2 = log2_cap(n_ids * k);
     d.nb_slots.assign(1ull << d.nb_log2, ExactSlot{~0ull, 0, 0});
-    d.nb_bloom_log2 = d.nb_log2 + 2;                                         // slots >= 2 x keys → >= 8 bits per key
-    d.nb_bloom.assign((1ull << d.nb_bloom_log2) / 32, 0);
+    d.nb_bloom_log2 = d.nb_log2 > 8 ? d.nb_log2 - 2 : 6;                     // 64-bit words: slots >= 2 x keys → >= 32 bits per key, three of them set
+    d.nb_bloom.assign(1ull << d.nb_bloom_log2, 0);
     const u64 nmask = (1ull << d.nb_log2) - 1;
     for (size_t i = 0; i < n_ids; i++)
         for (u32 j = 0; j < k; j++) {
@@ -610,8 +610,8 @@ void derive_index(const HostIndex& ix, DerivedIndex& d, bool allow_rekey) {
             u64 h = hash_slot_host(key, 64 - d.nb_log2);
             while (d.nb_slots[h].key != ~0ull && d.nb_slots[h].key != key) h = (h + 1) & nmask;
             if (d.nb_slots[h].key == ~0ull) d.nb_slots[h] = ExactSlot{key, (u32)i, 0};      // (a second id with this key: both are flagged at j)
-            const u32 bit = hash_slot_host(key, 64 - d.nb_bloom_log2);
-            d.nb_bloom[bit >> 5] |= 1u << (bit & 31);
+            const u64 hb = hash64_host(key);
+            d.nb_bloom[hb >> (64 - d.nb_bloom_log2)] |= bloom_mask(hb, d.nb_bloom_log2);
         }
     // per line: which cells are ambiguous / must be folded (most lines: none — the kernels skip them without reading the row)
     d.line_amb.assign(d.n_raw, 0); d.line_fold.assign(d.n_raw, 0);
