@@ -160,6 +160,7 @@ struct bk_ctx {
     DevBuf<u32> d_pile_all;                 // one such block per genome (databases of at most four genomes: one-pass map)
     DevBuf<double> d_noise;                 // Noise.max per row
     DevBuf<double> d_nz_maf, d_nz_s, d_nz_s2, d_nz_tab, d_nz_warm;   // noise scratch (bk_noise.cuh: NoiseView)
+    DevBuf<u8> d_nz_nzflag; DevBuf<u32> d_nz_list, d_nz_rank, d_nz_nact;
     DevBuf<u8> d_nz_flag; DevBuf<u32> d_nz_stats;
     u32 nz_max_chunks = 1;
     DevBuf<bk_variant> d_vars;
@@ -323,6 +324,7 @@ void bk_destroy(bk_ctx* ctx) {
     ctx->d_ctr.release(); ctx->d_pile.release(); ctx->d_pile_all.release();
     ctx->d_noise.release(); ctx->d_vars.release();
     ctx->d_nz_maf.release(); ctx->d_nz_s.release(); ctx->d_nz_s2.release(); ctx->d_nz_tab.release(); ctx->d_nz_warm.release();
+    ctx->d_nz_nzflag.release(); ctx->d_nz_list.release(); ctx->d_nz_rank.release(); ctx->d_nz_nact.release();
     ctx->d_nz_flag.release(); ctx->d_nz_stats.release();
     ctx->d_stage[0].release(); ctx->d_stage[1].release(); ctx->d_stage_off.release();
     ctx->d_shard_stats.release(); ctx->d_shard_sizes.release();
@@ -443,6 +445,8 @@ static int size_for_index(bk_ctx* ctx) {
         ctx->nz_max_chunks = (max_len + BK_NOISE_HALF + BK_NZ_CHUNK - 1) / BK_NZ_CHUNK;
         BK_CUDA(ctx->d_nz_maf.reserve((rows + BK_NZ_PAD * seqs) * 3));
         BK_CUDA(ctx->d_nz_s.reserve(it_slots)); BK_CUDA(ctx->d_nz_s2.reserve(it_slots));
+        BK_CUDA(ctx->d_nz_nzflag.reserve(it_slots)); BK_CUDA(ctx->d_nz_list.reserve(it_slots)); BK_CUDA(ctx->d_nz_rank.reserve(it_slots));
+        BK_CUDA(ctx->d_nz_nact.reserve(seqs));
         BK_CUDA(ctx->d_nz_tab.reserve(it_slots * BK_NOISE_TABLE));
         BK_CUDA(ctx->d_nz_warm.reserve(chunk_slots * BK_NOISE_TABLE));
         BK_CUDA(ctx->d_nz_flag.reserve(chunk_slots));
@@ -1100,6 +1104,7 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     nv.maf = ctx->d_nz_maf.p; nv.snap_s = ctx->d_nz_s.p; nv.snap_s2 = ctx->d_nz_s2.p; nv.snap_tab = ctx->d_nz_tab.p;
     nv.warm = ctx->d_nz_warm.p; nv.flag = ctx->d_nz_flag.p; nv.stats = ctx->noise_debug ? ctx->d_nz_stats.p : nullptr;
     nv.noise_max = ctx->d_noise.p;
+    nv.actflag = ctx->d_nz_nzflag.p; nv.act_list = ctx->d_nz_list.p; nv.act_rank = ctx->d_nz_rank.p; nv.act_n = ctx->d_nz_nact.p;
     const u32 nseq = ctx->I->max_seqs_per_genome;
     if (ctx->noise_debug) cudaMemsetAsync(ctx->d_nz_stats.p, 0, 64, st);
     k_noise_fracs<<<dim3((d.max_genome_rows + BK_NZ_PAD + 255) / 256, nseq), 256, 0, st>>>(nv);
@@ -1112,6 +1117,9 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
         cudaStreamSynchronize(st);
         fprintf(stderr, "[noise] table chunks replayed %u (%u iterations); chain rounds %u, stops %u, serial iterations %u; kcycles: s %u, s2 %u, slowest table lane %u\n",
                 h[0], h[1], h[2], h[3], h[4], h[5] / 64, h[6] / 64, h[7] / 64);
+#ifdef BK_NZ_WHY
+        fprintf(stderr, "[noise] stops by cause: operand too large %u, near a zone border %u, above the zones %u, below the zones %u; iterations accepted in stopped rounds %u\n", h[8], h[9], h[10], h[11], h[12]);
+#endif
 #ifdef BK_NZ_PHASES
         fprintf(stderr, "[noise] s2 chain kcycles by phase: tile %u, operands+maps %u, warp scan %u, combine %u, check+reduce %u, prefix %u, stop %u, serial %u\n",
                 h[8] / 64, h[9] / 64, h[10] / 64, h[11] / 64, h[12] / 64, h[13] / 64, h[14] / 64, h[15] / 64);

@@ -47,9 +47,10 @@ typedef long long i64;
 #endif
 #define BK_NZ_WARPS (BK_NZ_SEQ_THREADS / 32)
 #define BK_NZ_ROUND (BK_NZ_SEQ_THREADS * BK_NZ_IPT)   // iterations per chain round
-#define BK_NZ_TILE 1024          // iterations of fractions staged per shared-memory tile of a chain block
+#define BK_NZ_MIN_RUN 64         // a run of iterations that fits three zones but is shorter than this is walked in real FP64 (a round costs ~100 such iterations)
+#define BK_NZ_SERIAL_RUN 64      // ... for at least this many iterations
 #ifndef BK_NZ_SERIAL
-#define BK_NZ_SERIAL 8           // iterations executed serially per batch (after a stop, and for as long as the exponent keeps moving)
+#define BK_NZ_SERIAL 8           // iterations executed serially after a round that accepted next to nothing although the look-ahead saw a long run
 #endif
 #define BK_NZ_PAD_LO 100         // zero positions in front of every sequence in the fraction array
 #define BK_NZ_PAD (BK_NZ_PAD_LO + 150)   // total padding positions per sequence
@@ -206,6 +207,43 @@ BK_HD bool nz2_zones(u64 sb, NzZ2* z) {                    // false: s is zero /
     z->scale = nz_d((u64)(2098u - z->el) << 52);          // 1 / ulp(lowest zone)
     z->xmax = nz_d((u64)(z->el + BK_NZ_ZONES) << 52);     // operands beyond the top of the zones cannot leave the sum inside them
     return true;
+}
+// Where to put the three zones: look-ahead.  The window sum after every iteration is known APPROXIMATELY before the
+// chains start (k_noise_fracs adds the 300 fractions of the window in any order: the chain's own value differs from it
+// by rounding noise only), and with it the binades the chain is going to visit.  A round picks the lowest zone so that
+// the longest run of iterations ahead of it fits — one binade of room on either side of the start (the fixed choice of
+// the first version) ended 60-80 % of the rounds of a thin sample after ~130 of 256 iterations, because the sum of a
+// sparse window halves or doubles within a few dozen positions.  The choice is a hint: every operation is still checked
+// against the zones it was computed for.
+// key = (highest exponent field << 16) | (0xFFFF - lowest exponent field); merging two keys = per-half maximum.
+#define BK_NZ_HINT_NEUTRAL 0u
+BK_HD u32 nz_hint_key(u64 bits) {
+    const u32 e = (u32)(bits >> 52);                       // (sign set: e >= 0x800 → breaks)
+    if (bits == 0 || e < 66u || e >= 0x7FCu) return (0x7FFu << 16) | (0xFFFFu - 1u);     // a sum the rounds cannot carry: the run ends here
+    const u64 m = bits & BK_NZ_MASK52;
+    const u32 lo = e - (m < (1ull << 23) ? 1u : 0u), hi = e + (m > BK_NZ_MASK52 - (1ull << 23) ? 1u : 0u);    // next to a power of two: either side
+    return (hi << 16) | (0xFFFFu - lo);
+}
+BK_HD u32 nz_hint_start(u32 ef) { return (ef << 16) | (0xFFFFu - ef); }
+BK_HD u32 nz_hint_merge(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __vmaxu2(a, b);
+#else
+    const u32 h = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16), l = (a & 0xFFFFu) > (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
+    return (h << 16) | l;
+#endif
+}
+BK_HD bool nz_hint_fits(u32 key) { return (key >> 16) - (0xFFFFu - (key & 0xFFFFu)) <= BK_NZ_ZONES - 1u; }
+// lowest zone for the merged key of the run (it contains the start: ef - 2 <= result <= ef).  A spare zone goes BELOW the
+// run: every iteration subtracts before it adds.
+BK_HD u32 nz_hint_el(u32 key) {
+    const u32 hi = key >> 16, lo = 0xFFFFu - (key & 0xFFFFu);
+    return hi - lo == BK_NZ_ZONES - 1u ? lo : lo - 1u;
+}
+BK_HD void nz2_zones_at(u32 el, NzZ2* z) {
+    z->el = el;
+    z->scale = nz_d((u64)(2098u - el) << 52);
+    z->xmax = nz_d((u64)(el + BK_NZ_ZONES) << 52);
 }
 BK_HD i64 nz2_start(const NzZ2& z, u64 sb) {
     const i64 m = (i64)((sb & BK_NZ_MASK52) | (1ull << 52));
@@ -383,6 +421,11 @@ struct NoiseView {
     u32* stats;           // [0] chunks replayed, [1] iterations replayed, [2] chain rounds, [3] chain stops, [4] serial iterations,
                           // [5] / [6] cycles/16 of the s / s2 chain, [7] cycles/16 of the slowest table lane
     double* noise_max;    // rows
+    // active iterations (nz_chain_block): an iteration whose six operands are all zero leaves both sums as they are
+    u8* actflag;          // rows + 50 * seqs: iteration i has a non-zero operand (at ibase + i; k_noise_fracs)
+    u32* act_list;        // rows + 50 * seqs: the active iterations of a sequence, ascending (at ibase)
+    u32* act_rank;        // rows + 50 * seqs: active iterations <= i (at ibase + i)
+    u32* act_n;           // seqs
 };
 
 struct NzSeq { u32 r0, len, iters, mbase, ibase, cbase; bool ok; };
@@ -406,35 +449,63 @@ __device__ __forceinline__ NzSeq nz_seq(const NoiseView& nv, u32 q) {
 
 __constant__ double c_tau[301];
 
-// grid (ceil((max_rows + BK_NZ_PAD) / 256), max_seqs)
+// grid (ceil((max_rows + BK_NZ_PAD) / 256), max_seqs).  Also the look-ahead of the chains (nz_hint_key): the approximate
+// window sums after every iteration go where the chains will write the exact ones (snap_s / snap_s2).
 __global__ void __launch_bounds__(256) k_noise_fracs(NoiseView nv) {
+    __shared__ double fr[(256 + BK_NOISE_WINDOW) * 3];              // positions x0 - 100 .. x0 + 255
     const NzSeq s = nz_seq(nv, blockIdx.y);
     if (!s.ok) return;
-    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;          // position p = x - BK_NZ_PAD_LO
-    if (x >= s.len + BK_NZ_PAD) return;
-    double m3[3] = {0.0, 0.0, 0.0};
-    if (x >= BK_NZ_PAD_LO && x < BK_NZ_PAD_LO + s.len) {
-        const u32 row = s.r0 + x - BK_NZ_PAD_LO;
-        const uint4 f = *reinterpret_cast<const uint4*>(nv.pile + (size_t)row * 4);
-        const uint4 r = *reinterpret_cast<const uint4*>(nv.pile + nv.pile_stride + (size_t)row * 4);
-        const u32 f4[4] = {f.x, f.y, f.z, f.w}, r4[4] = {r.x, r.y, r.z, r.w};
-        nz_fractions(f4, r4, m3);
+    const u32 x0 = blockIdx.x * blockDim.x;                         // position p = x - BK_NZ_PAD_LO
+    if (x0 >= s.len + BK_NZ_PAD) return;
+    for (u32 t = threadIdx.x; t < 256 + BK_NOISE_WINDOW; t += 256) {
+        const i64 x = (i64)x0 - BK_NOISE_WINDOW + t;
+        double m3[3] = {0.0, 0.0, 0.0};
+        if (x >= BK_NZ_PAD_LO && x < (i64)BK_NZ_PAD_LO + s.len) {
+            const u32 row = s.r0 + (u32)x - BK_NZ_PAD_LO;
+            const uint4 f = *reinterpret_cast<const uint4*>(nv.pile + (size_t)row * 4);
+            const uint4 r = *reinterpret_cast<const uint4*>(nv.pile + nv.pile_stride + (size_t)row * 4);
+            const u32 f4[4] = {f.x, f.y, f.z, f.w}, r4[4] = {r.x, r.y, r.z, r.w};
+            nz_fractions(f4, r4, m3);
+        }
+        fr[t * 3] = m3[0]; fr[t * 3 + 1] = m3[1]; fr[t * 3 + 2] = m3[2];
+        if (t >= BK_NOISE_WINDOW && x < (i64)s.len + BK_NZ_PAD) {
+            double* o = nv.maf + (size_t)(s.mbase - BK_NZ_PAD_LO + (u32)x) * 3;
+            o[0] = m3[0]; o[1] = m3[1]; o[2] = m3[2];
+        }
     }
-    double* o = nv.maf + (size_t)(s.mbase - BK_NZ_PAD_LO + x) * 3;
-    o[0] = m3[0]; o[1] = m3[1]; o[2] = m3[2];
+    __syncthreads();
+    const u32 x = x0 + threadIdx.x;
+    if (x >= BK_NZ_PAD_LO && x - BK_NZ_PAD_LO < s.iters) {           // iteration i = position i: the window is positions i - 99 .. i
+        double a = 0.0, b = 0.0;
+        for (u32 w = 1; w <= BK_NOISE_WINDOW; w++)
+#pragma unroll
+            for (u32 j = 0; j < 3; j++) { const double v = fr[(threadIdx.x + w) * 3 + j]; a += v; b += v * v; }
+        nv.snap_s[s.ibase + x - BK_NZ_PAD_LO] = a;
+        nv.snap_s2[s.ibase + x - BK_NZ_PAD_LO] = b;
+        const double* fo = fr + threadIdx.x * 3;                                 // position i - 100
+        const double* fn = fr + (threadIdx.x + BK_NOISE_WINDOW) * 3;             // position i
+        nv.actflag[s.ibase + x - BK_NZ_PAD_LO] = (fo[0] != 0.0 || fo[1] != 0.0 || fo[2] != 0.0 || fn[0] != 0.0 || fn[1] != 0.0 || fn[2] != 0.0) ? 1 : 0;
+    }
 }
 
-// ---- chain block: 256 threads, one iteration per thread and round ---------------------------------------------
-#define BK_NZ_CHAIN_SMEM ((BK_NZ_TILE + BK_NOISE_WINDOW) * 3 * 8)
+// ---- chain block: 256 threads, one ACTIVE iteration per thread and pass ---------------------------------------
+// An iteration whose six operands are zero (no minor allele at position i nor at i - 100) leaves s and s² exactly as
+// they are, so the chains only walk the active ones: all of them at 10,000x, two thirds at 5,000x, 9 % at 2,000x, 90 of
+// 29,953 at 400x.  The sums of the skipped iterations are read through act_rank / act_list (k_noise_tau).
+// A pass takes the next 256 active iterations, loads their operands and looks ahead (nz_hint_key): if the run of
+// iterations that fits three zones is long, the pass is a round (three block scans, below); if the sum is about to halve
+// or double every few iterations — a window that holds a handful of fractions — the run and what follows are added up
+// in real FP64, one after the other like the reference, which costs ~1 % of a round per iteration.
+#define BK_NZ_CHAIN_SMEM (BK_NZ_ROUND * 6 * 8)
 #define BK_NZ_TABLE_POS (BK_NOISE_WINDOW + BK_NZ_WARM + BK_NZ_CHUNK)          // positions a chunk lane touches
 #define BK_NZ_TABLE_WARPS 8                                                   // chunk lanes per table block
 #define BK_NZ_TABLE_SMEM (BK_NZ_TABLE_WARPS * BK_NZ_TABLE_POS * 3 * 8)
 #define BK_NZ_SEQ_SMEM (BK_NZ_TABLE_SMEM > BK_NZ_CHAIN_SMEM ? BK_NZ_TABLE_SMEM : BK_NZ_CHAIN_SMEM)
 
 // Developer builds only (tools/build_variant.sh ... -DBK_NZ_PHASES, run with BK_NOISE_DEBUG=1): cycles of the s² chain
-// by phase of a round — 0 tile staging, 1 operands + increments + per-thread maps, 2 warp scan, 3 barrier + cross-warp
-// combine, 4 sums + range check + reduction + barrier, 5 accepted prefix + barrier, 6 the stop's iteration, 7 serial
-// batches — into stats[8..15] (cycles / 16).  The product build compiles none of it.
+// by phase of a pass — 0 compaction, 1 operands + look-ahead, 2 split + warp scan, 3 barrier + maps + cross-warp combine,
+// 4 sums + range check + reduction + barrier, 5 accepted prefix + barrier, 6 the stop's iteration, 7 serial runs — into
+// stats[8..15] (cycles / 16).  The product build compiles none of it.
 #ifdef BK_NZ_PHASES
 #define BK_NZ_PH_DECL long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define BK_NZ_PH(i) do { const long long ph_n = clock64(); ph_acc[i] += (unsigned long long)(ph_n - ph_t); ph_t = ph_n; } while (0)
@@ -451,103 +522,163 @@ __device__ __forceinline__ NzVec nzvec_shfl_up(const NzVec& f, int o) {
     return g;
 }
 
+// The active iterations of a sequence → act_list / act_rank / act_n.  Both chain blocks run it and write the same
+// values; each reads what it needs after its own barrier.  A warp owns a contiguous span of iterations and walks it 32
+// at a time (one coalesced load of the flags k_noise_fracs wrote, a ballot), sixteen loads in flight.
+#define BK_NZ_CU 16
+__device__ __forceinline__ u32 nz_compact_active(const NoiseView& nv, const NzSeq& sq, u32* wtmp /* BK_NZ_WARPS words of shared memory */) {
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u8* fl = nv.actflag + sq.ibase;
+    const u32 steps = ((sq.iters + 31) / 32 + BK_NZ_WARPS - 1) / BK_NZ_WARPS;   // 32-iteration steps per warp
+    const u32 b = wid * steps * 32;
+    u32 cnt = 0;
+    for (u32 st = 0; st < steps; st += BK_NZ_CU) {
+        u32 f[BK_NZ_CU];
+#pragma unroll
+        for (u32 u = 0; u < BK_NZ_CU; u++) { const u32 i = b + (st + u) * 32 + lane; f[u] = (st + u < steps && i < sq.iters) ? fl[i] : 0u; }
+#pragma unroll
+        for (u32 u = 0; u < BK_NZ_CU; u++) cnt += (u32)__popc(__ballot_sync(0xFFFFFFFFu, f[u] != 0));
+    }
+    if (lane == 0) wtmp[wid] = cnt;
+    __syncthreads();
+    u32 base = 0, total = 0;
+#pragma unroll
+    for (u32 w = 0; w < BK_NZ_WARPS; w++) { const u32 v = wtmp[w]; if (w < wid) base += v; total += v; }
+    u32* list = nv.act_list + sq.ibase;
+    u32* rank = nv.act_rank + sq.ibase;
+    for (u32 st = 0; st < steps; st += BK_NZ_CU) {
+        u32 f[BK_NZ_CU];
+#pragma unroll
+        for (u32 u = 0; u < BK_NZ_CU; u++) { const u32 i = b + (st + u) * 32 + lane; f[u] = (st + u < steps && i < sq.iters) ? fl[i] : 0u; }
+#pragma unroll
+        for (u32 u = 0; u < BK_NZ_CU; u++) {
+            const u32 i = b + (st + u) * 32 + lane;
+            const u32 m = __ballot_sync(0xFFFFFFFFu, f[u] != 0);
+            const u32 incl = base + (u32)__popc(m & (0xFFFFFFFFu >> (31 - lane)));       // active iterations <= i
+            if (f[u]) list[incl - 1] = i;
+            if (st + u < steps && i < sq.iters) rank[i] = incl;
+            base += (u32)__popc(m);
+        }
+    }
+    if (tid == 0) nv.act_n[blockIdx.y] = total;
+    __syncthreads();                                                            // (the list is read by other threads of this block)
+    return total;
+}
+
 template <bool SQUARE>
-__device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* mt) {
+__device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq& sq, double* xs) {
     __shared__ i64 wsumA[2][BK_NZ_WARPS];
     __shared__ u32 wnextL[2][BK_NZ_WARPS], wnextH[2][BK_NZ_WARPS];               // per warp: class transition of the whole warp
     __shared__ i32 wsumR[2][BK_NZ_WARPS];                              // per warp: roundings of the whole warp
     __shared__ u32 wbad[2][BK_NZ_WARPS];
+    __shared__ u32 whint[2][BK_NZ_WARPS], wlast[BK_NZ_WARPS];           // look-ahead: run keys of the warps (per pass parity) / the warps' last fitting keys
+    __shared__ u32 wfit[BK_NZ_WARPS + 1];                               // look-ahead: fitting iterations per warp (and scratch of the compaction)
     __shared__ double sstate[2];
+    static_assert(BK_NZ_IPT == 1, "one active iteration per thread and pass");
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const double* mafp = nv.maf + (size_t)(sq.mbase - BK_NZ_PAD_LO) * 3;       // position -100
-    double* snap = (SQUARE ? nv.snap_s2 : nv.snap_s) + sq.ibase;
-    const u32 iters = sq.iters;
-    const u32 pos_total = sq.len + BK_NZ_PAD;                                   // positions present in mafp
-    double s = 0.0;
-    u32 i0 = 0, tile_lo = 0, tile_hi = 0;                                       // tile covers iterations [tile_lo, tile_hi)
-    u32 round = 0, serial_left = 0;
-    const u32 width = BK_NZ_ROUND;                                              // iterations tried per round
-    u32 st_rounds = 0, st_stops = 0, st_serial = 0;
     const long long t_begin = clock64();
     BK_NZ_PH_DECL
-    while (i0 < iters) {
-        if (i0 + 1 > tile_hi || (i0 + BK_NZ_ROUND > tile_hi && tile_hi < iters)) {
-            __syncthreads();
-            tile_lo = i0; tile_hi = min(iters, i0 + BK_NZ_TILE);
-            const u32 nx = (tile_hi - tile_lo + BK_NOISE_WINDOW) * 3;            // positions tile_lo-100 .. tile_hi-1
-            const size_t x0 = (size_t)tile_lo * 3;                               // mafp index of position tile_lo-100
-            for (u32 x = tid; x < nx; x += BK_NZ_SEQ_THREADS) mt[x] = (tile_lo + x / 3 < pos_total) ? mafp[x0 + x] : 0.0;
-            __syncthreads();
-            BK_NZ_PH(0);
-        }
-        const u32 tl = tile_lo;
-        auto M = [mt, tl](i32 p, u32 j) { return mt[(u32)(p + BK_NOISE_WINDOW - (i32)tl) * 3 + j]; };
-        const u32 n_it = min(width, tile_hi - i0);
-        const u64 sb = nz_b(s);
-        NzZ2 z;
-        if (sb == 0) {
-            // s is exactly zero (sparse coverage: the last positive fraction has left the window): every iteration whose six
-            // operands are zero leaves it there — find the first one that does not, all iterations of the round at once
-            u32 first = n_it;
-#pragma unroll
-            for (u32 j = 0; j < BK_NZ_IPT; j++) {
-                const u32 it = tid * BK_NZ_IPT + j;
-                if (it < n_it && first == n_it) {
-                    bool any = false;
-#pragma unroll
-                    for (u32 q = 0; q < 6; q++) any = any || nz_operand<SQUARE>(M, (i32)(i0 + it), q) != 0.0;
-                    if (any) first = it;
-                }
-            }
-            first = __reduce_min_sync(0xFFFFFFFFu, first);
-            const u32 zbuf = round & 1;
-            round++;
-            if (lane == 0) wbad[zbuf][wid] = first;
-            __syncthreads();
-#pragma unroll
-            for (u32 w = 0; w < BK_NZ_WARPS; w++) first = min(first, wbad[zbuf][w]);
-#pragma unroll
-            for (u32 j = 0; j < BK_NZ_IPT; j++) if (tid * BK_NZ_IPT + j < first) snap[i0 + tid * BK_NZ_IPT + j] = 0.0;
-            i0 += first;
-            if (first < n_it) {                              // the iteration that brings the sum back: like the reference
-#pragma unroll
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)i0, q));
-                if (tid == 0) snap[i0] = s;
-                i0++; st_serial++;
-            }
-            BK_NZ_PH(7);
-            continue;
-        }
-        if (!nz2_zones(sb, &z) || serial_left) {
-            // s is tiny / negative / non-finite, or the last round accepted next to nothing (operands as large as the sum
-            // one after the other): a few iterations like the reference, then rounds again
-            const u32 n_ser = min(tile_hi - i0, (u32)BK_NZ_SERIAL);
-            for (u32 it = 0; it < n_ser; it++) {
-#pragma unroll
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
-                if (tid == 0) snap[i0 + it] = s;
-            }
-            i0 += n_ser; st_serial += n_ser;
-            serial_left = 0;
-            BK_NZ_PH(7);
-            continue;
-        }
+    const u32 n_act = nz_compact_active(nv, sq, wfit);
+    BK_NZ_PH(0);
+    const double* maf0 = nv.maf + (size_t)sq.mbase * 3;                         // position 0
+    const u32* list = nv.act_list + sq.ibase;
+    double* snap = (SQUARE ? nv.snap_s2 : nv.snap_s) + sq.ibase;
+    double s = 0.0;
+    u32 a0 = 0, round = 0, force_serial = 0;                                    // a0 = active iterations done
+    u32 pf_a0 = 0xFFFFFFFFu, it_n = 0, hk_n = BK_NZ_HINT_NEUTRAL;               // the pass whose operands are in x_n / hb_n and whose keys are in whint
+    u64 hb_n = 0;
+    double x_n[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    u32 st_rounds = 0, st_stops = 0, st_serial = 0;
+    while (a0 < n_act) {
+        const u32 n_it = min((u32)BK_NZ_ROUND, n_act - a0);
         const u32 buf = round & 1;
-        round++; st_rounds++;
+        round++;
+        // this thread's iteration: its six operands (-old_j, +new_j; src/call.rs:845-895) from the fraction array, its look-ahead
+        // key — loaded during the previous round if that round was expected to end where it did (pf_a0), else now
+        u32 it = 0, hk = BK_NZ_HINT_NEUTRAL;
+        double x[6];
+        const bool prefetched = pf_a0 == a0;
+        if (!prefetched) {
+            if (tid < n_it) {
+                it_n = list[a0 + tid];
+                const double* mo = maf0 + ((i64)it_n - BK_NOISE_WINDOW) * 3;
+                const double* mn = maf0 + (i64)it_n * 3;
+                hb_n = nz_b(snap[it_n]);                                         // (k_noise_fracs left the approximate window sum here)
+#pragma unroll
+                for (u32 j = 0; j < 3; j++) { x_n[2 * j] = mo[j]; x_n[2 * j + 1] = mn[j]; }
+            }
+        }
+        if (tid < n_it) {
+            it = it_n;
+#pragma unroll
+            for (u32 j = 0; j < 3; j++) {
+                double o = x_n[2 * j], n = x_n[2 * j + 1];
+                if (SQUARE) { o = nz_mul(o, o); n = nz_mul(n, n); }
+                x[2 * j] = -o; x[2 * j + 1] = n;
+            }
+            hk = nz_hint_key(hb_n);
+        } else {
+#pragma unroll
+            for (u32 q = 0; q < 6; q++) x[q] = 0.0;
+        }
+#pragma unroll
+        for (u32 q = 0; q < 6; q++) xs[tid * 6 + q] = x[q];
+        // look-ahead: how many of the iterations ahead fit three zones, and where to put the zones
+        const u64 sb = nz_b(s);
+        const u32 ef = (u32)(sb >> 52);
+        const bool capable = ef >= 66u && ef < 0x7FCu;                           // positive, normal, finite (a set sign bit makes ef >= 0x800)
+        const u32 start = nz_hint_start(capable ? ef : 1023u);
+        if (!prefetched) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 g = __shfl_up_sync(0xFFFFFFFFu, hk, o); if (lane >= (u32)o) hk = nz_hint_merge(hk, g); }
+            if (lane == 31) whint[buf][wid] = hk;
+            hk_n = hk;
+            __syncthreads();
+        }
+        hk = hk_n;                                                               // (prefetched: scanned and published before the last round's barriers)
+        // the next pass, if this one turns out to be a round that accepts everything: its iteration index now, ...
+        const u32 a_next = a0 + n_it, n_next = min((u32)BK_NZ_ROUND, n_act - a_next);
+        u32 it_p = 0;
+        if (tid < n_next) it_p = list[a_next + tid];
+        u32 pre = start;
+#pragma unroll
+        for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { const u32 v = whint[buf][w]; if (w < wid) pre = nz_hint_merge(pre, v); }
+        hk = nz_hint_merge(hk, pre);
+        const bool fits = tid < n_it && nz_hint_fits(hk);                        // (the keys only grow along the run: fits is a prefix)
+        const u32 fv = fits ? hk : start;
+        const u32 vh = __reduce_max_sync(0xFFFFFFFFu, fv >> 16), vl = __reduce_max_sync(0xFFFFFFFFu, fv & 0xFFFFu);
+        const u32 nf = (u32)__popc(__ballot_sync(0xFFFFFFFFu, fits));
+        if (lane == 0) { wlast[wid] = (vh << 16) | vl; wfit[wid] = nf; }
+        __syncthreads();
+        u32 F = start, run = 0;
+#pragma unroll
+        for (u32 w = 0; w < BK_NZ_WARPS; w++) { F = nz_hint_merge(F, wlast[w]); run += wfit[w]; }
+        BK_NZ_PH(1);
+        if (!capable || force_serial || run < BK_NZ_MIN_RUN) {
+            // the sum is zero / tiny / negative, or about to leave any three zones within a few iterations: like the reference
+            const u32 n_ser = min(n_it, force_serial ? (u32)BK_NZ_SERIAL : (capable ? max(run + 1u, (u32)BK_NZ_SERIAL_RUN) : (u32)BK_NZ_SERIAL_RUN));
+            double keep = 0.0;
+            for (u32 t = 0; t < n_ser; t++) {
+#pragma unroll
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, xs[t * 6 + q]);
+                if (t == tid) keep = s;
+            }
+            if (tid < n_ser) snap[it] = keep;
+            a0 += n_ser; st_serial += n_ser; force_serial = 0; pf_a0 = 0xFFFFFFFFu;
+            __syncthreads();                                                     // (xs is rewritten by the next pass)
+            BK_NZ_PH(7);
+            continue;
+        }
+        st_rounds++;
+        NzZ2 z;
+        nz2_zones_at(nz_hint_el(F), &z);
         const i64 S0 = nz2_start(z, sb);
-        const u32 it0 = tid * BK_NZ_IPT;                                         // this thread's first iteration of the round
         i64 A[BK_NZ_OPT]; u32 fc[BK_NZ_OPT]; bool ok[BK_NZ_OPT];
         i64 PA = 0, incl = 0;
-        const bool warp_on = wid * 32 * BK_NZ_IPT < n_it;                        // warps without an iteration skip the work
+        const bool warp_on = wid * 32 < n_it;                                    // warps without an iteration skip the work
         if (warp_on) {
 #pragma unroll
-            for (u32 q = 0; q < BK_NZ_OPT; q++) {
-                const u32 it = it0 + q / 6;
-                const double x = it < n_it ? nz_operand<SQUARE>(M, (i32)(i0 + it), q % 6) : 0.0;
-                ok[q] = nz2_split(z, x, &A[q], &fc[q]);
-                PA += A[q];
-            }
-            BK_NZ_PH(1);
+            for (u32 q = 0; q < BK_NZ_OPT; q++) { ok[q] = nz2_split(z, x[q], &A[q], &fc[q]); PA += A[q]; }
             incl = PA;                                                           // scan 1: the A's
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const i64 g = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (u32)o) incl += g; }
@@ -558,6 +689,15 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         if (lane == 31) wsumA[buf][wid] = incl;
         BK_NZ_PH(2);
         __syncthreads();
+        // ... its operands and its approximate sum while this round computes (nothing waits for them before the round's end)
+        if (tid < n_next) {
+            it_n = it_p;
+            const double* mo = maf0 + ((i64)it_p - BK_NOISE_WINDOW) * 3;
+            const double* mn = maf0 + (i64)it_p * 3;
+            hb_n = nz_b(snap[it_p]);
+#pragma unroll
+            for (u32 j = 0; j < 3; j++) { x_n[2 * j] = mo[j]; x_n[2 * j + 1] = mn[j]; }
+        }
         i64 Pex = incl - PA;
 #pragma unroll
         for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { const i64 v = wsumA[buf][w]; if (w < wid) Pex += v; }      // (unrolled: the loads issue together)
@@ -592,6 +732,13 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         for (int o = 1; o < 32; o <<= 1) { const i32 g = __shfl_up_sync(0xFFFFFFFFu, rincl, o); if (lane >= (u32)o) rincl += g; }
         if (lane == 31) wsumR[buf][wid] = rincl;
         __syncthreads();
+        {   // ... and the scan of its look-ahead keys, published by the barriers that end this round
+            u32 k2 = tid < n_next ? nz_hint_key(hb_n) : BK_NZ_HINT_NEUTRAL;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const u32 g = __shfl_up_sync(0xFFFFFFFFu, k2, o); if (lane >= (u32)o) k2 = nz_hint_merge(k2, g); }
+            if (lane == 31) whint[buf ^ 1][wid] = k2;
+            hk_n = k2;
+        }
         i32 Rex = rincl - rt;
 #pragma unroll
         for (u32 w = 0; w < BK_NZ_WARPS - 1; w++) { const i32 v = wsumR[buf][w]; if (w < wid) Rex += v; }
@@ -603,7 +750,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
             if (!nz2_inside(Tq[q]) && bad > q) bad = q;
         }
         const u32 total_ops = n_it * 6;
-        u32 mine = bad < BK_NZ_OPT ? min(tid * BK_NZ_OPT + bad, total_ops) : total_ops;     // (operations past the round's end are zeros)
+        u32 mine = bad < BK_NZ_OPT ? min(tid * BK_NZ_OPT + bad, total_ops) : total_ops;     // (operations past the pass's end are zeros)
         mine = __reduce_min_sync(0xFFFFFFFFu, mine);
         if (lane == 0) wbad[buf][wid] = mine;
         __syncthreads();
@@ -611,9 +758,7 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
         u32 n_ok = total_ops;
 #pragma unroll
         for (u32 w = 0; w < BK_NZ_WARPS; w++) n_ok = min(n_ok, wbad[buf][w]);
-#pragma unroll
-        for (u32 j = 0; j < BK_NZ_IPT; j++)                                      // iterations whose six operations were all accepted
-            if (it0 + j < n_it && (it0 + j) * 6 + 5 < n_ok) snap[i0 + it0 + j] = nz2_value(z, Tq[j * 6 + 5]);
+        if (tid < n_it && tid * 6 + 5 < n_ok) snap[it] = nz2_value(z, Tq[5]);    // iterations whose six operations were all accepted
         if (n_ok > 0) {
             const u32 owner = (n_ok - 1) / BK_NZ_OPT, oq = (n_ok - 1) - owner * BK_NZ_OPT;
             if (tid == owner) {
@@ -623,17 +768,26 @@ __device__ __forceinline__ void nz_chain_block(const NoiseView& nv, const NzSeq&
                 sstate[buf] = nz2_value(z, Tl);
             }
         }
+#ifdef BK_NZ_WHY                                   // developer builds: why the accepted prefix ended → stats[8..12]
+        if (n_ok < total_ops && tid == n_ok / BK_NZ_OPT && nv.stats) {
+            const u32 q = n_ok % BK_NZ_OPT;
+            const u32 why = !ok[q] ? 0u : (T.bad == q ? 1u : (Tq[q] <= (1ll << 52) ? 3u : 2u));      // operand too large / near a border / above / below
+            atomicAdd(nv.stats + 8 + why, 1u); atomicAdd(nv.stats + 12, n_ok / 6);
+        }
+#endif
         __syncthreads();
         if (n_ok > 0) s = sstate[buf];
         BK_NZ_PH(5);
-        if (n_ok == total_ops) { i0 += n_it; continue; }
+        if (n_ok == total_ops) { a0 += n_it; pf_a0 = a0; continue; }
+        pf_a0 = 0xFFFFFFFFu;
         // the operation that ended the accepted prefix and the rest of its iteration, in real FP64
         st_stops++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
-        for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
-        if (tid == 0) snap[i0 + ib] = s;
-        i0 += ib + 1;
-        serial_left = ib < 24 ? 1u : 0u;               // (a round costs about as much as 25 serial iterations)
+        for (u32 q = qb; q < 6; q++) s = nz_add(s, xs[ib * 6 + q]);
+        if (tid == ib) snap[it] = s;
+        a0 += ib + 1;
+        force_serial = ib < BK_NZ_SERIAL ? 1u : 0u;    // (the look-ahead saw a long run and was wrong: a few iterations like the reference)
+        __syncthreads();                               // (xs is rewritten by the next pass)
         BK_NZ_PH(6);
     }
     BK_NZ_PH_STORE;
@@ -651,6 +805,9 @@ __global__ void __launch_bounds__(BK_NZ_SEQ_THREADS) k_noise_seq(NoiseView nv) {
     double* mt = reinterpret_cast<double*>(nz_sm);
     if (blockIdx.x == 0) { nz_chain_block<false>(nv, s, mt); return; }
     if (blockIdx.x == 1) { nz_chain_block<true>(nv, s, mt); return; }
+#ifdef BK_NZ_NO_TABLES                              // developer builds: profile the chain blocks alone (results are wrong)
+    return;
+#endif
     // table chunks: warp w of this block owns chunk (blockIdx.x - 2) * 8 + w; its lanes stage the fractions the chunk
     // touches into shared memory, lane 0 walks them
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -732,7 +889,10 @@ __global__ void __launch_bounds__(256) k_noise_tau(NoiseView nv) {
     if (i >= s.iters || i < BK_NOISE_HALF) return;
     u32 cn0 = 0;                                                   // n after iteration i: positions [i-99, i]
     for (u32 x = 0; x < BK_NOISE_WINDOW; x++) cn0 += cnt[threadIdx.x + x];
-    const double s0 = nv.snap_s[s.ibase + i], s20 = nv.snap_s2[s.ibase + i];
+    // the sums after iteration i are the sums after the last ACTIVE iteration up to i (nz_chain_block), zero before the first
+    const u32 rk = nv.act_rank[s.ibase + i];
+    const u32 ia = rk ? nv.act_list[s.ibase + rk - 1] : 0u;
+    const double s0 = rk ? nv.snap_s[s.ibase + ia] : 0.0, s20 = rk ? nv.snap_s2[s.ibase + ia] : 0.0;
     const double* mxp = nv.snap_tab + (size_t)(s.ibase + i) * BK_NOISE_TABLE;
     double mx[BK_NOISE_TABLE];
 #pragma unroll

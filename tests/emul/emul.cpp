@@ -247,53 +247,58 @@ void emul_count_get(void* h, u64* kmers, u32* counts) {
 }  // extern "C"
 template <bool SQUARE, class LdM>
 static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
-    // the two-zone rounds of bk_noise.cuh: nz_chain_block, stepped in thread order (the block-wide scans of the device are
-    // replaced by sequential sums / compositions of the same primitives: both are associative)
+    // nz_chain_block of bk_noise.cuh, stepped in thread order (the block-wide scans of the device are replaced by
+    // sequential sums / compositions of the same primitives: both are associative).  snap holds the approximate window
+    // sums on entry (k_noise_fracs); the sums of the iterations that are not active are filled in at the end (the device
+    // reads them through act_rank / act_list in k_noise_tau).
+    std::vector<u32> list;
+    for (u32 i = 0; i < iters; i++) {
+        bool any = false;
+        for (u32 j = 0; j < 3; j++) any = any || M((i32)i, j) != 0.0 || M((i32)i - BK_NOISE_WINDOW, j) != 0.0;
+        if (any) list.push_back(i);
+    }
+    const u32 n_act = (u32)list.size();
+    auto X = [&](u32 a, u32 q) { return nz_operand<SQUARE>(M, (i32)list[a], q); };
     double s = 0.0;
-    u32 i0 = 0, serial_left = 0;
-    const u32 width = BK_NZ_ROUND;
-    while (i0 < iters) {
-        const u32 n_it = std::min<u32>(width, iters - i0);
+    u32 a0 = 0, force_serial = 0;
+    while (a0 < n_act) {
+        const u32 n_it = std::min<u32>(BK_NZ_ROUND, n_act - a0);
         const u64 sb = nz_b(s);
-        NzZ2 z;
-        if (sb == 0) {                                       // the zero skip of nz_chain_block
-            u32 first = n_it;
-            for (u32 t = 0; t < n_it && first == n_it; t++)
-                for (u32 q = 0; q < 6; q++) if (nz_operand<SQUARE>(M, (i32)(i0 + t), q) != 0.0) { first = t; break; }
-            for (u32 t = 0; t < first; t++) snap[i0 + t] = 0.0;
-            i0 += first;
-            if (first < n_it) {
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)i0, q));
-                snap[i0] = s;
-                i0++; stats[4]++;
-            }
-            continue;
+        const u32 ef = (u32)(sb >> 52);
+        const bool capable = ef >= 66u && ef < 0x7FCu;
+        const u32 start = nz_hint_start(capable ? ef : 1023u);
+        u32 runkey = start, F = start, run = 0;
+        for (u32 t = 0; t < n_it; t++) {
+            runkey = nz_hint_merge(runkey, nz_hint_key(nz_b(snap[list[a0 + t]])));
+            if (nz_hint_fits(runkey)) { F = nz_hint_merge(F, runkey); run++; }
         }
-        if (!nz2_zones(sb, &z) || serial_left) {
-            const u32 n_ser = std::min<u32>(iters - i0, BK_NZ_SERIAL);
-            for (u32 it = 0; it < n_ser; it++) {
-                for (u32 q = 0; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + it), q));
-                snap[i0 + it] = s;
+        if (!capable || force_serial || run < BK_NZ_MIN_RUN) {
+            const u32 n_ser = std::min<u32>(n_it, force_serial ? (u32)BK_NZ_SERIAL : (capable ? std::max<u32>(run + 1u, BK_NZ_SERIAL_RUN) : (u32)BK_NZ_SERIAL_RUN));
+            for (u32 t = 0; t < n_ser; t++) {
+                for (u32 q = 0; q < 6; q++) s = nz_add(s, X(a0 + t, q));
+                snap[list[a0 + t]] = s;
             }
-            i0 += n_ser; stats[4] += n_ser; serial_left = 0;
+            a0 += n_ser; stats[4] += n_ser; force_serial = 0;
             continue;
         }
         stats[2]++;
+        NzZ2 z;
+        {
+            const u32 el = nz_hint_el(F);
+            if (el + 2 < ef || el > ef) { stats[0] = 0xBAD; return; }        // the zones must hold the start
+            nz2_zones_at(el, &z);
+        }
         const i64 S0 = nz2_start(z, sb);
-        const u32 n_thr = (n_it + BK_NZ_IPT - 1) / BK_NZ_IPT;    // threads with an iteration (thread t: iterations t * IPT ..)
+        const u32 n_thr = n_it;                              // one active iteration per thread
         std::vector<NzThread> T(n_thr);
         std::vector<i64> Pex(n_thr);
-        i64 run = 0;
+        i64 runA = 0;
         for (u32 t = 0; t < n_thr; t++) {                    // scan 1 + the thread maps
             i64 A[BK_NZ_OPT]; u32 fc[BK_NZ_OPT]; bool ok[BK_NZ_OPT]; i64 PA = 0;
-            for (u32 q = 0; q < BK_NZ_OPT; q++) {
-                const u32 it = t * BK_NZ_IPT + q / 6;
-                const double x = it < n_it ? nz_operand<SQUARE>(M, (i32)(i0 + it), q % 6) : 0.0;
-                ok[q] = nz2_split(z, x, &A[q], &fc[q]); PA += A[q];
-            }
-            Pex[t] = run;
-            nz2_thread(A, fc, ok, S0 + run, t * BK_NZ_OPT, &T[t]);
-            run += PA;
+            for (u32 q = 0; q < BK_NZ_OPT; q++) { ok[q] = nz2_split(z, X(a0 + t, q), &A[q], &fc[q]); PA += A[q]; }
+            Pex[t] = runA;
+            nz2_thread(A, fc, ok, S0 + runA, t * BK_NZ_OPT, &T[t]);
+            runA += PA;
         }
         for (u32 g = 0; g < 3; g++) for (u32 fcc = 0; fcc < 4; fcc++) for (u32 v = 0; v < 8; v++)      // the table against its formula
             if ((i32)(signed char)(unsigned char)(nz2_round_table(g, fcc) >> (8 * v)) != nz2_round_slow(g, fcc, v)) { stats[0] = 0xBAD; return; }
@@ -314,21 +319,27 @@ static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
             cs = nzvec_get(T[t].next, cs);
             composed = nzvec_compose(composed, T[t].next);
         }
-        for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[i0 + t] = nz2_value(z, Tq[t * 6 + 5]);
+        for (u32 t = 0; t < n_it; t++) if (t * 6 + 5 < n_ok) snap[list[a0 + t]] = nz2_value(z, Tq[t * 6 + 5]);
         if (n_ok > 0) s = nz2_value(z, Tq[n_ok - 1]);
-        if (n_ok == n_it * 6) { i0 += n_it; continue; }
+        if (n_ok == n_it * 6) { a0 += n_it; continue; }
         stats[3]++;
         const u32 ib = n_ok / 6, qb = n_ok - ib * 6;
         if (getenv("EMUL_DEBUG")) {
-            const double x = nz_operand<SQUARE>(M, (i32)(i0 + ib), qb);
+            const double x = X(a0 + ib, qb);
             i64 A; u32 fc; const bool ok = nz2_split(z, x, &A, &fc);
-            fprintf(stderr, "[stop] sq=%d i=%u op=%u accepted=%u s=%.6g x=%.6g ok=%d el=%u T=%lld (2^53=%lld) threadbad=%u\n", (int)SQUARE, i0 + ib, qb, n_ok, s, x, (int)ok, z.el,
+            fprintf(stderr, "[stop] sq=%d i=%u op=%u accepted=%u s=%.6g x=%.6g ok=%d el=%u T=%lld (2^53=%lld) threadbad=%u\n", (int)SQUARE, list[a0 + ib], qb, n_ok, s, x, (int)ok, z.el,
                     (long long)Tq[n_ok], (long long)(1ll << 53), T[ib].bad);
         }
-        for (u32 q = qb; q < 6; q++) s = nz_add(s, nz_operand<SQUARE>(M, (i32)(i0 + ib), q));
-        snap[i0 + ib] = s;
-        i0 += ib + 1;
-        serial_left = ib < 24 ? 1 : 0;
+        for (u32 q = qb; q < 6; q++) s = nz_add(s, X(a0 + ib, q));
+        snap[list[a0 + ib]] = s;
+        a0 += ib + 1;
+        force_serial = ib < BK_NZ_SERIAL ? 1 : 0;
+    }
+    double last = 0.0;
+    u32 a = 0;
+    for (u32 i = 0; i < iters; i++) {
+        if (a < n_act && list[a] == i) { last = snap[i]; a++; }
+        else snap[i] = last;
     }
 }
 
@@ -342,6 +353,12 @@ int emul_noise(const u32* fwd, const u32* rev, u32 len, double* out_max, u32* st
     const double* m0 = maf.data() + (size_t)BK_NZ_PAD_LO * 3;
     auto M = [m0](i32 p, u32 j) { return m0[(long long)p * 3 + j]; };
     std::vector<double> snap_s(iters), snap_s2(iters), snap_tab((size_t)iters * BK_NOISE_TABLE);
+    for (u32 i = 0; i < iters; i++) {                          // k_noise_fracs: approximate window sums where the exact ones will go
+        double a = 0.0, b = 0.0;
+        for (i32 p2 = (i32)i - (BK_NOISE_WINDOW - 1); p2 <= (i32)i; p2++)
+            for (u32 j = 0; j < 3; j++) { const double v = M(p2, j); a += v; b += v * v; }
+        snap_s[i] = a; snap_s2[i] = b;
+    }
     emul_chain<false>(M, iters, snap_s.data(), stats5);
     emul_chain<true>(M, iters, snap_s2.data(), stats5);
     const u32 n_chunks = (iters + BK_NZ_CHUNK - 1) / BK_NZ_CHUNK;
