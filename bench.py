@@ -74,29 +74,82 @@ def committed_traffic(kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per box
-    (rank 0, every GPU of the job) so that the ranks' host threads are not disturbed by eight pollers."""
+    """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per box (rank 0, every
+    GPU of the job).  The numbers come from NVML inside this process (what nvidia-smi prints, without forking a poller
+    that asks every GPU for its power draw every 50 ms — at eight GPUs that poller held the driver long enough to show in
+    the ranks' launch rates); nvidia-smi is the fallback when the NVML module is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_indices):
-        self.gpus, self.proc, self.lines = gpu_indices, None, []
+    def __init__(self, gpu_indices, period_s=0.05):
+        self.gpus, self.proc, self.lines, self.period = list(gpu_indices), None, [], period_s
+        self.sm, self.mx, self.reasons, self.nv, self.thread, self.stop_flag = [], [], set(), None, None, False
+        self.source = None
+
+    def _physical(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            try:
+                return [int(ids[g]) for g in self.gpus]
+            except (ValueError, IndexError):
+                return None                      # UUIDs: let nvidia-smi sort it out
+        return self.gpus
 
     def start(self):
+        try:
+            if os.environ.get("BK_BENCH_SAMPLER") == "smi":      # developer runs: the forked poller, for comparison
+                raise RuntimeError("forced")
+            import pynvml
+            phys = self._physical()
+            if phys is None:
+                raise RuntimeError("device ids")
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(g) for g in phys]
+            self.get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.mx = [float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)) for h in self.handles]
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(g) for g in self.gpus), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            for h in self.handles:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(self.get_reasons(h))
+                    for bit, name in self.REASONS:
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(self.period)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "gpus": list(self.gpus), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -117,7 +170,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "gpus": list(self.gpus)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": list(self.gpus), "source": "nvidia-smi"}
 
 
 def make_workload(sample_index, depth):
@@ -524,17 +577,32 @@ def main():
         for k_, v_ in ctx.stage_times().items():
             alone[k_] = alone.get(k_, 0.0) + v_ / n_alone
     latency_ms = (time.perf_counter() - t0) * 1e3 / n_alone
+    # the timed region runs without the per-stage events (bk_stage_timing: instrumentation, ~20 driver calls per sample on
+    # the one host thread a context has); the stage times of samples in flight come from the un-timed leg behind it
+    for c in ctxs:
+        c.set_stage_timing(False)
+    run_steps(S, step_device)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import resource
+    ru0 = resource.getrusage(resource.RUSAGE_SELF)
     e0.record()
-    run_steps(args.steps, step_device, collect=True)
+    run_steps(args.steps, step_device)
     torch.cuda.synchronize()
     e1.record()
+    ru1 = resource.getrusage(resource.RUSAGE_SELF)
+    host_cpu_ms = {"user": (ru1.ru_utime - ru0.ru_utime) * 1e3 / args.steps, "sys": (ru1.ru_stime - ru0.ru_stime) * 1e3 / args.steps,
+                   "note": "CPU time of this process (all threads) per step of the timed region"}
     barrier()
     res = last["res"]
     t_end = time.perf_counter() + 0.5
     while time.perf_counter() < t_end:                     # same work, same samples in flight, not timed
         run_steps(max(S, args.steps // 4), step_device)
+    torch.cuda.synchronize()
+    for c in ctxs:
+        c.set_stage_timing(True)
+    n_collect = max(S, args.steps // 4)
+    run_steps(n_collect, step_device, collect=True)
     torch.cuda.synchronize()
     clk = clocks.stop() if clocks else None
     if clk:
@@ -602,7 +670,7 @@ def main():
                 "note": "k_scan streams the reads (the HBM-bound stage of SURVEY.md 8d: 1 B/base); the other stages are "
                         "latency-bound random access (leftover / bins / map) or a sequential FP64 chain (noise) whose "
                         "algorithmic bytes are ~3 % of the path's: the whole path against its bytes is roofline_path"}
-    stages = {k_: (v_ / args.steps) for k_, v_ in stage_acc.items()}
+    stages = {k_: (v_ / n_collect) for k_, v_ in stage_acc.items()}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the SAME sample --------------
     cpu = None
@@ -651,7 +719,8 @@ def main():
             "e2e_ascii": None if e2e_value is None else {"value": e2e_ascii_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                                          "input": "ASCII bases + u32 read offsets in pinned host memory (bk_reads_push): bound by the H2D rate, see h2d_ceiling"},
             "h2d_ceiling": h2d_probe,
-            "gpu_launches": int(stage_acc["launches"]),
+            "gpu_launches": int(round(stage_acc["launches"] / n_collect * args.steps)),      # kernels of the timed region (the same count every sample)
+            "host_cpu_ms_per_step": host_cpu_ms,
             "roofline": roofline,
             "roofline_path": {"alg_bytes_per_step": 1.03 * n_bases, "achieved_gbs": 1.03 * n_bases * world / (ms_step * 1e-3) / 1e9,
                               "frac_of_hbm": 1.03 * n_bases / (ms_step * 1e-3) / 1e9 / peak,

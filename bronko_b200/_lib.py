@@ -100,6 +100,7 @@ SIGNATURES = {
     "bk_sample_noise_max": (C.c_int, [P, P, u64]),
     "bk_kmer_counts_get": (C.c_int, [P, C.c_int, P, P, P]),
     "bk_stage_times_get": (C.c_int, [P, C.POINTER(StageTimes)]),
+    "bk_stage_timing": (C.c_int, [P, C.c_int]),
     "bk_write_vcf": (C.c_int, [P, C.c_char_p, C.c_char_p]),
     "bk_write_pileup": (C.c_int, [P, C.c_char_p]),
     "bk_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bk_host.h"
+#define BK_VARS_EAGER 1024
 #include "bk_shard.cuh"
 #include "bk_fastq.cuh"
 
@@ -155,6 +156,25 @@ struct bk_ctx {
     FileState file[2];
     DevBuf<Counters> d_ctr;
     Counters* h_ctr = nullptr;              // pinned
+    // Everything a sample copies back sits in PINNED memory: a cudaMemcpyAsync into pageable memory makes the calling
+    // thread wait for the stream inside the driver, spinning — a core per context for as long as its sample runs.
+    u32* h_gstats = nullptr; size_t h_gstats_cap = 0;            // 2 files x genomes x 4
+    bk_variant* h_vars = nullptr;                                // the first BK_VARS_EAGER variants travel with the counters
+    u32* h_sizes = nullptr; size_t h_sizes_cap = 0;              // read-sharded sample: the all-gathered pair counts
+    cudaEvent_t ev_wait = nullptr;                               // host_wait
+    int pinned_u32(u32** p, size_t* cap, size_t n) {
+        if (n <= *cap) return BK_OK;
+        if (*p) cudaFreeHost(*p);
+        *p = nullptr; *cap = 0;
+        if (cudaMallocHost((void**)p, n * sizeof(u32)) != cudaSuccess) return BK_ERR_NOMEM;
+        *cap = n;
+        return BK_OK;
+    }
+    // the host thread sleeps until the stream has drained (BK_SPIN=1: spins, ~50 us sooner)
+    cudaError_t host_wait(cudaStream_t st) {
+        cudaError_t e = cudaEventRecord(ev_wait, st);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_wait);
+    }
     u64* h_stats = nullptr;                 // pinned: globally reduced KMC numbers of a sharded sample
     DevBuf<u32> d_pile;                     // 4 arrays x max_genome_rows x 4
     DevBuf<u32> d_pile_all;                 // one such block per genome (databases of at most four genomes: one-pass map)
@@ -199,7 +219,9 @@ struct bk_ctx {
         err = buf;
         return code;
     }
+    bool stage_timing = true;               // bk_stage_timing
     int span_begin(int stage, cudaStream_t st) {
+        if (!stage_timing) return -1;
         if (spans_used == spans.size()) {
             Span s; s.stage = stage; s.st = st;
             if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return -1;
@@ -267,6 +289,8 @@ int bk_create(bk_ctx** out, int device) {
     bool ok = mk(&ctx->s_count[0], prio_least) && mk(&ctx->copy_stream, prio_least) &&
               cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->h_ctr, sizeof(Counters)) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->h_vars, BK_VARS_EAGER * sizeof(bk_variant)) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_wait, (ctx->spin_wait ? 0u : (unsigned)cudaEventBlockingSync) | cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->h_stats, 8 * sizeof(u64)) == cudaSuccess &&
               cudaEventCreate(&ctx->ev_begin) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_end, ctx->spin_wait ? cudaEventDefault : cudaEventBlockingSync) == cudaSuccess;
@@ -335,6 +359,10 @@ void bk_destroy(bk_ctx* ctx) {
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_vars) cudaFreeHost(ctx->h_vars);
+    if (ctx->h_gstats) cudaFreeHost(ctx->h_gstats);
+    if (ctx->h_sizes) cudaFreeHost(ctx->h_sizes);
+    if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     if (ctx->h_stats) cudaFreeHost(ctx->h_stats);
     for (cudaStream_t st : ctx->owned_streams) cudaStreamDestroy(st);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
@@ -1137,11 +1165,12 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     BK_CUDA(cudaGetLastError());
 
     BK_CUDA(cudaMemcpyAsync(ctx->h_ctr, dc, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    std::vector<u32> hg[2];
-    for (int f = 0; f < n_files; f++) {
-        hg[f].resize((size_t)d.n_genomes * 4);
-        BK_CUDA(cudaMemcpyAsync(hg[f].data(), ctx->file[f].gstats.p, hg[f].size() * 4, cudaMemcpyDeviceToHost, st));
-    }
+    if (ctx->pinned_u32(&ctx->h_gstats, &ctx->h_gstats_cap, (size_t)d.n_genomes * 8)) return ctx->fail(BK_ERR_NOMEM, "out of pinned host memory");
+    const u32* hg[2] = {ctx->h_gstats, ctx->h_gstats + (size_t)d.n_genomes * 4};
+    for (int f = 0; f < n_files; f++)
+        BK_CUDA(cudaMemcpyAsync(ctx->h_gstats + (size_t)f * d.n_genomes * 4, ctx->file[f].gstats.p, (size_t)d.n_genomes * 16, cudaMemcpyDeviceToHost, st));
+    const size_t n_eager = std::min<size_t>(BK_VARS_EAGER, ctx->d_vars.cap);
+    BK_CUDA(cudaMemcpyAsync(ctx->h_vars, ctx->d_vars.p, n_eager * sizeof(bk_variant), cudaMemcpyDeviceToHost, st));   // (the variants of nearly every sample: no second round trip)
     if (ctx->shard) {                                    // the globally reduced KMC numbers of both files (bk_shard.cuh: k_shard_pack)
         const u32 stride = 4 + d.n_genomes * 4;
         BK_CUDA(cudaMemcpyAsync(ctx->h_stats, ctx->d_shard_stats.p, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -1195,8 +1224,16 @@ static int stage_score(bk_ctx* ctx, bk_sample_result* out, cudaStream_t st) {
     r.num_unmapped_kmers = uc - pv;                                             // src/call.rs:242, 336 (usize arithmetic)
     ctx->variants.resize(c.n_var);
     if (c.n_var) {
-        BK_CUDA(cudaMemcpyAsync(ctx->variants.data(), ctx->d_vars.p, (size_t)c.n_var * sizeof(bk_variant), cudaMemcpyDeviceToHost, st));
-        BK_CUDA(cudaStreamSynchronize(st));
+        memcpy(ctx->variants.data(), ctx->h_vars, std::min<size_t>(c.n_var, n_eager) * sizeof(bk_variant));
+        if (c.n_var > n_eager) {                         // (thousands of variants: the rest, through a pinned bounce buffer)
+            bk_variant* more = nullptr;
+            if (cudaMallocHost((void**)&more, (size_t)(c.n_var - n_eager) * sizeof(bk_variant)) != cudaSuccess) return ctx->fail(BK_ERR_NOMEM, "out of pinned host memory");
+            cudaError_t e = cudaMemcpyAsync(more, ctx->d_vars.p + n_eager, (size_t)(c.n_var - n_eager) * sizeof(bk_variant), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = ctx->host_wait(st);
+            if (e == cudaSuccess) memcpy(ctx->variants.data() + n_eager, more, (size_t)(c.n_var - n_eager) * sizeof(bk_variant));
+            cudaFreeHost(more);
+            BK_CUDA(e);
+        }
         std::sort(ctx->variants.begin(), ctx->variants.end(), [](const bk_variant& a, const bk_variant& b) {
             if (a.seq != b.seq) return a.seq < b.seq;
             if (a.pos != b.pos) return a.pos < b.pos;
@@ -1260,6 +1297,12 @@ int bk_sample_finish(bk_ctx* ctx, bk_sample_result* out) {
 
 #include "bk_shard.inc"
 #include "bk_fastq.inc"
+
+int bk_stage_timing(bk_ctx* ctx, int on) {
+    if (!ctx) return BK_ERR_ARG;
+    ctx->stage_timing = on != 0;
+    return BK_OK;
+}
 
 int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out) {
     if (!ctx || !out) return BK_ERR_ARG;

@@ -226,6 +226,10 @@ int bk_sample_noise_max(bk_ctx* ctx, double* out, uint64_t cap_rows);        /* 
  * Pass NULL pointers to query the count. */
 int bk_kmer_counts_get(bk_ctx* ctx, int file_slot, uint64_t* kmers, uint32_t* counts, uint64_t* n);
 int bk_stage_times_get(bk_ctx* ctx, bk_stage_times* out);
+/* Per-stage CUDA events on or off (on when a context is created).  Off: a sample records only its begin / end events —
+ * ~20 fewer driver calls per sample on the host thread, which is what a GPU that is fed by several contexts of one
+ * process runs out of first; bk_stage_times then holds total_ms and the launch counts only.  No effect on results. */
+int bk_stage_timing(bk_ctx* ctx, int on);
 
 /* ---- writers: src/call.rs:648-774 (formats in SURVEY.md Appendix D) ------------------------ */
 int bk_write_vcf(bk_ctx* ctx, const char* reads_path, const char* out_path);

@@ -29,6 +29,7 @@ class FakeBronko:
     def push_ptr(self, *a): pass
     def push_packed_ptr(self, *a): pass
     def close(self): pass
+    def set_stage_timing(self, on): pass
 
     def finish(self):
         self.n += 1
