@@ -73,6 +73,9 @@ def committed_traffic(kernel):
     return None, None
 
 
+REF_BUDGET_S = 100.0        # --impl reference: warm-up + K steps of the CPU port stay inside this (plus ~20 s for its FASTQ leg)
+
+
 class ClockSampler:
     """SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE sampler per box (rank 0, every
     GPU of the job).  The numbers come from NVML inside this process (what nvidia-smi prints, without forking a poller
@@ -270,13 +273,27 @@ def run_reference(args, rank, world):
     from bronko_b200 import sim
     cores = os.cpu_count() or 1
     files = make_workload(0, args.depth)
-    n_bases = sum(len(b) for b, _ in files)
+    full_bases = sum(len(b) for b, _ in files)
     oi = O.Index.build(21, [sim.genome_path(n) for n in sim.SARS4])
+    # A step is a BOUNDED sample of the workload: the whole C2 sample takes the port ~3 s, so with the driver's K the
+    # steps take the first n read pairs of it, n sized so that warm-up + K steps stay inside REF_BUDGET_S (the whole
+    # sample when it fits).  Bases per second barely depend on n: the port's time is counting, linear in the reads.
+    t0 = time.perf_counter()
+    oracle_step(oi, files, cores)                                     # untimed: page-in + the rate of the full sample
+    t_full = time.perf_counter() - t0
+    frac = min(1.0, max(0.02, REF_BUDGET_S / (t_full * max(1, args.steps + min(args.warmup, 1)))))
+    step_files = files
+    if frac < 1.0:
+        step_files = []
+        for b, o in files:
+            n = max(1, int((len(o) - 1) * frac))
+            step_files.append((b[:int(o[n])], o[:n + 1]))
+    n_bases = sum(len(b) for b, _ in step_files)
     for _ in range(max(0, min(args.warmup, 1))):
-        oracle_step(oi, files, cores)
+        oracle_step(oi, step_files, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(oi, files, cores)
+        oracle_step(oi, step_files, cores)
     dt = time.perf_counter() - t0
     v = n_bases * args.steps / dt
     fq = None
@@ -289,7 +306,8 @@ def run_reference(args, rank, world):
                 cpu_fastq_sample(oi, paths, cores, os.path.join(td, "ref.vcf"))
             fq = {"samples_per_min": 60.0 * reps / (time.perf_counter() - t1), "input": "plain single-member .fastq.gz, R1 + R2",
                   "threads": cores, "samples": reps}
-    sample = "SARS-CoV-2 %dx 150bp PE (%d bases/step), oracle port, %d threads" % (args.depth, n_bases, cores)
+    sample = "SARS-CoV-2 %dx 150bp PE: the first %.0f %% of the read pairs of the C2 sample per step (%d of %d bases), oracle port, %d threads" % (
+        args.depth, 100.0 * n_bases / full_bases, n_bases, full_bases, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

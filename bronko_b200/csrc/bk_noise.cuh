@@ -47,8 +47,10 @@ typedef long long i64;
 #endif
 #define BK_NZ_WARPS (BK_NZ_SEQ_THREADS / 32)
 #define BK_NZ_ROUND (BK_NZ_SEQ_THREADS * BK_NZ_IPT)   // iterations per chain round
+#ifndef BK_NZ_MIN_RUN
 #define BK_NZ_MIN_RUN 64         // a run of iterations that fits three zones but is shorter than this is walked in real FP64 (a round costs ~100 such iterations)
 #define BK_NZ_SERIAL_RUN 64      // ... for at least this many iterations
+#endif
 #ifndef BK_NZ_SERIAL
 #define BK_NZ_SERIAL 8           // iterations executed serially after a round that accepted next to nothing although the look-ahead saw a long run
 #endif

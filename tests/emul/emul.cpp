@@ -344,6 +344,22 @@ static void emul_chain(const LdM& M, u32 iters, double* snap, u32* stats) {
 }
 
 extern "C" {
+// the look-ahead of nz_chain_block on its own: s = the sum a pass starts from, ahead[n] = approximate window sums of the
+// iterations ahead → out[0] = iterations that fit three zones, out[1] = exponent field of the lowest zone (0: serial)
+void emul_hint(double s, const double* ahead, u32 n, u32* out) {
+    const u64 sb = nz_b(s);
+    const u32 ef = (u32)(sb >> 52);
+    const bool capable = ef >= 66u && ef < 0x7FCu;
+    const u32 start = nz_hint_start(capable ? ef : 1023u);
+    u32 runkey = start, F = start, run = 0;
+    for (u32 t = 0; t < n; t++) {
+        runkey = nz_hint_merge(runkey, nz_hint_key(nz_b(ahead[t])));
+        if (nz_hint_fits(runkey)) { F = nz_hint_merge(F, runkey); run++; }
+    }
+    out[0] = run;
+    out[1] = capable ? nz_hint_el(F) : 0u;
+}
+
 int emul_noise(const u32* fwd, const u32* rev, u32 len, double* out_max, u32* stats5) {
     for (int i = 0; i < 5; i++) stats5[i] = 0;
     if (len < BK_NOISE_WINDOW) { for (u32 i = 0; i < len; i++) out_max[i] = 0.0; return 1; }

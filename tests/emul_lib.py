@@ -24,7 +24,7 @@ def lib():
             "emul_revcomp": (u64, [u64, C.c_int]), "emul_tau_table": (None, [P]),
             "emul_clean_sample_id": (u64, [C.c_char_p, C.c_char_p, u64]),
             "emul_count": (u64, [P, P, P, u64, u32, u32, u32, u32, P, P]), "emul_count_get": (None, [P, P, P]),
-            "emul_noise": (C.c_int, [P, P, u32, P, P]), "emul_group_check": (u64, [P, P, u64, u32, u32]),
+            "emul_noise": (C.c_int, [P, P, u32, P, P]), "emul_hint": (None, [C.c_double, P, u32, P]), "emul_group_check": (u64, [P, P, u64, u32, u32]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -95,3 +95,11 @@ def noise(fwd, rev):
     out, st = np.zeros(n, dtype=np.float64), np.zeros(5, dtype=np.uint32)
     lib().emul_noise(ptr(fwd), ptr(rev), n, ptr(out), ptr(st))
     return out, tuple(int(x) for x in st)
+
+
+def hint(s, ahead):
+    """(iterations ahead that fit three zones, exponent field of the lowest zone) — the look-ahead of nz_chain_block."""
+    a = np.ascontiguousarray(ahead, dtype=np.float64)
+    out = np.zeros(2, np.uint32)
+    lib().emul_hint(float(s), ptr(a), len(a), ptr(out))
+    return int(out[0]), int(out[1])

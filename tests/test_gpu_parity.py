@@ -89,6 +89,30 @@ def test_sars_deeper_sample(ctx_sars):
     assert g.num_minor_variants > 0 and g.num_major_variants > 0
 
 
+@pytest.mark.parametrize("depth", [400, 1500, 2000, 2500, 5000])
+def test_sars_depth_ladder_noise_regimes(ctx_sars, depth):
+    """The regimes of the noise chains (bk_noise.cuh: nz_chain_block): 90 active iterations of 29,953 at 400x (all walked in
+    real FP64), a few thousand at 1,500-2,500x (serial runs and rounds mixed, the look-ahead choosing), two thirds at 5,000x
+    (mostly rounds).  Noise.max and everything behind it bit for bit."""
+    c, oi = ctx_sars
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[0]), depth, sim.SEED0 + depth)
+    run_both(c, oi, [(r1, o1), (r2, o2)])
+
+
+def test_stage_timing_off_changes_nothing(ctx_sars):
+    c, oi = ctx_sars
+    r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[1]), 300, sim.SEED0 + 31)
+    c.set_stage_timing(False)
+    try:
+        g, o = run_both(c, oi, [(r1, o1), (r2, o2)])
+        t = c.stage_times()
+        assert t["scan_ms"] == 0 and t["score_ms"] == 0 and t["total_ms"] > 0 and t["launches"] > 0
+    finally:
+        c.set_stage_timing(True)
+    c.call_sample([(r1, o1), (r2, o2)])
+    assert c.stage_times()["scan_ms"] > 0
+
+
 def test_vcf_and_pileup_text_identical(ctx_sars, tmp_path):
     c, oi = ctx_sars
     r1, o1, r2, o2, _ = sim.simulate_pairs(sim.load_genome(sim.SARS4[2]), 500, sim.SEED0 + 11)

@@ -71,3 +71,22 @@ def test_simulated_sample():
     p = s.pileup()
     got, _ = emul_lib.noise(np.asarray(p[0]), np.asarray(p[1]))
     assert np.array_equal(got, np.asarray(s.noise_max()))
+
+
+def test_look_ahead_places_the_zones():
+    """nz_hint_*: the lowest zone holds the start, covers the longest run ahead, and a spare zone goes below the run."""
+    ef = lambda x: int(np.float64(x).view(np.uint64) >> np.uint64(52))
+    assert emul_lib.hint(0.3, [0.3] * 200) == (200, ef(0.3) - 1)                       # one binade: room on both sides
+    assert emul_lib.hint(0.3, [0.3, 0.2, 0.1, 0.07]) == (4, ef(0.07))                  # three binades down: the lowest one is zone 0
+    assert emul_lib.hint(0.3, [0.3, 0.2, 0.1, 0.07, 0.03, 0.3]) == (4, ef(0.07))       # a fourth does not fit: the run ends before it
+    assert emul_lib.hint(0.3, [0.6, 1.1]) == (2, ef(0.3))                              # upwards: the start is the lowest zone
+    assert emul_lib.hint(0.3, [0.6, 0.3, 0.6]) == (3, ef(0.3) - 1)                     # two binades: the spare one below
+    run, el = emul_lib.hint(0.3, [0.3, 0.0, 0.3])                                      # an empty window ends the run
+    assert run == 1 and el == ef(0.3) - 1
+    run, el = emul_lib.hint(0.3, [0.25 * (1 + 1e-12)] * 5)                             # next to a power of two: both binades count
+    assert run == 5 and el == ef(0.2) - 1                                              # (0.125..0.25 and 0.25..0.5 → spare below)
+    assert emul_lib.hint(0.0, [0.3] * 5)[1] == 0 and emul_lib.hint(-1e-18, [0.3] * 5)[1] == 0    # nothing to scale by: serial
+    for s0 in (0.3, 0.26, 0.49):                                                       # the zones always hold the start
+        for ahead in ([0.9], [0.07], [0.13, 0.6], [1e-9], [3.0]):
+            el = emul_lib.hint(s0, ahead)[1]
+            assert ef(s0) - 2 <= el <= ef(s0)

@@ -1,4 +1,5 @@
-B="--no-cpu-baseline --no-e2e --no-fastq --no-sharded"
-timeout 250 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_r02.csv python bench.py $B --steps 4 --warmup 3 --in-flight 1 > gpurun_out/bench_under_ncu_r02.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on --launch-skip 164 -c 41 -o gpurun_out/r02_full -f python bench.py $B --steps 2 --warmup 3 --in-flight 1 > gpurun_out/ncu_r02_full.log 2>&1
-tail -2 gpurun_out/ncu_r02_full.log | cut -c1-200; ls -la gpurun_out/r02_full.ncu-rep
+timeout 60 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1 || exit 1
+S=$(date +%s); timeout 900 python -m pytest tests -x -q -m gpu --timeout 300 2>&1 | tail -4; echo "pytest wall $(( $(date +%s) - S ))s"
+S=$(date +%s); timeout 600 python bench.py > gpurun_out/bench_r02_n1.json 2> gpurun_out/bench_r02_n1.err; echo "bench rc=$? wall $(( $(date +%s) - S ))s"
+S=$(date +%s); timeout 300 python bench.py --impl reference > gpurun_out/bench_r02_ref.json 2> gpurun_out/bench_r02_ref.err; echo "ref rc=$? wall $(( $(date +%s) - S ))s"
+cut -c1-250 gpurun_out/bench_r02_n1.json; cut -c1-400 gpurun_out/bench_r02_ref.json
