@@ -584,9 +584,9 @@ def main():
     torch.cuda.synchronize()
     # clocks / throttle reasons: sampled from here, through the device-timed region, to the end of an un-timed leg of the
     # same load behind it (the timed region alone, ~0.1 s, is shorter than nvidia-smi's start-up)
-    clocks = ClockSampler(list(range(world))) if rank == 0 else None
-    if clocks:
-        clocks.start()
+    # every rank watches its own GPU through NVML (two light queries per 50 ms inside the process); rank 0 merges
+    clocks = ClockSampler([local_rank])
+    clocks.start()
     alone = {}
     n_alone = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
@@ -622,9 +622,19 @@ def main():
     n_collect = max(S, args.steps // 4)
     run_steps(n_collect, step_device, collect=True)
     torch.cuda.synchronize()
-    clk = clocks.stop() if clocks else None
-    if clk:
-        clk["window"] = "single-sample latency leg + device-timed region + 0.5 s of the same load behind it; one sampler (rank 0) for every GPU of the job"
+    clk = clocks.stop()
+    if dist is not None:                                   # lowest per-GPU median, highest maximum, any reason seen anywhere
+        names = [n for _, n in ClockSampler.REASONS]
+        t = torch.tensor([-(clk.get("sm_mhz") or 0.0), clk.get("sm_max_mhz") or 0.0] + [1.0 if n in clk.get("reasons", []) else 0.0 for n in names],
+                         dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cnt = torch.tensor([float(clk.get("samples") or 0)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        v = t.tolist()
+        clk = {"sm_mhz": -v[0] or None, "sm_max_mhz": v[1] or None, "reasons": [n for n, f in zip(names, v[2:]) if f > 0] + [r for r in clk.get("reasons", []) if r not in names],
+               "samples": int(cnt.item()), "gpus": list(range(world)), "source": clk.get("source"),
+               "merge": "sm_mhz = lowest per-GPU median under load, sm_max_mhz = highest maximum, reasons = seen on any GPU"}
+    clk["window"] = "single-sample latency leg + device-timed region + 0.5 s of the same load behind it; every rank samples its own GPU"
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     total_bases = n_bases * world
