@@ -86,7 +86,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_indices, period_s=0.05):
+    def __init__(self, gpu_indices, period_s=0.1):
         self.gpus, self.proc, self.lines, self.period = list(gpu_indices), None, [], period_s
         self.sm, self.mx, self.reasons, self.nv, self.thread, self.stop_flag = [], [], set(), None, None, False
         self.source = None
@@ -130,17 +130,19 @@ class ClockSampler:
             self.proc = None
 
     def _poll(self):
-        nv = self.nv
+        nv, n = self.nv, 0
         while not self.stop_flag:
             for h in self.handles:
                 try:
                     self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                    r = int(self.get_reasons(h))
-                    for bit, name in self.REASONS:
-                        if r & bit:
-                            self.reasons.add(name)
+                    if n % 2 == 0:                           # (the reasons are sticky enough for every other poll)
+                        r = int(self.get_reasons(h))
+                        for bit, name in self.REASONS:
+                            if r & bit:
+                                self.reasons.add(name)
                 except Exception:
                     pass
+            n += 1
             time.sleep(self.period)
 
     def _pump(self):
