@@ -7,8 +7,9 @@
 // followed per iteration by the modified Thompson-tau rejection loop, which only READS that state.
 // Everything is split so that only genuinely sequential work stays sequential:
 //
-//   k_noise_fracs   one thread per position: sorted allele fractions (order-free).
-//   k_noise_seq     block 0 / 1 of every sequence: the s / s2 chains, replicated EXACTLY by integer prefix sums
+//   k_noise_fracs   one thread per position: sorted allele fractions (order-free); per iteration whether any of its
+//                   six operands is non-zero ("active") and the APPROXIMATE window sums (the chains' look-ahead).
+//   k_noise_seq     block 0 / 1 of every sequence: the s / s2 chains over the active iterations, replicated EXACTLY
 //                   (see "chains" below); blocks >= 2: the max table, one lane per chunk of 128 iterations,
 //                   started SPECULATIVELY 256 iterations early from the ten largest fractions of the window.
 //   k_noise_fix     verifies every speculative chunk against the true state at its boundary (the table after
@@ -17,13 +18,16 @@
 //                   had not converged yet, until it meets the speculative trajectory.
 //   k_noise_tau     one thread per output position: n (a count), then the Thompson-tau loop on the snapshots.
 //
-// chains.  While s stays inside one binade [2^e, 2^(e+1)) its ulp u = 2^(e-52) is fixed; with S = s/u (an integer
-// in [2^52, 2^53)) and X = x/u:  fl(s + x) = (S + RN(X))·u  as long as the result stays strictly inside the binade,
-// and RN(X) depends on S only through its parity (exact ties X = a + 1/2 round to even).  Every operation is thus
-// a map "parity → integer increment", those maps compose associatively, and 1536 consecutive operations (256
-// iterations, one per thread) are one block-wide scan.  The first operation whose result leaves the binade (or whose
-// operand is as large as the sum / subnormal) ends the accepted prefix and is executed in real FP64; stretches
-// where that keeps happening (very sparse coverage) are executed serially like the reference.
+// chains.  An iteration whose six operands are zero changes nothing and is skipped.  The others are taken 256 at a time:
+// a look-ahead over the approximate window sums decides whether the run of iterations ahead that fits three adjacent
+// binades is long enough for a ROUND, or whether it and what follows are added up in real FP64 like the reference
+// (sparse windows: the sum halves, doubles or cancels every few iterations).  A round works in units of the lowest
+// binade's ulp u: with S = s/u and X = x/u = A + f, fl(s + x) = (S + A + r)·u where the rounding r (|r| <= 2) depends on
+// S only through S mod 8 once the binade ("zone") of the operation is known — which the integer prefix sum of the A's
+// tells.  Every operation is thus a map "S mod 8 -> r", those maps compose associatively, and 1536 consecutive
+// operations (256 iterations, one per thread) are three block-wide scans.  The first operation that cannot be decided
+// or leaves the zones ends the accepted prefix and is executed in real FP64.  ("three-zone rounds" and "look-ahead"
+// below; nz_chain_block.)
 //
 // Written once for nvcc (kernels below) and g++ (tests/emul steps the same primitives on the CPU; tests only).
 #pragma once
@@ -39,11 +43,11 @@ typedef long long i64;
 #define BK_NZ_CHUNK 128          // iterations per speculative table chunk
 #define BK_NZ_WARM 256           // warm-up iterations in front of a chunk
 #ifndef BK_NZ_IPT
-#define BK_NZ_IPT 1              // iterations per thread and chain round
+#define BK_NZ_IPT 1              // iterations per thread and chain round (nz_chain_block is written for 1)
 #endif
 #define BK_NZ_OPT (6 * BK_NZ_IPT) // operations per thread and round
 #ifndef BK_NZ_SEQ_THREADS
-#define BK_NZ_SEQ_THREADS 256     // threads of a chain block (512: measured no faster — the round is bound by instruction issue, not latency)
+#define BK_NZ_SEQ_THREADS 256     // threads of a chain block = active iterations per pass (512: measured slower — a pass is dependent integer chains, and a stop throws more away)
 #endif
 #define BK_NZ_WARPS (BK_NZ_SEQ_THREADS / 32)
 #define BK_NZ_ROUND (BK_NZ_SEQ_THREADS * BK_NZ_IPT)   // iterations per chain round

@@ -8,7 +8,7 @@ for spec in "$@"; do
   v=${spec%%[:@]*}; abl=""; infl=4
   [[ $spec == *:* ]] && { abl=${spec#*:}; abl=${abl%%@*}; }
   [[ $spec == *@* ]] && infl=${spec##*@}
-  BK_ABLATE=$abl BRONKO_B200_LIB=$PWD/bronko_b200/csrc/variants/$v.so python bench.py --no-e2e --no-cpu-baseline --in-flight $infl --depth ${DEPTH:-10000} --steps ${STEPS:-80} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  BK_ABLATE=$abl BRONKO_B200_LIB=$PWD/bronko_b200/csrc/variants/$v.so python bench.py --no-e2e --no-cpu-baseline --no-fastq --no-sharded --in-flight $infl --depth ${DEPTH:-10000} --steps ${STEPS:-80} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" "$spec" <<'PY'
 import json, sys
 v = sys.argv[1]
