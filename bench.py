@@ -749,7 +749,8 @@ def main():
             "e2e_ascii": None if e2e_value is None else {"value": e2e_ascii_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                                          "input": "ASCII bases + u32 read offsets in pinned host memory (bk_reads_push): bound by the H2D rate, see h2d_ceiling"},
             "h2d_ceiling": h2d_probe,
-            "gpu_launches": int(round(stage_acc["launches"] / n_collect * args.steps)),      # kernels of the timed region (the same count every sample)
+            "gpu_launches": int(round(stage_acc["launches"] / n_collect * args.steps)) * world,   # kernels of the timed region, all ranks (the same count every sample and rank)
+            "gpu_launches_per_rank": int(round(stage_acc["launches"] / n_collect * args.steps)),
             "host_cpu_ms_per_step": host_cpu_ms,
             "roofline": roofline,
             "roofline_path": {"alg_bytes_per_step": 1.03 * n_bases, "achieved_gbs": 1.03 * n_bases * world / (ms_step * 1e-3) / 1e9,
