@@ -795,7 +795,7 @@ def fastq_legs(args, ctxs, files, oi):
                 r.write_vcf(paths[0], os.path.join(td, "%s_%d.vcf" % (kind, ci)))
                 return len(r.variants)
             nv = [one(0, 0)]                                           # warm-up (page cache, allocations)
-            per_ctx = 2
+            per_ctx = 8 if bgzf else 2                                 # (a BGZF sample takes ~10 ms, a plain-gzip one ~1.4 s of host inflate per context)
             n = per_ctx * len(ctxs)
 
             def worker(ci):                                            # one host thread per context (a context is not thread-safe)
