@@ -465,7 +465,7 @@ def main():
     ap.add_argument("--shard-chunks", type=int, default=40, help="read chunks of the C3 sample (rounded up to a multiple of the ranks)")
     ap.add_argument("--shard-steps", type=int, default=3)
     ap.add_argument("--shard-warmup", type=int, default=1)
-    ap.add_argument("--in-flight", type=int, default=4,
+    ap.add_argument("--in-flight", type=int, default=6,
                     help="samples in flight per GPU (one bk_ctx + streams each); 1 = strictly one sample at a time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
